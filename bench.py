@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/sec of the batched capture env (step + obs) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--layout tinyCapture] [--envs 65536]
+
+One "step" = one pass of the hot path over the whole batch: pm_step (rules of
+4 ordered sub-moves + four fp32 [8,H,W] observations per env, rewards, done,
+legal masks, shaping) followed by pm_reset on the envs that just finished, so
+episodes keep cycling.  Default workload = the configuration BASELINE.json's
+metric is quoted on: tinyCapture, 65,536 envs per GPU, uniform random actions
+(self-play, all four agents driven by the caller), length 300.  Envs shard per
+GPU with no data-path collective ("weak" scaling: per-GPU batch fixed).
+
+Printed JSON (rank 0, one line) follows the driver contract; see DESIGN.md §5.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes per agent-step = obs write 32*H*W + 1/4 of the per-env
+# state read+write, actions and small outputs.
+ALGO_BYTES_PER_AGENT_STEP = {"tinyCapture": 4529, "smallCapture": 4985, "bloxCapture": 12875}
+PY_REFERENCE_AGENT_STEPS_PER_CORE = {"tinyCapture": 1819, "smallCapture": 1554, "bloxCapture": 1031}
+
+
+def layout_path(name):
+    return os.path.join(ROOT, "pacman_marl_2025_b200", "layouts", name + ".lay")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed regions run."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_rate(layout, n_envs, steps, warmup, length, nthreads=0):
+    """agent-steps/s of the CPU port (oracle/pm_oracle.c, OpenMP over envs) incl. observations."""
+    import numpy as np
+    from oracle import oracle
+    rows = [ln.strip() for ln in open(layout_path(layout))]
+    env = oracle.OracleBatch(rows, n_envs, length=length)
+    env.reset(with_obs=False)
+    rng = np.random.default_rng(12345)
+    acts = rng.integers(0, 5, size=(8, n_envs, 4)).astype(np.int32)
+    threads = oracle.max_threads() if nthreads <= 0 else nthreads
+    import ctypes as C
+    L = oracle.lib()
+    obs = np.empty((n_envs, 4, 8, env.H, env.W), np.float32)
+    rew = np.zeros((n_envs, 2)); done = np.zeros(n_envs, np.uint8); legal = np.zeros((n_envs, 4), np.uint8)
+    sc = np.zeros(n_envs, np.int32); sh = np.zeros((n_envs, 4))
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def one(i):
+        L.pmo_step_batch(C.c_void_p(env.buf.ctypes.data), n_envs, p(acts[i % 8]), p(obs), p(rew), p(done), p(legal),
+                         p(sc), p(sh), 1, threads)
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one(i)
+    dt = time.perf_counter() - t0
+    return 4.0 * n_envs * steps / dt, dt / steps, threads
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on the box's host
+    cores.  The reference is pure Python (cannot travel to the GPU box), so
+    this times the oracle port with all host threads; rank 0 only."""
+    if rank != 0:
+        return
+    n = args.envs
+    v, sps, threads = oracle_rate(args.layout, n, args.steps, args.warmup, args.length)
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec (env step+obs)", "value": v, "unit": "agent-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitsets + f64 rewards -> f32 obs",
+        "data": "synthetic (uniform random actions, seeded)",
+        "config": {"workload": f"{args.layout}, {n} envs x 4 agents, self-play random actions, length {args.length}, "
+                               "auto-reset", "envs": n, "layout": args.layout},
+        "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps of the full {n}-env batch on {threads} OpenMP threads "
+                                   f"(C port of capture.py/gymPacMan.py; the Python reference itself ran "
+                                   f"{PY_REFERENCE_AGENT_STEPS_PER_CORE.get(args.layout)} agent-steps/s/core at survey time)"},
+        "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def measure_layout(torch, env_cls, layout, n_envs, steps, warmup, length, device, pool=8):
+    """-> dict(step_ms total loop, kernel_ms step kernel alone) for one layout on this rank."""
+    env = env_cls(layout_file=layout_path(layout), self_play=True, length=length, num_envs=n_envs, device=device)
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    acts = torch.randint(0, 5, (pool, n_envs, 4), generator=g, dtype=torch.uint8).to(device)
+    env.reset_batched()
+
+    def one(i):
+        o = env.step_batched(acts[i % pool])
+        env.reset_batched(mask=o["done"])
+    for i in range(warmup):
+        one(i)
+    return env, acts, one
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--layout", default="tinyCapture")
+    ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
+    ap.add_argument("--length", type=int, default=300)
+    ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / other layouts (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    torch.cuda.set_device(local)
+    device = torch.device(f"cuda:{local}")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    N, K, W = args.envs, args.steps, args.warmup
+    H, Wd = gymPacMan_parallel_env(layout_file=layout_path(args.layout), self_play=True, num_envs=1,
+                                   device=device).obs_shape[1:]
+    env, acts, one = measure_layout(torch, gymPacMan_parallel_env, args.layout, N, K, W, args.length, device)
+    pool = acts.shape[0]
+
+    with ClockSampler(local) as clk:
+        # ---- (1) whole-step throughput: K x (pm_step + pm_reset(done)), inputs resident in HBM ----
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for i in range(K):
+            one(i)
+        ev1.record()
+        barrier()
+        loop_ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([loop_ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            loop_ms = float(t.item())
+
+        # ---- (2) the dominant kernel alone (pm_env_kernel<STEP>): event pair around every launch ----
+        KK = min(K, 200)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KK)]
+        torch.cuda.synchronize()
+        for i in range(KK):
+            evs[i][0].record()
+            o = env.step_batched(acts[i % pool])
+            evs[i][1].record()
+            env.reset_batched(mask=o["done"])
+        torch.cuda.synchronize()
+        kern_ms = sum(a.elapsed_time(b) for a, b in evs) / KK
+
+        # ---- (3) end to end through the C ABI with HOST buffers (pm_step_host): pinned actions in,
+        #          rewards/done/legal/score_change/shaped rewards out, obs stay in HBM for the policy ----
+        acts_host = [acts[i].cpu().pin_memory() for i in range(pool)]
+        for i in range(3):
+            env.step_host(acts_host[i % pool]); env.reset_batched(mask=env._done)
+        KE = min(K, 200)
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for i in range(KE):
+            env.step_host(acts_host[i % pool])
+            env.reset_batched(mask=env._done)
+        ev1.record()
+        barrier()
+        e2e_ms = max(ev0.elapsed_time(ev1), 0.0)
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        # same, but also hauling the 4 x [N,8,H,W] fp32 observations to the host (a CPU-side consumer)
+        e2e_obs = None
+        if rank == 0 and not args.no_extras:
+            for i in range(2):
+                env.step_host(acts_host[i % pool], want_obs=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(5):
+                env.step_host(acts_host[i % pool], want_obs=True)
+                env.reset_batched(mask=env._done)
+            torch.cuda.synchronize()
+            e2e_obs = 4.0 * N * 5 / (time.perf_counter() - t0)
+    clocks = clk.summary()
+
+    h2d = N * 4
+    d2h = N * (16 + 1 + 4 + 4 + 16)
+    value = 4.0 * N * K * world / (loop_ms * 1e-3)
+    peak, peak_src = peaks()
+    algo = ALGO_BYTES_PER_AGENT_STEP.get(args.layout, 32 * H * Wd + 75)
+    achieved = algo * 4.0 * N / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(f"{args.layout}:{N}")
+
+    line = {
+        "metric": "agent-steps/sec (env step+obs)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": loop_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 bitsets + f64 rewards -> f32 obs", "data": "synthetic (uniform random actions, seeded)",
+        "config": {"workload": f"{args.layout}, {N} envs/GPU x 4 agents, self-play random actions, length {args.length}, "
+                               "auto-reset by done mask", "envs_per_gpu": N, "layout": args.layout,
+                   "obs_bytes_per_step_per_gpu": 4 * N * 32 * H * Wd,
+                   "l2": "no flush: each step writes %.2f GB of observations per GPU (>> 126 MB L2)" % (4 * N * 32 * H * Wd / 1e9),
+                   "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "roofline": {"bound": "hbm", "kernel": "pm_env_kernel<STEP>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": algo * 4 * N, "kernel_ms": kern_ms},
+        "e2e": {"value": 4.0 * N * KE * world / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": KE, "wall_ms_rank0": e2e_wall_ms,
+                "note": "pm_step_host: pinned host actions in, rewards/done/legal/score_change/shaped rewards to pinned "
+                        "host memory, stream sync every step; observations stay in HBM for the policy net",
+                "with_obs_to_host_agent_steps_per_s": e2e_obs},
+        "gpu_launches": 2 * K,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        # CPU port on this box's host cores: bounded sample of the same workload
+        ncpu = min(N, 16384)
+        v, sps, threads = oracle_rate(args.layout, ncpu, 6, 2, args.length)
+        line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                                "sample": f"6 steps x {ncpu} envs of the same workload, {threads} OpenMP threads; "
+                                          f"Python reference at survey time: {PY_REFERENCE_AGENT_STEPS_PER_CORE.get(args.layout)} agent-steps/s/core"}
+        v1, _, _ = oracle_rate(args.layout, 4096, 4, 1, args.length, nthreads=1)
+        line["cpu_baseline"]["one_core_value"] = v1
+        # the other shipped layouts, same batch, short loop (informational)
+        also = {}
+        del env, acts, one
+        torch.cuda.empty_cache()
+        for lay in ("smallCapture", "bloxCapture"):
+            if lay == args.layout:
+                continue
+            e2, a2, one2 = measure_layout(torch, gymPacMan_parallel_env, lay, N, 0, 5, args.length, device)
+            h2, w2 = e2.obs_shape[1:]
+            kk = 60
+            ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(kk)]
+            torch.cuda.synchronize()
+            ev0.record()
+            for i in range(kk):
+                ee[i][0].record(); o = e2.step_batched(a2[i % a2.shape[0]]); ee[i][1].record()
+                e2.reset_batched(mask=o["done"])
+            ev1.record()
+            torch.cuda.synchronize()
+            km = sum(a.elapsed_time(b) for a, b in ee) / kk
+            ab = ALGO_BYTES_PER_AGENT_STEP[lay]
+            also[lay] = {"value": 4.0 * N * kk / (ev0.elapsed_time(ev1) * 1e-3), "kernel_ms": km,
+                         "roofline_frac": ab * 4.0 * N / (km * 1e-3) / 1e9 / peak}
+            del e2, a2, one2
+            torch.cuda.empty_cache()
+        line["also"] = also
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

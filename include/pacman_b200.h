@@ -1,0 +1,158 @@
+/*
+ * pacman_b200.h — C ABI of the B200-native batched capture-the-flag Pac-Man
+ * environment (libpacman_b200.so).
+ *
+ * The reference has no FFI: its "operator API" for this path is the Python class
+ * gymPacMan.gymPacMan_parallel_env (gymPacMan.py:12-270) plus three trainer
+ * helpers (pacman_mappo_resnet.py:241-290,577) and distanceCalculator.py:111-150.
+ * Each entry point below names the reference interface it replaces.  All data
+ * pointers marked [dev] are device pointers owned by the caller (PyTorch
+ * tensors in the bundled host code), every launch goes to the caller's stream,
+ * nothing here synchronises the device except the *_host entry point, and no
+ * entry point keeps global state (re-entrant).  Return value: 0 = OK,
+ * > 0 = cudaError_t from the launch, < 0 = PM_E* argument error.
+ *
+ * Batch layout ("SoA over envs"): N independent 4-agent games share one board
+ * size W x H.  Boards come from a table of L packed layout records (L = 1: one
+ * layout for all envs; L = N: one maze per env; env n uses layout_id[n], or
+ * n % L when layout_id is NULL).
+ */
+#ifndef PACMAN_B200_H
+#define PACMAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_ABI_VERSION 1
+
+/* argument errors */
+#define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
+#define PM_ELAYOUT  (-2)  /* layout text malformed (ragged, != 4 agents, open border)  */
+#define PM_ETOOBIG  (-3)  /* W*H > PM_MAX_CELLS or W,H > 255                           */
+#define PM_ENOGPU   (-4)  /* no CUDA device / kernel image not loadable on this device */
+
+#define PM_MAX_CELLS 1024
+
+/* gym action ints, gymPacMan.py:66-89 */
+enum { PM_NORTH = 0, PM_EAST = 1, PM_SOUTH = 2, PM_WEST = 3, PM_STOP = 4 };
+
+typedef void *pm_stream_t; /* cudaStream_t */
+
+/* ---- sizes ------------------------------------------------------------- */
+int pm_abi_version(void);
+/* u32 words of the per-batch geometry record / of one packed layout record */
+int pm_geom_words(int W, int H);
+int pm_layout_words(int W, int H);
+/* bytes of the device state blob for N envs */
+size_t pm_state_bytes(int W, int H, int64_t n_envs);
+
+/* ---- host-side packing (pure CPU, no CUDA call) -------------------------- */
+/* Geometry record: plane masks for the three half-board formulas
+ * (capture.py:325-350) and the food-dump visit order of
+ * AgentRules.dumpFoodFromDeath (capture.py:635-661) as an offset table.      */
+int pm_pack_geom(int W, int H, uint32_t *out);
+/* One `.lay` board (layout.py:95-130): text = H rows of W chars, row 0 = top.
+ * Writes pm_layout_words(W,H) words; *has_caps (optional) = board has capsules. */
+int pm_pack_layout(const char *text, int W, int H, uint32_t *out, int *has_caps);
+
+/* ---- batch descriptor ---------------------------------------------------- */
+typedef struct pm_env_desc {
+    int32_t W, H;
+    int32_t n_layouts;            /* L                                             */
+    int32_t has_caps;             /* any layout in the table has a capsule          */
+    int64_t n_envs;               /* N                                             */
+    const uint32_t *geom;         /* [dev] pm_geom_words words                      */
+    const uint32_t *layouts;      /* [dev] L * pm_layout_words words                */
+    const uint32_t *layout_id;    /* [dev] [N] or NULL                              */
+    void *state;                  /* [dev] pm_state_bytes bytes                     */
+    /* gymPacMan.__init__ kwargs (gymPacMan.py:15) */
+    int32_t length;
+    int32_t reward_for_legal_action;
+    int32_t defence_reward;
+    /* bit i set: agent i ignores `actions` and plays a uniformly random LEGAL action drawn in-kernel at
+       its own sub-move (the randomTeam opponent, agents/randomTeam.py:94-100; gymPacMan.py:157)      */
+    int32_t random_agent_mask;
+    double shaping_scale;         /* SHAPING_SCALE, pacman_mappo_resnet.py:34       */
+    uint64_t random_seed;         /* counter-based: draw = hash(seed, env, step, agent) */
+} pm_env_desc;
+
+/* Outputs of one step; any pointer may be NULL to skip that output. */
+typedef struct pm_step_out {
+    float *obs;                   /* [dev] agent a, env n at obs + a*obs_agent_stride + n*8*H*W (fp32 [8][H][W]) */
+    int64_t obs_agent_stride;     /* in floats; N*8*H*W for a dense [4][N][8][H][W] tensor                      */
+    double *reward;               /* [dev] [2][N]: row 0 red team (agents 0,2), row 1 blue (1,3); fp64 like the
+                                     reference's Python floats                                                  */
+    uint8_t *done;                /* [dev] [N]                                                                   */
+    uint8_t *legal;               /* [dev] [N][4] bit a = gym action a legal, from the FINAL state              */
+    int32_t *score_change;        /* [dev] [N]                                                                   */
+    double *shaping;              /* [dev] [4][N] compute_heuristic_shaping per agent (fp64)                    */
+    float *shaped_reward;         /* [dev] [4][N] fp32(2*team_reward + shaping_scale*shaping), i.e. the value
+                                     the trainer stores in reward_buf (pacman_mappo_resnet.py:518-522)          */
+} pm_step_out;
+
+/* ---- environment --------------------------------------------------------- */
+/* gymPacMan_parallel_env.reset (gymPacMan.py:92-141) for every env with
+ * mask[n] != 0 (mask NULL = all).  Writes obs/legal only for the envs it resets. */
+int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, int64_t obs_agent_stride,
+             uint8_t *legal, pm_stream_t stream);
+
+/* gymPacMan_parallel_env.step (gymPacMan.py:143-193): four ordered sub-moves
+ * (GameState.generateSuccessor, capture.py:107-123), per-agent mid-step
+ * observation (get_Observation, :195-229), team rewards (get_reward, :231-259),
+ * termination (:261-270).  actions: [dev] [N][4], one element per agent;
+ * action_itemsize = 1 (uint8) or 8 (int64).  Values outside 0..4 act as an
+ * illegal move (-> Stop, no legal-action bonus).                             */
+int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
+            pm_stream_t stream);
+
+/* get_Observation(agentIndex) on the CURRENT state (gymPacMan.py:195-229) for
+ * all four agents of every env. */
+int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream);
+
+/* pm_step with HOST buffers (the call a CPU-side consumer of the reference API makes):
+ * copies actions_host ([N][4] uint8, ideally pinned) into actions_dev, runs pm_step
+ * into the DEVICE buffers of out_dev, copies every member of out_dev that has a
+ * non-NULL counterpart in out_host back to the host, and synchronises the stream.
+ * out_host->obs may be NULL to keep observations resident in HBM for a policy
+ * network on the same GPU. */
+int pm_step_host(const pm_env_desc *d, const uint8_t *actions_host, uint8_t *actions_dev,
+                 const pm_step_out *out_dev, const pm_step_out *out_host, pm_stream_t stream);
+
+/* Unpack the device state into plain arrays (GameState accessors,
+ * capture.py:125-234): agents [N][4][7] int32 = x,y,dir,isPacman,scaredTimer,
+ * numCarrying,numReturned; food/caps [N][H*W] uint8 (cell y*W+x);
+ * misc [N][2] int32 = score, steps.  Any pointer may be NULL.               */
+int pm_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc,
+                 pm_stream_t stream);
+/* Inverse of pm_get_state (test / checkpoint-restore hook). All four required. */
+int pm_set_state(const pm_env_desc *d, const int32_t *agents, const uint8_t *food, const uint8_t *caps,
+                 const int32_t *misc, pm_stream_t stream);
+
+/* ---- maze distances ------------------------------------------------------ */
+/* distanceCalculator.computeDistances (distanceCalculator.py:111-150) for L
+ * layouts at once.  Node order = walls.asList(False) (x-major, y-minor).
+ *   n_open [dev] [L] int32        number of open cells per layout
+ *   node_of_cell [dev] [L][H*W] int16   cell (y*W+x) -> node index, -1 for walls
+ *   dist [dev] [L][nmax][nmax] uint16   dist[l][i][j] = distance(node i, node j);
+ *        0xFFFF = unreachable (sys.maxsize in the reference) or i/j >= n_open[l] */
+int pm_distances(int W, int H, const uint32_t *layouts, int n_layouts, int32_t *n_open,
+                 int16_t *node_of_cell, uint16_t *dist, int nmax, pm_stream_t stream);
+
+/* ---- rollout post-processing --------------------------------------------- */
+/* compute_gae (pacman_mappo_resnet.py:277-290) over M independent columns:
+ * rew/val/done/adv/ret are [T][M] fp32 row-major, last_value [M]; fp32
+ * arithmetic in the reference's operation order (no FMA contraction).        */
+int pm_gae(const float *rew, const float *val, const float *done, const float *last_value,
+           double gamma, double lam, float *adv, float *ret, int T, int64_t M, pm_stream_t stream);
+/* Minibatch advantage normalisation (pacman_mappo_resnet.py:577): for each
+ * consecutive group of mb indices, out = (adv[idx]-mean)/(std_unbiased+1e-8). */
+int pm_adv_norm(const float *adv, const int64_t *inds, float *out, int64_t n, int mb, pm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PACMAN_B200_H */

@@ -1,0 +1,49 @@
+"""In-tree build of libpacman_b200.so for sm_100a (nvcc cross-compiles without a GPU).
+
+    python -m pacman_marl_2025_b200.build [--force] [-v]
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libpacman_b200.so")
+SOURCES = ["pm_env.cu", "pm_bfs.cu", "pm_gae.cu", "pm_pack.cpp"]
+HEADERS = ["pm_env_core.cuh", "pm_format.h", os.path.join("..", "..", "include", "pacman_b200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",                      # rewards/GAE reproduce the reference's one-rounding-per-op arithmetic
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-shared", "-cudart", "static",
+]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; cannot build libpacman_b200.so")
+
+
+def stale() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return OUT
+    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+          [os.path.join(CSRC, f) for f in SOURCES]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,260 @@
+// pm_env.cu — sm_100a kernels + C-ABI entry points for reset / step / observe
+// of the batched capture environment.  The per-thread logic lives in
+// pm_env_core.cuh; this file owns the CTA choreography, launch geometry and the
+// ABI glue (include/pacman_b200.h).
+//
+// CTA choreography (one CTA = E consecutive envs):
+//   stage geometry masks (+ the layout record when the batch has one layout)
+//   into shared memory -> phase A (thread el < E steps env n0+el, leaves four
+//   snapshots in smem) -> for each pass of KB agents: phase B1 (all threads
+//   build observation bit-string words) -> phase B2 (each warp streams whole
+//   observations to HBM with 128-bit stores).
+// HBM traffic per env-step: ~2 x (64 + 4*NW) B of state, 4 B actions, ~70 B of
+// small outputs, and 4 * 32*H*W B of observations (98+ % of all bytes).
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/pacman_b200.h"
+#include "pm_env_core.cuh"
+
+#define PM_THREADS 256
+
+template <int MODE>
+__global__ void __launch_bounds__(PM_THREADS) pm_env_kernel(const PmParams P, const uint32_t magic) {
+    extern __shared__ __align__(16) uint32_t sm[];
+    const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, P.E, P.KB, P.has_caps, P.L);
+    const int tid = threadIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.x * P.E;
+
+    // ---- stage per-batch tables ----
+    if (tid < 16) {
+        float4 v = make_float4((tid & 1) ? 1.f : 0.f, (tid & 2) ? 1.f : 0.f, (tid & 4) ? 1.f : 0.f, (tid & 8) ? 1.f : 0.f);
+        reinterpret_cast<float4 *>(sm + M.lut)[tid] = v;
+    }
+    for (int i = tid; i < 4 * P.NCAT; i += PM_THREADS) sm[M.masks + i] = __ldg(P.geom + PM_G_HDR + i);
+    if (P.L == 1)
+        for (int i = tid; i < P.LS; i += PM_THREADS) sm[M.lay + i] = __ldg(P.layouts + i);
+    __syncthreads();
+
+    // ---- phase A: rules, one thread per env ----
+    if (tid < P.E) {
+        if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, M, tid, n0);
+        else pm_phaseA_static<MODE>(P, sm, M, tid, n0);
+    }
+    if (P.obs == nullptr) return;
+    __syncthreads();
+
+    // ---- phase B: observations ----
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int k0 = 0; k0 < 4; k0 += P.KB) {
+        pm_phaseB1<MODE>(P, sm, M, tid, PM_THREADS, magic, k0);
+        __syncthreads();
+        pm_phaseB2(P, sm, M, warp, PM_THREADS / 32, lane, n0, k0);
+        if (k0 + P.KB < 4) __syncthreads();
+    }
+}
+
+// ---- state export / import (GameState accessors; tests, checkpoints) ---------
+__global__ void pm_get_state_kernel(const PmParams P, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P.N) return;
+    const int64_t NP = pm_np(P.N);
+    const pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
+    const pm_u4 B = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agB(P.N))[n];
+    const pm_u4 Mi = reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n];
+    const uint32_t a[4] = {A.x, A.y, A.z, A.w}, b[4] = {B.x, B.y, B.z, B.w};
+    if (agents)
+        for (int i = 0; i < 4; ++i) {
+            int32_t *o = agents + (n * 4 + i) * 7;
+            o[0] = a[i] & 0xff; o[1] = (a[i] >> 8) & 0xff; o[2] = (a[i] >> 16) & 7; o[3] = (a[i] >> 19) & 1;
+            o[4] = (a[i] >> 20) & 0xff; o[5] = b[i] & 0xffff; o[6] = b[i] >> 16;
+        }
+    if (misc) { misc[2 * n] = (int32_t)Mi.x; misc[2 * n + 1] = (int32_t)Mi.y; }
+    const uint32_t *gfood = reinterpret_cast<const uint32_t *>(P.state + pm_st_food(P.N));
+    const uint32_t *gcaps = reinterpret_cast<const uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
+    for (int c = 0; c < P.HW; ++c) {
+        if (food) food[n * P.HW + c] = (gfood[(size_t)(c >> 5) * NP + n] >> (c & 31)) & 1;
+        if (caps) caps[n * P.HW + c] = (gcaps[(size_t)(c >> 5) * NP + n] >> (c & 31)) & 1;
+    }
+}
+
+__global__ void pm_set_state_kernel(const PmParams P, const int32_t *agents, const uint8_t *food, const uint8_t *caps,
+                                    const int32_t *misc) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= P.N) return;
+    const int64_t NP = pm_np(P.N);
+    uint32_t a[4], b[4], s[4];
+    for (int i = 0; i < 4; ++i) {
+        const int32_t *o = agents + (n * 4 + i) * 7;
+        a[i] = pm_agA_pack(o[0], o[1], o[2], o[3], o[4]);
+        b[i] = (uint32_t)o[5] | (uint32_t)o[6] << 16;
+        s[i] = (uint32_t)o[0] | (uint32_t)o[1] << 8 | (uint32_t)o[5] << 16;
+    }
+    pm_u4 A, B, S, Mi;
+    A.x = a[0]; A.y = a[1]; A.z = a[2]; A.w = a[3];
+    B.x = b[0]; B.y = b[1]; B.z = b[2]; B.w = b[3];
+    S.x = s[0]; S.y = s[1]; S.z = s[2]; S.w = s[3];
+    uint32_t *gfood = reinterpret_cast<uint32_t *>(P.state + pm_st_food(P.N));
+    uint32_t *gcaps = reinterpret_cast<uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
+    int rf = 0, bf = 0;
+    for (int w = 0; w < P.NW; ++w) {
+        uint32_t fw = 0, cw = 0;
+        for (int bit = 0; bit < 32; ++bit) {
+            const int c = w * 32 + bit;
+            if (c >= P.HW) break;
+            if (food[n * P.HW + c]) { fw |= 1u << bit; if (c % P.W < (P.W >> 1)) ++rf; else ++bf; }
+            if (caps[n * P.HW + c]) cw |= 1u << bit;
+        }
+        gfood[(size_t)w * NP + n] = fw;
+        gcaps[(size_t)w * NP + n] = cw;
+    }
+    Mi.x = (uint32_t)misc[2 * n]; Mi.y = (uint32_t)misc[2 * n + 1]; Mi.z = (uint32_t)rf | (uint32_t)bf << 16; Mi.w = 0;
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_misc(P.N))[n] = Mi;
+}
+
+// ---------------------------------------------------------------------------
+// host glue
+// ---------------------------------------------------------------------------
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Launch geometry: E envs per CTA and KB agents per observation pass, chosen so
+// that >= 3 CTAs of 256 threads fit in the 227 KB of shared memory per SM.
+// PM_E / PM_KB override (tuning hook used by bench sweeps).
+static void pick_geometry(PmParams &P) {
+    int E = env_int("PM_E", 0), KB = env_int("PM_KB", 0);
+    if (E <= 0) E = 64;
+    if (KB != 1 && KB != 2 && KB != 4) KB = P.NCAT <= 48 ? 4 : 2;
+    while (E > 1 && (E & (E - 1))) E &= E - 1;           // power of two
+    if (E > PM_THREADS) E = PM_THREADS;
+    for (;;) {
+        const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, E, KB, P.has_caps, P.L);
+        if ((size_t)M.total * 4 <= 72 * 1024 || (E <= 8 && KB == 1)) break;
+        if (KB > 1) KB >>= 1; else E >>= 1;
+    }
+    P.E = E; P.KB = KB; P.lgE = 0;
+    while ((1 << P.lgE) < E) ++P.lgE;
+}
+
+static int fill_params(const pm_env_desc *d, PmParams &P) {
+    if (!d || !d->geom || !d->layouts || !d->state || d->n_envs <= 0 || d->n_layouts <= 0) return PM_EINVAL;
+    if (d->W < 3 || d->H < 3) return PM_EINVAL;
+    if (d->W > 255 || d->H > 255 || d->W * d->H > PM_MAX_CELLS) return PM_ETOOBIG;
+    memset(&P, 0, sizeof(P));
+    P.W = d->W; P.H = d->H; P.HW = d->W * d->H; P.NW = pm_nw(P.HW); P.NCAT = pm_ncat(P.HW);
+    P.ND = pm_nd(P.W, P.H); P.LS = pm_layout_words_(P.HW);
+    P.L = d->n_layouts; P.has_caps = d->has_caps != 0; P.N = d->n_envs;
+    P.geom = d->geom; P.layouts = d->layouts; P.layout_id = d->layout_id; P.state = (uint8_t *)d->state;
+    P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
+    P.shaping_scale = d->shaping_scale;
+    P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
+    pick_geometry(P);
+    return 0;
+}
+
+template <int MODE>
+static int launch_env(const PmParams &P, cudaStream_t st) {
+    const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, P.E, P.KB, P.has_caps, P.L);
+    const size_t smem = (size_t)M.total * 4;
+    static size_t configured[64][3];                   // per device, per kernel instance
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
+    if (smem > configured[dev & 63][MODE]) {
+        cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured[dev & 63][MODE] = smem;
+    }
+    const uint32_t magic = (uint32_t)((0x100000000ull / (uint64_t)P.NCAT) + 1);
+    const unsigned grid = (unsigned)((P.N + P.E - 1) / P.E);
+    pm_env_kernel<MODE><<<grid, PM_THREADS, smem, st>>>(P, magic);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, int64_t obs_agent_stride, uint8_t *legal,
+                        pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    if (obs && (obs_agent_stride & 3)) return PM_EINVAL;
+    P.mask = mask; P.obs = obs; P.obs_agent_stride = obs_agent_stride; P.legal = legal;
+    return launch_env<PM_MODE_RESET>(P, (cudaStream_t)stream);
+}
+
+extern "C" int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    if (!obs || (obs_agent_stride & 3)) return PM_EINVAL;
+    P.obs = obs; P.obs_agent_stride = obs_agent_stride;
+    return launch_env<PM_MODE_OBSERVE>(P, (cudaStream_t)stream);
+}
+
+extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
+                       pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    if (!actions || !out || (action_itemsize != 1 && action_itemsize != 8)) return PM_EINVAL;
+    if (out->obs && (out->obs_agent_stride & 3)) return PM_EINVAL;
+    P.actions = actions; P.act_size = action_itemsize;
+    P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
+    P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
+    P.shaping = out->shaping; P.shaped = out->shaped_reward;
+    return launch_env<PM_MODE_STEP>(P, (cudaStream_t)stream);
+}
+
+// ---- host-buffer step ------------------------------------------------------
+extern "C" int pm_step_host(const pm_env_desc *d, const uint8_t *actions_host, uint8_t *actions_dev,
+                            const pm_step_out *od, const pm_step_out *oh, pm_stream_t stream) {
+    if (!d || !actions_host || !actions_dev || !od || !oh) return PM_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)d->n_envs, HW = (size_t)d->W * d->H;
+    cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, N * 4, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    if (int rc = pm_step(d, actions_dev, 1, od, stream)) return rc;
+#define PM_D2H(member, bytes)                                                                  \
+    if (oh->member) {                                                                          \
+        if (!od->member) return PM_EINVAL;                                                     \
+        e = cudaMemcpyAsync(oh->member, od->member, bytes, cudaMemcpyDeviceToHost, st);        \
+        if (e != cudaSuccess) return (int)e;                                                   \
+    }
+    PM_D2H(reward, N * 16)
+    PM_D2H(done, N)
+    PM_D2H(legal, N * 4)
+    PM_D2H(score_change, N * 4)
+    PM_D2H(shaping, N * 32)
+    PM_D2H(shaped_reward, N * 16)
+#undef PM_D2H
+    if (oh->obs) {
+        if (!od->obs) return PM_EINVAL;
+        for (int a = 0; a < 4; ++a) {
+            e = cudaMemcpyAsync(oh->obs + a * oh->obs_agent_stride, od->obs + a * od->obs_agent_stride, N * 8 * HW * 4,
+                                cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    return (int)cudaStreamSynchronize(st);
+}
+
+extern "C" int pm_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc,
+                            pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    const unsigned grid = (unsigned)((P.N + 127) / 128);
+    pm_get_state_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, agents, food, caps, misc);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int pm_set_state(const pm_env_desc *d, const int32_t *agents, const uint8_t *food, const uint8_t *caps,
+                            const int32_t *misc, pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    if (!agents || !food || !caps || !misc) return PM_EINVAL;
+    const unsigned grid = (unsigned)((P.N + 127) / 128);
+    pm_set_state_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, agents, food, caps, misc);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,548 @@
+// pm_env_core.cuh — the rules + observation logic of the batched capture env,
+// written as three per-thread phases that the sm_100a kernel (pm_env.cu) runs
+// back to back inside one CTA:
+//
+//   phase A  (one thread per env)   the four ordered sub-moves of
+//            gymPacMan.step (gymPacMan.py:143-193): legal actions, move, pacman
+//            flag, food return (+ the agentState rebinding of capture.py:505),
+//            eating, capsules, collisions / respawns / food dump, scared timer,
+//            score, rewards, termination, shaping — and after each sub-move a
+//            compact SNAPSHOT (board bitsets + four cell positions) in shared
+//            memory, because the reference observes agent i right after ITS
+//            sub-move (gymPacMan.py:166).
+//   phase B1 (all threads)          snapshot -> observation bit string words
+//            (see pm_format.h) in shared memory.
+//   phase B2 (one warp per observation) bit string -> fp32 planes with
+//            coalesced 128-bit stores; this is the HBM-bound part.
+//
+// The functions are PM_HD (host + device) on purpose: tests/emu compiles the
+// very same code with g++ and replays the golden fixtures through it without a
+// GPU.  That emulation is test-only; the product never runs it.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "pm_format.h"
+
+#if defined(__CUDACC__)
+typedef uint4 pm_u4;
+typedef float4 pm_f4;
+#define PM_NOINLINE __host__ __device__ __noinline__
+#else
+struct alignas(16) pm_u4 { uint32_t x, y, z, w; };
+struct alignas(16) pm_f4 { float x, y, z, w; };
+#define PM_NOINLINE inline
+#endif
+
+#define PM_SCARED_TIME 40   // capture.py:75
+#define PM_MODE_STEP 0
+#define PM_MODE_RESET 1
+#define PM_MODE_OBSERVE 2
+
+// ---- exact fp64 helpers: the reference accumulates rewards as Python floats,
+// one rounding per operation; never let the compiler contract into FMA --------
+PM_HD double pm_dadd(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+PM_HD double pm_dmul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+PM_HD uint32_t pm_funnel_r(uint32_t lo, uint32_t hi, int r) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, r);
+#else
+    return r ? (lo >> r) | (hi << (32 - r)) : lo;
+#endif
+}
+
+struct PmParams {
+    int W, H, HW, NW, NCAT, ND, LS;
+    int L, has_caps;                    // layouts in table, capsules anywhere
+    int E, lgE, KB;                     // envs per CTA (power of two), log2(E), agents per B pass (1, 2 or 4)
+    int64_t N;
+    const uint32_t *geom, *layouts, *layout_id;
+    uint8_t *state;
+    int length, reward_legal, defence;
+    double shaping_scale;
+    int bot_mask; unsigned long long bot_seed;   // in-kernel uniform-random-legal agents
+    // step inputs / outputs (see pm_step_out in pacman_b200.h)
+    const void *actions; int act_size;
+    float *obs; int64_t obs_agent_stride;
+    double *reward; uint8_t *done; uint8_t *legal; int32_t *score_change; double *shaping; float *shaped;
+    const uint8_t *mask;                // reset only
+};
+
+// ---- shared-memory map (u32 word offsets) ----------------------------------
+struct PmSmem {
+    int lut, masks, lay, lid, posA, posB, patch, food, caps, cat, total;
+    int E1;                             // padded env stride (odd -> conflict-free both ways)
+};
+PM_HD PmSmem pm_smem_map(int NW, int NCAT, int LS, int E, int KB, int has_caps, int L) {
+    PmSmem m;
+    m.E1 = E | 1;
+    int o = 0;
+    m.lut = o; o += 64;                 // 16 x float4
+    m.masks = o; o += 4 * NCAT;
+    m.lay = o; o += (L == 1) ? LS : 0;
+    m.lid = o; o += E;
+    m.posA = o; o += 4 * m.E1;
+    m.posB = o; o += 4 * m.E1;
+    m.patch = o; o += 4 * m.E1;
+    m.food = o; o += 4 * NW * m.E1;
+    m.caps = o; o += has_caps ? 4 * NW * m.E1 : 0;
+    o = (o + 3) & ~3;
+    m.cat = o; o += KB * E * NCAT;
+    m.total = o;
+    return m;
+}
+
+PM_HD int pm_bit(const uint32_t *bits, int c) { return (bits[c >> 5] >> (c & 31)) & 1; }
+PM_HD int pm_sbit(const uint32_t *base, int stride, int c) { return (base[(c >> 5) * stride] >> (c & 31)) & 1; }
+
+// ---- food dump: AgentRules.dumpFoodFromDeath (capture.py:569-668) ------------
+// Walks the precomputed visit order (pm_pack_geom) from the death cell and drops
+// `todo` pellets on the first cells that are on the board interior, not wall,
+// not food, on the death cell's side, not a capsule and not under any agent.
+// food/caps: this env's working bitsets in shared memory (word stride `st`).
+// Returns pellets added to (red half | blue half << 16).
+PM_NOINLINE uint32_t pm_dump(int W, int H, int ND, const uint32_t *dumptab, const uint32_t *walls,
+                             uint32_t *food, const uint32_t *caps, int st, int vx, int vy, int todo,
+                             uint32_t cells01, uint32_t cells23) {
+    const int side = 2 * vx < W;
+    uint32_t added = 0;
+    for (int t = 0; t < ND && todo > 0; ++t) {
+        const uint32_t o = dumptab[t];
+        const int x = vx + (int)(int8_t)(o & 0xff), y = vy + (int)(int8_t)((o >> 8) & 0xff);
+        if (x <= 0 || y <= 0 || x >= W || y >= H) continue;          // capture.py:609
+        const int c = y * W + x;
+        if (pm_bit(walls, c)) continue;
+        if (pm_sbit(food, st, c)) continue;
+        if ((2 * x < W) != side) continue;                             // onRightSide
+        if (caps && pm_sbit(caps, st, c)) continue;
+        const uint32_t cc = (uint32_t)c;
+        if (cc == (cells01 & 0xffff) || cc == (cells01 >> 16) || cc == (cells23 & 0xffff) || cc == (cells23 >> 16)) continue;
+        food[(c >> 5) * st] |= 1u << (c & 31);
+        added += (x < (W >> 1)) ? 1u : 0x10000u;
+        --todo;
+    }
+    return added;
+}
+
+// Agents of one env, unpacked into registers (all loops over agents unroll).
+struct PmAgents {
+    int x[4], y[4], dir[4], pac[4], scared[4], carry[4], ret[4];
+    int sx[4], sy[4];
+};
+
+PM_HD void pm_home(PmAgents &g, int i) {        // configuration = start (capture.py:691-693 etc.)
+    g.pac[i] = 0; g.x[i] = g.sx[i]; g.y[i] = g.sy[i]; g.dir[i] = 4; g.scared[i] = 0;
+}
+
+// One pacman/ghost pair on the same cell (capture.py:682-701 and :708-727): an
+// unscared ghost kills the pacman (dump, respawn), a scared ghost is sent home.
+// `pacman` and `ghost` are compile-time after unrolling, so PmAgents stays in registers.
+PM_HD uint32_t pm_collide(PmAgents &g, const int pacman, const int ghost, int W, int H, int ND, const uint32_t *dumptab,
+                          const uint32_t *walls, uint32_t *fk, const uint32_t *ck, int E1) {
+    uint32_t added = 0;
+    if (g.scared[ghost] <= 0) {
+        if (g.carry[pacman] > 0) {
+            const uint32_t c01 = (uint32_t)(g.y[0] * W + g.x[0]) | (uint32_t)(g.y[1] * W + g.x[1]) << 16;
+            const uint32_t c23 = (uint32_t)(g.y[2] * W + g.x[2]) | (uint32_t)(g.y[3] * W + g.x[3]) << 16;
+            added = pm_dump(W, H, ND, dumptab, walls, fk, ck, E1, g.x[pacman], g.y[pacman], g.carry[pacman], c01, c23);
+            g.carry[pacman] = 0;
+        }
+        pm_home(g, pacman);
+    } else {
+        pm_home(g, ghost);
+    }
+    return added;
+}
+
+PM_HD int pm_legal_mask(const uint32_t *walls, int W, int c) {   // game.py:335-350, bit = gym action int
+    return (pm_bit(walls, c + W) ? 0 : 1) | (pm_bit(walls, c + 1) ? 0 : 2) | (pm_bit(walls, c - W) ? 0 : 4) |
+           (pm_bit(walls, c - 1) ? 0 : 8) | (pm_bit(walls, c) ? 0 : 16);
+}
+
+// Uniform draw from the set bits of `legal` (randomTeam: random.choice(legal actions),
+// agents/randomTeam.py:94-100).  Counter-based so a trajectory depends only on
+// (seed, env index, step, agent) and not on launch geometry or sharding.
+PM_HD int pm_random_legal(int legal, unsigned long long seed, unsigned long long n, unsigned ctr) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (n + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(ctr + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    int cnt = 0;
+    for (int b = 0; b < 5; ++b) cnt += (legal >> b) & 1;
+    int pick = (int)(((z >> 32) * (unsigned long long)cnt) >> 32);
+    for (int b = 0; b < 5; ++b)
+        if ((legal >> b) & 1) { if (pick == 0) return b; --pick; }
+    return 4;
+}
+
+// heuristic shaping (pacman_mappo_resnet.py:251-264); L1 distance is flip-invariant
+PM_HD double pm_shaping(int px, int py, int pcarry, int nx, int ny) {
+    int dx = px - nx, dy = py - ny;
+    const int dist = (dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy);
+    const double living = -0.15;
+    if (dist >= 2) return pm_dadd(pm_dadd(living, -0.4), -pm_dmul(0.15, (double)pcarry));
+    if (dist == 0) return pm_dadd(living, -0.05);
+    return living;
+}
+
+PM_HD void pm_store_snapshot(uint32_t *sm, const PmSmem &M, const PmParams &P, int k, int el, const PmAgents &g) {
+    const int HW = P.HW, W = P.W;
+    const int me = k, ally = k ^ 2, e1 = k ^ 1, e2 = k ^ 3;       // gym teams by index parity, gymPacMan.py:210
+    const uint32_t own = (uint32_t)(HW + g.y[me] * W + g.x[me]);
+    sm[M.posA + k * M.E1 + el] = own | (uint32_t)(4 * HW + g.y[ally] * W + g.x[ally]) << 16;
+    sm[M.posB + k * M.E1 + el] = (uint32_t)(5 * HW + g.y[e1] * W + g.x[e1]) | (uint32_t)(5 * HW + g.y[e2] * W + g.x[e2]) << 16;
+    sm[M.patch + k * M.E1 + el] = g.carry[me] > 0 ? (own | (uint32_t)(1 + g.carry[me]) << 16) : 0xffffffffu;
+}
+
+PM_HD void pm_unpack_agents(PmAgents &g, const pm_u4 &A, const pm_u4 &B, const uint32_t *tail) {
+    const uint32_t a[4] = {A.x, A.y, A.z, A.w}, b[4] = {B.x, B.y, B.z, B.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        g.x[i] = a[i] & 0xff; g.y[i] = (a[i] >> 8) & 0xff; g.dir[i] = (a[i] >> 16) & 7;
+        g.pac[i] = (a[i] >> 19) & 1; g.scared[i] = (a[i] >> 20) & 0xff;
+        g.carry[i] = b[i] & 0xffff; g.ret[i] = b[i] >> 16;
+        g.sx[i] = tail[PM_L_START + i] & 0xff; g.sy[i] = (tail[PM_L_START + i] >> 8) & 0xff;
+    }
+}
+PM_HD void pm_pack_agents(const PmAgents &g, pm_u4 &A, pm_u4 &B) {
+    uint32_t a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] = pm_agA_pack(g.x[i], g.y[i], g.dir[i], g.pac[i], g.scared[i]);
+        b[i] = (uint32_t)g.carry[i] | (uint32_t)g.ret[i] << 16;
+    }
+    A.x = a[0]; A.y = a[1]; A.z = a[2]; A.w = a[3];
+    B.x = b[0]; B.y = b[1]; B.z = b[2]; B.w = b[3];
+}
+
+// ============================================================================
+// phase A, MODE_STEP
+// ============================================================================
+PM_HD void pm_phaseA_step(const PmParams &P, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
+    const int64_t n = n0 + el;
+    if (n >= P.N) { sm[M.lid + el] = 0xffffffffu; return; }
+    const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
+    sm[M.lid + el] = lid;
+    const uint32_t *lay = (P.L == 1) ? sm + M.lay : P.layouts + (size_t)lid * P.LS;
+    const uint32_t *walls = lay + pm_l_walls(P.HW);
+    const uint32_t *tail = lay + pm_l_tail(P.HW);
+    const uint32_t *dumptab = P.geom + pm_g_dump_off(P.HW);
+    const int W = P.W, H = P.H, NW = P.NW, E1 = M.E1;
+    const int64_t NP = pm_np(P.N);
+    const uint32_t teams = tail[PM_L_TEAMS];
+
+    // ---- load state (128-bit loads, coalesced across the env dimension) ----
+    pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
+    pm_u4 B = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agB(P.N))[n];
+    pm_u4 S = reinterpret_cast<const pm_u4 *>(P.state + pm_st_snap(P.N))[n];
+    pm_u4 Mi = reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n];
+    uint32_t *gfood = reinterpret_cast<uint32_t *>(P.state + pm_st_food(P.N));
+    uint32_t *gcaps = reinterpret_cast<uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
+    uint32_t *food = sm + M.food + el;                 // slot k, word w at food[(k*NW + w)*E1]
+    uint32_t *caps = P.has_caps ? sm + M.caps + el : nullptr;
+    for (int w = 0; w < NW; ++w) food[w * E1] = gfood[(size_t)w * NP + n];
+    if (caps) for (int w = 0; w < NW; ++w) caps[w * E1] = gcaps[(size_t)w * NP + n];
+
+    PmAgents g;
+    pm_unpack_agents(g, A, B, tail);
+    int score = (int)Mi.x, steps = (int)Mi.y;
+    int rf = (int)(Mi.z & 0xffff), bf = (int)(Mi.z >> 16);       // pellets on the red / blue food half
+    uint32_t snap[4] = {S.x, S.y, S.z, S.w};
+
+    uint32_t act4;
+    if (P.act_size == 1) act4 = reinterpret_cast<const uint32_t *>(P.actions)[n];
+    else {
+        const long long *a8 = reinterpret_cast<const long long *>(P.actions) + 4 * n;
+        act4 = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { long long v = a8[i]; act4 |= (uint32_t)((v < 0 || v > 4) ? 255 : (int)v) << (8 * i); }
+    }
+
+    double red_r = 0.0, blue_r = 0.0, shap[4];
+    int sc_total = 0, red_sc = 0, blue_sc = 0;
+    bool food_dirty = false, caps_dirty = false;
+
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        uint32_t *fk = food + (size_t)a * NW * E1;
+        uint32_t *ck = caps ? caps + (size_t)a * NW * E1 : nullptr;
+        if (a > 0) {                                   // working copy for this sub-move; slot a-1 stays as snapshot
+            for (int w = 0; w < NW; ++w) fk[w * E1] = fk[(w - NW) * E1];
+            if (ck) for (int w = 0; w < NW; ++w) ck[w * E1] = ck[(w - NW) * E1];
+        }
+        // ---- get_reward pre-state (gymPacMan.py:231-259) ----
+        const bool gym_red = (a & 1) == 0;
+        const int o1 = gym_red ? 1 : 0, o2 = o1 + 2;
+        const int mine_before = gym_red ? rf : bf, theirs_before = gym_red ? bf : rf;
+        const int pb1 = g.pac[o1], pb2 = g.pac[o2];
+
+        // ---- AgentRules.applyAction (capture.py:468-517) ----
+        int c = g.y[a] * W + g.x[a];
+        const int legal = pm_legal_mask(walls, W, c);
+        int u = (act4 >> (8 * a)) & 0xff;
+        if ((P.bot_mask >> a) & 1) u = pm_random_legal(legal, P.bot_seed, (unsigned long long)n, (unsigned)steps * 4u + a);
+        const bool req_legal = u <= 4 && ((legal >> u) & 1);
+        if (!req_legal) u = 4;
+        const int dx = (u == 1) - (u == 3), dy = (u == 0) - (u == 2);
+        g.x[a] += dx; g.y[a] += dy; c += dx + dy * W;
+        if (u != 4) g.dir[a] = u;                      // Stop keeps the heading, game.py:115-117
+        const int is_red = (teams >> a) & 1;
+        g.pac[a] = is_red ^ (2 * g.x[a] < W ? 1 : 0);
+        int pacflag = g.pac[a];
+        int sc = 0;
+        if (g.carry[a] > 0 && !g.pac[a]) {
+            sc = is_red ? g.carry[a] : -g.carry[a];
+            g.ret[a] += g.carry[a];
+            g.carry[a] = 0;
+            pacflag = g.pac[3];                        // the rebinding quirk: capture.py:505 -> :514
+        }
+        if (pacflag) {                                 // AgentRules.consume (capture.py:519-560)
+            if (pm_sbit(fk, E1, c)) {
+                bool given = false;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (!given && (int)((teams >> i) & 1) == is_red && g.x[i] == g.x[a] && g.y[i] == g.y[a]) { g.carry[i] += 1; given = true; }
+                fk[(c >> 5) * E1] &= ~(1u << (c & 31));
+                food_dirty = true;
+                if (g.x[a] < (W >> 1)) --rf; else --bf;
+            }
+            if (ck && pm_sbit(ck, E1, c) && (is_red ? (2 * g.x[a] > W) : (2 * g.x[a] <= W))) {
+                ck[(c >> 5) * E1] &= ~(1u << (c & 31));
+                caps_dirty = true;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if ((int)((teams >> i) & 1) != is_red) g.scared[i] = PM_SCARED_TIME;
+            }
+        }
+        // ---- AgentRules.checkDeath (capture.py:670-728) ----
+        // The branch (mover is pacman / ghost) is chosen once; enemies are then
+        // visited in index order against live positions and timers.
+        const bool mover_is_pac = g.pac[a] != 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            if (e == a) continue;
+            if ((int)((teams >> e) & 1) == is_red) continue;
+            if (g.x[e] != g.x[a] || g.y[e] != g.y[a]) continue;
+            uint32_t added = 0;
+            if (mover_is_pac) {
+                if (!g.pac[e]) added = pm_collide(g, a, e, W, H, P.ND, dumptab, walls, fk, ck, E1);   // a = pacman, e = ghost
+            } else {
+                if (g.pac[e]) added = pm_collide(g, e, a, W, H, P.ND, dumptab, walls, fk, ck, E1);    // e = pacman, a = ghost
+            }
+            if (added) { rf += (int)(added & 0xffff); bf += (int)(added >> 16); food_dirty = true; }
+        }
+        g.scared[a] = g.scared[a] > 0 ? g.scared[a] - 1 : 0;      // decrementTimer, capture.py:562-567
+        score += sc;
+        sc_total += sc;
+        if (gym_red) red_sc += sc; else blue_sc -= sc;
+
+        // ---- get_reward post-state ----
+        double r = gym_red ? red_r : blue_r;
+        const int mine_after = gym_red ? rf : bf, theirs_after = gym_red ? bf : rf;
+        if (mine_before < mine_after) r = pm_dadd(r, 1.0);
+        if (theirs_before > theirs_after) r = pm_dadd(r, 0.1);
+        if (P.defence) {
+            if (pb1 && !g.pac[o1] && g.x[o1] == g.sx[o1] && g.y[o1] == g.sy[o1]) r = pm_dadd(r, 0.25);
+            if (pb2 && !g.pac[o2] && g.x[o2] == g.sx[o2] && g.y[o2] == g.sy[o2]) r = pm_dadd(r, 0.25);
+        }
+        if (P.reward_legal && req_legal) r = pm_dadd(r, 0.01);
+        if (gym_red) red_r = r; else blue_r = r;
+
+        // ---- observation snapshot for agent a (gymPacMan.py:166) + shaping ----
+        pm_store_snapshot(sm, M, P, a, el, g);
+        shap[a] = pm_shaping((int)(snap[a] & 0xff), (int)((snap[a] >> 8) & 0xff), (int)(snap[a] >> 16), g.x[a], g.y[a]);
+        snap[a] = (uint32_t)g.x[a] | (uint32_t)g.y[a] << 8 | (uint32_t)g.carry[a] << 16;
+    }
+
+    // ---- step epilogue (gymPacMan.py:171-193) ----
+    blue_r = pm_dadd(blue_r, (double)(blue_sc > 0 ? blue_sc : 0));
+    red_r = pm_dadd(red_r, (double)(red_sc > 0 ? red_sc : 0));
+    bool term = false;
+    if (bf == 0 && g.carry[0] == 0 && g.carry[2] == 0) term = true;      // check_termination, :261-270
+    if (rf == 0 && g.carry[1] == 0 && g.carry[3] == 0) term = true;
+    if (steps >= P.length) term = true;
+    if (term) {
+        const double bonus = pm_dadd(20.0, pm_dmul(1.0 / 5, (double)(score < 0 ? -score : score)));
+        if (score < 0) blue_r = pm_dadd(blue_r, bonus);
+        else if (score > 0) red_r = pm_dadd(red_r, bonus);
+    }
+    steps += 1;
+
+    // ---- outputs ----
+    if (P.reward) { P.reward[n] = red_r; P.reward[P.N + n] = blue_r; }
+    if (P.done) P.done[n] = term ? 1 : 0;
+    if (P.score_change) P.score_change[n] = sc_total;
+    if (P.legal) {
+        uint32_t lm = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, g.y[i] * W + g.x[i]) << (8 * i);
+        reinterpret_cast<uint32_t *>(P.legal)[n] = lm;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (P.shaping) P.shaping[(size_t)i * P.N + n] = shap[i];
+        if (P.shaped) {
+            const double team = (i & 1) ? blue_r : red_r;      // sum over both learners = 2 * team reward
+            P.shaped[(size_t)i * P.N + n] = (float)pm_dadd(pm_dadd(team, team), pm_dmul(P.shaping_scale, shap[i]));
+        }
+    }
+    // ---- state write-back ----
+    pm_pack_agents(g, A, B);
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
+    S.x = snap[0]; S.y = snap[1]; S.z = snap[2]; S.w = snap[3];
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
+    Mi.x = (uint32_t)score; Mi.y = (uint32_t)steps; Mi.z = (uint32_t)rf | (uint32_t)bf << 16;
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_misc(P.N))[n] = Mi;
+    if (food_dirty) for (int w = 0; w < NW; ++w) gfood[(size_t)w * NP + n] = food[(3 * NW + w) * E1];
+    if (caps_dirty) for (int w = 0; w < NW; ++w) gcaps[(size_t)w * NP + n] = caps[(3 * NW + w) * E1];
+}
+
+// ============================================================================
+// phase A, MODE_RESET / MODE_OBSERVE: one state, four observations of it
+// ============================================================================
+template <int MODE>
+PM_HD void pm_phaseA_static(const PmParams &P, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
+    const int64_t n = n0 + el;
+    if (n >= P.N || (MODE == PM_MODE_RESET && P.mask && !P.mask[n])) { sm[M.lid + el] = 0xffffffffu; return; }
+    const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
+    sm[M.lid + el] = lid;
+    const uint32_t *lay = (P.L == 1) ? sm + M.lay : P.layouts + (size_t)lid * P.LS;
+    const uint32_t *tail = lay + pm_l_tail(P.HW);
+    const int NW = P.NW, E1 = M.E1, W = P.W;
+    const int64_t NP = pm_np(P.N);
+    uint32_t *gfood = reinterpret_cast<uint32_t *>(P.state + pm_st_food(P.N));
+    uint32_t *gcaps = reinterpret_cast<uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
+    uint32_t *food = sm + M.food + el;
+    uint32_t *caps = P.has_caps ? sm + M.caps + el : nullptr;
+    PmAgents g;
+    if (MODE == PM_MODE_RESET) {
+        // CaptureRules.newGame -> GameState.initialize (capture.py:369-382,311-323; game.py:490-508)
+        pm_u4 A, B, S, Mi;
+        uint32_t a[4], s[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t st = tail[PM_L_START + i];
+            a[i] = pm_agA_pack(st & 0xff, (st >> 8) & 0xff, 4, (st >> 16) & 1, 0);
+            s[i] = st & 0xffff;
+        }
+        A.x = a[0]; A.y = a[1]; A.z = a[2]; A.w = a[3];
+        B.x = B.y = B.z = B.w = 0;
+        S.x = s[0]; S.y = s[1]; S.z = s[2]; S.w = s[3];
+        Mi.x = 0; Mi.y = 0; Mi.z = tail[PM_L_FOODCNT]; Mi.w = 0;
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_misc(P.N))[n] = Mi;
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t f = lay[pm_l_food(P.HW) + w], cp = lay[pm_l_caps(P.HW) + w];
+            food[w * E1] = f; gfood[(size_t)w * NP + n] = f;
+            gcaps[(size_t)w * NP + n] = cp;
+            if (caps) caps[w * E1] = cp;
+        }
+        pm_unpack_agents(g, A, B, tail);
+    } else {
+        pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
+        pm_u4 B = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agB(P.N))[n];
+        for (int w = 0; w < NW; ++w) food[w * E1] = gfood[(size_t)w * NP + n];
+        if (caps) for (int w = 0; w < NW; ++w) caps[w * E1] = gcaps[(size_t)w * NP + n];
+        pm_unpack_agents(g, A, B, tail);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pm_store_snapshot(sm, M, P, k, el, g);
+    if (P.legal) {
+        const uint32_t *walls = lay + pm_l_walls(P.HW);
+        uint32_t lm = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, g.y[i] * W + g.x[i]) << (8 * i);
+        reinterpret_cast<uint32_t *>(P.legal)[n] = lm;
+    }
+}
+
+// ============================================================================
+// phase B1: snapshot -> observation bit-string words in shared memory
+// ============================================================================
+// 32 bits of an NW-word bitset (word stride st) starting at bit s; s may be
+// negative or run past the end (missing bits read as zero).
+PM_HD uint32_t pm_extract32(const uint32_t *w, int st, int NW, int s) {
+    const int k = s >> 5, r = s & 31;
+    const uint32_t lo = ((unsigned)k < (unsigned)NW) ? w[k * st] : 0u;
+    const uint32_t hi = ((unsigned)(k + 1) < (unsigned)NW) ? w[(k + 1) * st] : 0u;
+    return pm_funnel_r(lo, hi, r);
+}
+
+template <int MODE>
+PM_HD void pm_phaseB1(const PmParams &P, uint32_t *sm, const PmSmem &M, int tid, int nthreads, uint32_t magic, int k0) {
+    const int NCAT = P.NCAT, NW = P.NW, HW = P.HW, E = P.E, E1 = M.E1;
+    const int total = P.KB * E * NCAT;
+    const uint32_t *m2 = sm + M.masks, *m3 = m2 + NCAT, *m6 = m3 + NCAT, *m7 = m6 + NCAT;
+    for (int idx = tid; idx < total; idx += nthreads) {
+#if defined(__CUDA_ARCH__)
+        const int u = (int)__umulhi((uint32_t)idx, magic);
+#else
+        const int u = (int)(((uint64_t)(uint32_t)idx * magic) >> 32);
+#endif
+        const int j = idx - u * NCAT;
+        const int k = k0 + (u >> P.lgE), el = u & (E - 1);
+        const uint32_t lid = sm[M.lid + el];
+        if (lid == 0xffffffffu) continue;
+        const uint32_t *lay = (P.L == 1) ? sm + M.lay : P.layouts + (size_t)lid * P.LS;
+        const int slot = (MODE == PM_MODE_STEP) ? k : 0;
+        const uint32_t *food = sm + M.food + (size_t)slot * NW * E1 + el;
+        const int b0 = 32 * j;
+        uint32_t w = lay[pm_l_wallcat(HW) + j];
+        w |= pm_extract32(food, E1, NW, b0 - 6 * HW) & m6[j];
+        w |= pm_extract32(food, E1, NW, b0 - 7 * HW) & m7[j];
+        if (P.has_caps) {
+            const uint32_t *caps = sm + M.caps + (size_t)slot * NW * E1 + el;
+            w |= pm_extract32(caps, E1, NW, b0 - 2 * HW) & m2[j];
+            w |= pm_extract32(caps, E1, NW, b0 - 3 * HW) & m3[j];
+        }
+        const uint32_t pa = sm[M.posA + k * E1 + el], pb = sm[M.posB + k * E1 + el];
+        unsigned d;
+        d = (pa & 0xffff) - (unsigned)b0; if (d < 32u) w |= 1u << d;
+        d = (pa >> 16) - (unsigned)b0;    if (d < 32u) w |= 1u << d;
+        d = (pb & 0xffff) - (unsigned)b0; if (d < 32u) w |= 1u << d;
+        d = (pb >> 16) - (unsigned)b0;    if (d < 32u) w |= 1u << d;
+        sm[M.cat + idx] = w;
+    }
+}
+
+// ============================================================================
+// phase B2: bit string -> fp32 planes, one warp per observation
+// ============================================================================
+PM_HD void pm_phaseB2(const PmParams &P, uint32_t *sm, const PmSmem &M, int warp, int nwarps, int lane, int64_t n0, int k0) {
+    const int NCAT = P.NCAT, E = P.E, E1 = M.E1;
+    const int nf4 = 2 * P.HW;                          // float4s per observation (8*HW/4)
+    const pm_f4 *lut = reinterpret_cast<const pm_f4 *>(sm + M.lut);
+    const int sh = (lane & 7) * 4;
+    for (int u = warp; u < P.KB * E; u += nwarps) {
+        const int k = k0 + (u >> P.lgE), el = u & (E - 1);
+        if (sm[M.lid + el] == 0xffffffffu) continue;
+        const uint32_t patch = sm[M.patch + k * E1 + el];
+        const int pf = patch == 0xffffffffu ? -1 : (int)((patch & 0xffff) >> 2);
+        const uint32_t *cat = sm + M.cat + (size_t)u * NCAT;
+        pm_f4 *dst = reinterpret_cast<pm_f4 *>(P.obs + (size_t)k * P.obs_agent_stride + (size_t)(n0 + el) * 8 * P.HW);
+        for (int f = lane; f < nf4; f += 32) {
+            const uint32_t nib = (cat[f >> 3] >> sh) & 15u;
+            pm_f4 v = lut[nib];
+            if (f == pf) {                             // own cell carries 1 + numCarrying (gymPacMan.py:205)
+                const float val = (float)(patch >> 16);
+                const int comp = patch & 3;
+                if (comp == 0) v.x = val; else if (comp == 1) v.y = val; else if (comp == 2) v.z = val; else v.w = val;
+            }
+            dst[f] = v;
+        }
+    }
+}

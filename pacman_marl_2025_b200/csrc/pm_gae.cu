@@ -1,0 +1,101 @@
+// pm_gae.cu — rollout post-processing kernels (sm_100a).
+//
+//  pm_gae      compute_gae (pacman_mappo_resnet.py:277-290) for M independent
+//              columns of a [T][M] rollout buffer: one thread per column walks t
+//              from T-1 down to 0, so every load/store of a warp is a coalesced
+//              128 B row segment.  20 algorithmic bytes per (t, column): read
+//              reward, value, done; write advantage, return.  The arithmetic
+//              reproduces torch's fp32 op order (Python float scalars are rounded
+//              to fp32 before meeting a tensor; float*float stays double), with
+//              explicit _rn intrinsics so nothing contracts into FMA.
+//  pm_adv_norm per-minibatch (adv - mean) / (std_unbiased + 1e-8)
+//              (pacman_mappo_resnet.py:577): one CTA per minibatch, gather by
+//              index, warp-shuffle + shared-memory block reductions.
+#include <cuda_runtime.h>
+
+#include "../../include/pacman_b200.h"
+
+#define GAE_UNROLL 8
+
+__global__ void __launch_bounds__(128) pm_gae_kernel(const float *__restrict__ rew, const float *__restrict__ val,
+                                                     const float *__restrict__ done, const float *__restrict__ last_value,
+                                                     float gamma_f, float gl_f, double gamma_d, float *__restrict__ adv,
+                                                     float *__restrict__ ret, int T, int64_t M) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    // t = T-1 bootstraps from last_value: gamma * next_val is Python float * float (double), then meets a tensor
+    float gv_next = (float)(gamma_d * (double)last_value[m]);
+    bool first = true;
+    float lastgaelam = 0.0f;
+    float v_next = 0.0f;
+    for (int t0 = T - 1; t0 >= 0; t0 -= GAE_UNROLL) {
+        float r[GAE_UNROLL], v[GAE_UNROLL], d[GAE_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GAE_UNROLL; ++u) {           // independent loads first: GAE_UNROLL rows in flight per thread
+            const int t = t0 - u;
+            if (t >= 0) {
+                const size_t o = (size_t)t * M + m;
+                r[u] = __ldcs(rew + o); v[u] = __ldcs(val + o); d[u] = __ldcs(done + o);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < GAE_UNROLL; ++u) {
+            const int t = t0 - u;
+            if (t >= 0) {
+                const float nonterm = __fsub_rn(1.0f, d[u]);
+                const float gv = first ? gv_next : __fmul_rn(gamma_f, v_next);
+                first = false;
+                const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(gv, nonterm)), v[u]);
+                lastgaelam = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl_f, nonterm), lastgaelam));
+                const size_t o = (size_t)t * M + m;
+                __stcs(adv + o, lastgaelam);
+                __stcs(ret + o, __fadd_rn(lastgaelam, v[u]));
+                v_next = v[u];
+            }
+        }
+    }
+}
+
+extern "C" int pm_gae(const float *rew, const float *val, const float *done, const float *last_value, double gamma,
+                      double lam, float *adv, float *ret, int T, int64_t M, pm_stream_t stream) {
+    if (!rew || !val || !done || !last_value || !adv || !ret || T <= 0 || M <= 0) return PM_EINVAL;
+    const unsigned grid = (unsigned)((M + 127) / 128);
+    pm_gae_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rew, val, done, last_value, (float)gamma, (float)(gamma * lam),
+                                                          gamma, adv, ret, T, M);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float x, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();                                    // red[] may still be read from the previous call
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[w];           // same order in every thread -> identical result
+    return s;
+}
+
+__global__ void __launch_bounds__(256) pm_adv_norm_kernel(const float *__restrict__ adv, const int64_t *__restrict__ inds,
+                                                          float *__restrict__ out, int64_t n, int mb) {
+    __shared__ float red[8];
+    const int64_t s = (int64_t)blockIdx.x * mb;
+    const int k = (int)min((int64_t)mb, n - s);
+    float part = 0.f;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) part += adv[inds[s + i]];
+    const float mean = block_sum(part, red) / (float)k;
+    part = 0.f;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) { const float dlt = adv[inds[s + i]] - mean; part += dlt * dlt; }
+    const float var = block_sum(part, red) / (float)(k - 1);
+    const float denom = sqrtf(var) + 1e-8f;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[s + i] = (adv[inds[s + i]] - mean) / denom;
+}
+
+extern "C" int pm_adv_norm(const float *adv, const int64_t *inds, float *out, int64_t n, int mb, pm_stream_t stream) {
+    if (!adv || !inds || !out || n <= 0 || mb <= 1) return PM_EINVAL;
+    const unsigned grid = (unsigned)((n + mb - 1) / mb);
+    pm_adv_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(adv, inds, out, n, mb);
+    return (int)cudaGetLastError();
+}

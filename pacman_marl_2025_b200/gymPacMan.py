@@ -1,0 +1,482 @@
+"""Batched, GPU-resident drop-in for ``gymPacMan.gymPacMan_parallel_env``.
+
+Reference interface: `/root/reference/gymPacMan.py:12-270` (constructor kwargs
+`:15`, ``reset`` `:92-141`, ``step`` `:143-193`, ``get_Observation`` `:195-229`).
+The class keeps those names, argument meanings and return structure; every
+tensor gains a leading env dimension when ``num_envs > 1``:
+
+  ========================  ==========================  =============================
+  reference (1 env, CPU)    here, ``num_envs == 1``      here, ``num_envs == N > 1``
+  ========================  ==========================  =============================
+  obs[k]  f32 [8,H,W]       f32 [8,H,W]   (cuda)         f32 [N,8,H,W]   (cuda)
+  rewards[k]  float         float                        f64 [N]         (cuda)
+  terminations[k]  bool     bool                         bool [N]        (cuda)
+  legal_actions[k]  [int]   [int] (order N,S,E,W,Stop)   uint8 [N] bitmask (bit a)
+  score_change  int         int                          int32 [N]       (cuda)
+  ========================  ==========================  =============================
+
+All rule / observation / reward arithmetic runs in the hand-written sm_100a
+kernels behind the C ABI (``include/pacman_b200.h``); this file only owns
+tensors, argument marshalling and the dict-shaped return values.  There is no
+CPU path: constructing the env without the CUDA library or a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import layout as _layout
+from . import mazeGenerator as _maze
+
+file_path = os.path.dirname(os.path.abspath(__file__)) + "/"
+
+ACTION_NAMES = ["North", "East", "South", "West", "Stop"]
+# Actions.getPossibleActions iterates N, S, E, W, Stop (game.py:295-299,344-348)
+LEGAL_LIST_ORDER = [0, 2, 1, 3, 4]
+
+
+def legal_mask_to_list(mask: int) -> List[int]:
+    """Bitmask (bit a = gym action a) -> the reference's list, in its order."""
+    return [a for a in LEGAL_LIST_ORDER if (int(mask) >> a) & 1]
+
+
+def pack_tables(layouts: Sequence[_layout.Layout]):
+    """Layout objects -> (geom[u32], table[L, LS] u32, has_caps) via the library's host packer."""
+    L = _lib.load()
+    W, H = layouts[0].width, layouts[0].height
+    gw = L.pm_geom_words(W, H)
+    _lib.check(min(gw, 0), "pm_geom_words")
+    geom = np.zeros(gw, np.uint32)
+    _lib.check(L.pm_pack_geom(W, H, geom.ctypes.data), "pm_pack_geom")
+    LS = L.pm_layout_words(W, H)
+    table = np.zeros((len(layouts), LS), np.uint32)
+    has_caps = 0
+    for i, lay in enumerate(layouts):
+        if (lay.width, lay.height) != (W, H):
+            raise ValueError("all layouts of one batch must share the same width and height")
+        text = "".join(lay.layoutText)
+        if len(text) != W * H:
+            raise ValueError("ragged layout text")
+        hc = C.c_int(0)
+        _lib.check(L.pm_pack_layout(text.encode("ascii"), W, H, table[i].ctypes.data, C.byref(hc)), "pm_pack_layout")
+        has_caps |= hc.value
+    return geom, table, has_caps
+
+
+class _AgentStateView:
+    def __init__(self, row, start):
+        self.configuration = _ConfigView((int(row[0]), int(row[1])), ACTION_NAMES[int(row[2])])
+        self.start = _ConfigView(start, "Stop")
+        self.isPacman = bool(row[3])
+        self.scaredTimer = int(row[4])
+        self.numCarrying = int(row[5])
+        self.numReturned = int(row[6])
+
+    def getPosition(self):
+        return self.configuration.pos
+
+    def getDirection(self):
+        return self.configuration.direction
+
+
+class _ConfigView:
+    def __init__(self, pos, direction):
+        self.pos, self.direction = pos, direction
+
+    def getPosition(self):
+        return self.pos
+
+    def getDirection(self):
+        return self.direction
+
+
+class _StateView:
+    """Read-only GameState-like view of env ``n`` (capture.py:101-234 accessors).
+    Pulls the packed device state on first use of each step (one small D2H)."""
+
+    def __init__(self, env, n=0):
+        self._env, self._n = env, n
+        self.data = self
+
+    def _pull(self):
+        e = self._env
+        if e._state_cache_version != e._version:
+            e._state_cache = e.export_state()
+            e._state_cache_version = e._version
+        return e._state_cache
+
+    # GameStateData-ish
+    @property
+    def score(self):
+        return int(self._pull()["score"][self._n])
+
+    @property
+    def agentStates(self):
+        s = self._pull()
+        lay = self._env._layout_of(self._n)
+        return [_AgentStateView(s["agents"][self._n, i], lay.starts[i]) for i in range(4)]
+
+    @property
+    def layout(self):
+        return self._env._layout_of(self._n)
+
+    @property
+    def food(self):
+        lay = self.layout
+        a = self._pull()["food"][self._n].reshape(lay.height, lay.width).T.astype(bool)
+        return _layout.BoolGrid(lay.width, lay.height, a)
+
+    @property
+    def capsules(self):
+        lay = self.layout
+        cells = np.nonzero(self._pull()["caps"][self._n])[0]
+        return [(int(c % lay.width), int(c // lay.width)) for c in cells]
+
+    # GameState-ish
+    def getScore(self):
+        return self.score
+
+    def getAgentState(self, i):
+        return self.agentStates[i]
+
+    def getAgentPosition(self, i):
+        r = self._pull()["agents"][self._n, i]
+        return (int(r[0]), int(r[1]))
+
+    def getNumAgents(self):
+        return 4
+
+    def getWalls(self):
+        return self.layout.walls
+
+    def hasWall(self, x, y):
+        return bool(self.layout.walls[x][y])
+
+    def hasFood(self, x, y):
+        return bool(self.food[x][y])
+
+    def getCapsules(self):
+        return self.capsules
+
+    def _half(self, red):
+        f = self.food
+        half = int(f.width / 2)
+        a = f.array.copy()
+        if red:
+            a[half:, :] = False
+        else:
+            a[:half, :] = False
+        return _layout.BoolGrid(f.width, f.height, a)
+
+    def getRedFood(self):
+        return self._half(True)
+
+    def getBlueFood(self):
+        return self._half(False)
+
+    def getRedCapsules(self):
+        w = self.layout.width
+        return [(x, y) for x, y in self.capsules if x <= w / 2]
+
+    def getBlueCapsules(self):
+        w = self.layout.width
+        return [(x, y) for x, y in self.capsules if x > w / 2]
+
+    def getLegalActions(self, i=0):
+        x, y = self.getAgentPosition(i)
+        walls = self.layout.walls
+        out = []
+        for name, (dx, dy) in (("North", (0, 1)), ("South", (0, -1)), ("East", (1, 0)), ("West", (-1, 0)), ("Stop", (0, 0))):
+            if not walls[x + dx][y + dy]:
+                out.append(name)
+        return out
+
+    def isOnRedTeam(self, i):
+        lay = self.layout
+        return lay.starts[i][0] < lay.width / 2
+
+    def getRedTeamIndices(self):
+        return [i for i in range(4) if self.isOnRedTeam(i)]
+
+    def getBlueTeamIndices(self):
+        return [i for i in range(4) if not self.isOnRedTeam(i)]
+
+    def getInitialAgentPosition(self, i):
+        return self.layout.starts[i]
+
+
+class _GameView:
+    def __init__(self, env):
+        self.state = _StateView(env, 0)
+        self.length = env.length
+
+
+class gymPacMan_parallel_env:
+    metadata = {"render_modes": [], "name": "b200_capture_v1"}
+
+    def __init__(self, layout_file=f"{file_path}/layouts/smallCapture.lay", display=False, length=299,
+                 reward_forLegalAction=True, defenceReward=True, random_layout=False, enemieName="randomTeam",
+                 self_play=False, *, num_envs: int = 1, device=None, layouts: Optional[Sequence] = None,
+                 shaping_scale: float = 0.1, opponent_seed: int = 0):
+        if display:
+            raise NotImplementedError("display=True (tkinter viewer) is outside the batched GPU path")
+        if not torch.cuda.is_available():
+            raise RuntimeError("pacman_marl_2025_b200 needs a CUDA device; there is no CPU fallback")
+        self._L = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError("num_envs must be >= 1")
+        self.random_layout = random_layout
+        self.enemieName = enemieName
+        self.self_play = self_play
+        self.display = None
+        self.display_bool = False
+        self.reward_forLegalAction = reward_forLegalAction
+        self.defenceReward = defenceReward
+        self.length = length
+        self.shaping_scale = float(shaping_scale)
+        self.num_moves = 0
+        self.steps = 0
+        self.action_mapping = {0: "North", 1: "East", 2: "South", 3: "West", 4: "Stop", "North": "North",
+                               "East": "East", "South": "South", "West": "West", "Stop": "Stop"}
+        self.reversed_action_mapping = {"North": 0, "East": 1, "South": 2, "West": 3, "Stop": 4,
+                                        0: 0, 1: 1, 2: 2, 3: 3, 4: 4}
+        self._name_to_int = {"North": 0, "East": 1, "South": 2, "West": 3, "Stop": 4}
+        # agent keys: ints in self-play (gymPacMan.py:33-40).  Without self-play the red side is driven by an
+        # on-device opponent and still addressed by its index.
+        self.agents = [0, 1, 2, 3]
+        if not self_play and enemieName not in ("randomTeam",):
+            raise NotImplementedError(
+                f"enemieName={enemieName!r}: only the on-device randomTeam opponent exists; CPU bot teams "
+                "(agents/*.py) are outside the GPU path (SURVEY §8 row f1)")
+        self._opponent_seed = int(opponent_seed)
+
+        if layouts is not None:
+            lays = [l if isinstance(l, _layout.Layout) else _layout.Layout(list(l)) for l in layouts]
+        elif os.path.exists(layout_file) and not random_layout:
+            lays = [_layout.getLayout(layout_file)]
+        else:
+            lays = [_layout.Layout(_maze.randomLayout().split("\n"))]
+        self._install_layouts(lays)
+        self._version = 0
+        self._state_cache_version = -1
+        self._state_cache = None
+        self.game = _GameView(self)
+        self.reset()
+        self.max_score = int(self.game.state.getBlueFood().count())
+
+    # ------------------------------------------------------------------ setup
+    def _install_layouts(self, lays: List[_layout.Layout]):
+        self._layouts = lays
+        self.layout = lays[0]
+        W, H = self.layout.width, self.layout.height
+        geom, table, has_caps = pack_tables(lays)
+        dev = self.device
+        self._geom = torch.from_numpy(geom.view(np.int32)).to(dev)
+        self._table = torch.from_numpy(table.view(np.int32)).to(dev)
+        N = self.num_envs
+        nbytes = int(self._L.pm_state_bytes(W, H, N))
+        self._state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self._desc = _lib.PmEnvDesc(W, H, len(lays), int(has_caps), N, self._geom.data_ptr(), self._table.data_ptr(),
+                                    None, self._state.data_ptr(), int(self.length), int(bool(self.reward_forLegalAction)),
+                                    int(bool(self.defenceReward)), 0 if self.self_play else 0b0101,
+                                    self.shaping_scale, int(self._opponent_seed))
+        self.obs_shape = (8, H, W)
+        self._obs = torch.empty((4, N, 8, H, W), dtype=torch.float32, device=dev)
+        self._reward = torch.zeros((2, N), dtype=torch.float64, device=dev)
+        self._done = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._legal = torch.zeros((N, 4), dtype=torch.uint8, device=dev)
+        self._score_change = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._shaping = torch.zeros((4, N), dtype=torch.float64, device=dev)
+        self._shaped = torch.zeros((4, N), dtype=torch.float32, device=dev)
+        self._step_out = _lib.PmStepOut(self._obs.data_ptr(), self._obs[0].numel(), self._reward.data_ptr(),
+                                        self._done.data_ptr(), self._legal.data_ptr(), self._score_change.data_ptr(),
+                                        self._shaping.data_ptr(), self._shaped.data_ptr())
+
+    def _layout_of(self, n):
+        return self._layouts[n % len(self._layouts)]
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------ batched API
+    def reset_batched(self, mask: Optional[torch.Tensor] = None):
+        """Reset every env (mask None) or the envs with mask[n] != 0.  Returns
+        (obs [4,N,8,H,W], legal [N,4] bitmasks); rows of envs that were not
+        reset keep their previous contents."""
+        mptr = None
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            mptr = mask.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_reset(C.byref(self._desc), mptr, self._obs.data_ptr(), self._obs[0].numel(),
+                                        self._legal.data_ptr(), self._stream()), "pm_reset")
+        self._version += 1
+        return self._obs, self._legal
+
+    def step_batched(self, actions: torch.Tensor):
+        """actions: [N,4] uint8 or int64 on the env's device.  Returns a dict of
+        views of the env's output buffers (overwritten by the next call)."""
+        if actions.device != self.device:
+            actions = actions.to(self.device, non_blocking=True)
+        if actions.dtype not in (torch.uint8, torch.int64):
+            actions = actions.to(torch.int64)
+        actions = actions.contiguous()
+        if actions.numel() != 4 * self.num_envs:
+            raise ValueError(f"expected {self.num_envs}x4 actions, got {tuple(actions.shape)}")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_step(C.byref(self._desc), actions.data_ptr(), actions.element_size(),
+                                       C.byref(self._step_out), self._stream()), "pm_step")
+        self._version += 1
+        self.steps += 1
+        return dict(obs=self._obs, reward=self._reward, done=self._done, legal=self._legal,
+                    score_change=self._score_change, shaping=self._shaping, shaped_reward=self._shaped)
+
+    def step_host(self, actions_host: torch.Tensor, want_obs: bool = False):
+        """One step with HOST buffers through the C ABI's ``pm_step_host``: ``actions_host``
+        is a CPU uint8 [N,4] tensor (pinned memory makes the copy asynchronous);
+        rewards / done / legal / score_change / shaped rewards come back in pinned
+        host tensors; observations stay in HBM (``self._obs``) unless ``want_obs``.
+        The call returns after the stream has been synchronised."""
+        if actions_host.device.type != "cpu" or actions_host.dtype != torch.uint8 or not actions_host.is_contiguous():
+            raise ValueError("actions_host must be a contiguous CPU uint8 [N,4] tensor")
+        if actions_host.numel() != 4 * self.num_envs:
+            raise ValueError(f"expected {self.num_envs}x4 actions")
+        if not hasattr(self, "_host"):
+            N = self.num_envs
+            pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+            self._host = dict(reward=pin((2, N), torch.float64), done=pin((N,), torch.uint8),
+                              legal=pin((N, 4), torch.uint8), score_change=pin((N,), torch.int32),
+                              shaped_reward=pin((4, N), torch.float32))
+            self._act_dev = torch.empty((N, 4), dtype=torch.uint8, device=self.device)
+            h = self._host
+            self._host_out = _lib.PmStepOut(None, 0, h["reward"].data_ptr(), h["done"].data_ptr(), h["legal"].data_ptr(),
+                                            h["score_change"].data_ptr(), None, h["shaped_reward"].data_ptr())
+        ho = self._host_out
+        if want_obs:
+            if "obs" not in self._host:
+                self._host["obs"] = torch.empty(self._obs.shape, dtype=torch.float32).pin_memory()
+            ho = _lib.PmStepOut(self._host["obs"].data_ptr(), self._obs[0].numel(), ho.reward, ho.done, ho.legal,
+                                ho.score_change, None, ho.shaped_reward)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_step_host(C.byref(self._desc), actions_host.data_ptr(), self._act_dev.data_ptr(),
+                                            C.byref(self._step_out), C.byref(ho), self._stream()), "pm_step_host")
+        self._version += 1
+        self.steps += 1
+        return self._host
+
+    def observe_batched(self, out: Optional[torch.Tensor] = None):
+        """get_Observation for all four agents of every env on the CURRENT state."""
+        if out is None:
+            out = torch.empty_like(self._obs)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_observe(C.byref(self._desc), out.data_ptr(), out[0].numel(), self._stream()),
+                       "pm_observe")
+        return out
+
+    def export_state(self) -> Dict[str, np.ndarray]:
+        """Unpacked copy of the device state (GameState accessors; one D2H)."""
+        N, HW = self.num_envs, self.layout.width * self.layout.height
+        dev = self.device
+        ag = torch.empty((N, 4, 7), dtype=torch.int32, device=dev)
+        food = torch.empty((N, HW), dtype=torch.uint8, device=dev)
+        caps = torch.empty((N, HW), dtype=torch.uint8, device=dev)
+        misc = torch.empty((N, 2), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._L.pm_get_state(C.byref(self._desc), ag.data_ptr(), food.data_ptr(), caps.data_ptr(),
+                                            misc.data_ptr(), self._stream()), "pm_get_state")
+        misc = misc.cpu().numpy()
+        return dict(agents=ag.cpu().numpy(), food=food.cpu().numpy(), caps=caps.cpu().numpy(),
+                    score=misc[:, 0].copy(), steps=misc[:, 1].copy())
+
+    def import_state(self, agents, food, caps, score, steps):
+        """Inverse of :meth:`export_state` (checkpoint restore / crafted test states)."""
+        dev = self.device
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev).contiguous()
+        ag, fo, ca = t(agents, torch.int32), t(food, torch.uint8), t(caps, torch.uint8)
+        misc = t(np.stack([np.asarray(score), np.asarray(steps)], axis=1), torch.int32)
+        with torch.cuda.device(dev):
+            _lib.check(self._L.pm_set_state(C.byref(self._desc), ag.data_ptr(), fo.data_ptr(), ca.data_ptr(),
+                                            misc.data_ptr(), self._stream()), "pm_set_state")
+            torch.cuda.current_stream(dev).synchronize()
+        self._version += 1
+
+    # -------------------------------------------------------- reference API
+    def _legal_dict(self):
+        if self.num_envs == 1:
+            m = self._legal[0].cpu().tolist()
+            return {self.agents[i]: legal_mask_to_list(m[i]) for i in range(4)}
+        return {self.agents[i]: self._legal[:, i] for i in range(4)}
+
+    def _obs_dict(self):
+        if self.num_envs == 1:
+            return {self.agents[i]: self._obs[i, 0].clone() for i in range(4)}
+        return {self.agents[i]: self._obs[i].clone() for i in range(4)}
+
+    def reset(self, layout_file="None", enemieName="None", mask=None):
+        """gymPacMan.reset (gymPacMan.py:92-141).  ``mask`` (batched extension)
+        resets only the selected envs."""
+        self.steps = 0
+        self.num_moves = 0
+        new_lays = None
+        if os.path.exists(layout_file):
+            new_lays = [_layout.getLayout(layout_file)]
+        if self.random_layout:
+            new_lays = [_layout.Layout(_maze.randomLayout().split("\n"))]
+        if new_lays is not None:
+            self._install_layouts(new_lays)
+        if enemieName != "None":
+            if not self.self_play and enemieName != "randomTeam":
+                raise NotImplementedError(f"enemieName={enemieName!r} is outside the GPU path")
+            self.enemieName = enemieName
+        self.reset_batched(mask)
+        return self._obs_dict(), {"legal_actions": self._legal_dict()}
+
+    def _gather_actions(self, actions) -> torch.Tensor:
+        N = self.num_envs
+        if isinstance(actions, torch.Tensor) and actions.dim() == 2:
+            a = actions
+        else:
+            cols = []
+            for i in range(4):
+                if not self.self_play and i in (0, 2):
+                    cols.append(None)
+                    continue
+                v = actions[self.agents[i]]
+                if isinstance(v, str):
+                    v = self._name_to_int[v]
+                if isinstance(v, torch.Tensor):
+                    cols.append(v.to(self.device).reshape(N).to(torch.int64))
+                else:
+                    cols.append(torch.full((N,), int(v), dtype=torch.int64, device=self.device))
+            zero = torch.zeros((N,), dtype=torch.int64, device=self.device)
+            a = torch.stack([c if c is not None else zero for c in cols], dim=1)   # bot columns are ignored in-kernel
+        return a
+
+    def step(self, actions):
+        """gymPacMan.step (gymPacMan.py:143-193)."""
+        out = self.step_batched(self._gather_actions(actions))
+        obs = self._obs_dict()
+        if self.num_envs == 1:
+            rew = out["reward"][:, 0].cpu().tolist()
+            done = bool(out["done"][0].item())
+            rewards = {self.agents[i]: rew[i & 1] for i in range(4)}
+            terms = {self.agents[i]: done for i in range(4)}
+            sc = int(out["score_change"][0].item())
+        else:
+            rewards = {self.agents[i]: out["reward"][i & 1].clone() for i in range(4)}
+            d = out["done"].bool()
+            terms = {self.agents[i]: d for i in range(4)}
+            sc = out["score_change"].clone()
+        return obs, rewards, terms, {"legal_actions": self._legal_dict(), "score_change": sc}
+
+    def get_Observation(self, agentIndex):
+        """gymPacMan.get_Observation (gymPacMan.py:195-229) on the current state."""
+        o = self.observe_batched()
+        return o[agentIndex, 0].clone() if self.num_envs == 1 else o[agentIndex].clone()

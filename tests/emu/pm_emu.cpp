@@ -1,0 +1,105 @@
+// pm_emu.cpp — TEST-ONLY host emulation of the CUDA kernels' CTA choreography.
+//
+// Compiles the very same per-thread phase functions the sm_100a kernels run
+// (pacman_marl_2025_b200/csrc/pm_env_core.cuh) with g++ and executes them
+// "one CTA at a time, one thread at a time" on host memory, so the kernel logic
+// can be replayed against the golden fixtures in the GPU-less CI container.
+// It is never loaded by the product package: the product path has no CPU
+// fallback and fails loudly without the CUDA library.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../include/pacman_b200.h"
+#include "../../pacman_marl_2025_b200/csrc/pm_env_core.cuh"
+
+static const int EMU_THREADS = 256;
+
+static int fill(const pm_env_desc *d, PmParams &P, int E, int KB) {
+    memset(&P, 0, sizeof(P));
+    P.W = d->W; P.H = d->H; P.HW = d->W * d->H; P.NW = pm_nw(P.HW); P.NCAT = pm_ncat(P.HW);
+    P.ND = pm_nd(P.W, P.H); P.LS = pm_layout_words_(P.HW);
+    P.L = d->n_layouts; P.has_caps = d->has_caps != 0; P.N = d->n_envs;
+    P.geom = d->geom; P.layouts = d->layouts; P.layout_id = d->layout_id; P.state = (uint8_t *)d->state;
+    P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
+    P.shaping_scale = d->shaping_scale;
+    P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
+    P.E = E; P.KB = KB; P.lgE = 0;
+    while ((1 << P.lgE) < E) ++P.lgE;
+    return 0;
+}
+
+template <int MODE>
+static void run(const PmParams &P) {
+    const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, P.E, P.KB, P.has_caps, P.L);
+    std::vector<uint32_t> smv((size_t)M.total + 4);
+    uint32_t *sm = smv.data();
+    const uint32_t magic = (uint32_t)((0x100000000ull / (uint64_t)P.NCAT) + 1);
+    const int64_t nblk = (P.N + P.E - 1) / P.E;
+    for (int64_t b = 0; b < nblk; ++b) {
+        std::fill(smv.begin(), smv.end(), 0xdeadbeefu);            // catch reads of unwritten smem
+        const int64_t n0 = b * P.E;
+        for (int t = 0; t < 16; ++t) {
+            float *v = reinterpret_cast<float *>(sm + M.lut) + 4 * t;
+            v[0] = (t & 1) ? 1.f : 0.f; v[1] = (t & 2) ? 1.f : 0.f; v[2] = (t & 4) ? 1.f : 0.f; v[3] = (t & 8) ? 1.f : 0.f;
+        }
+        for (int i = 0; i < 4 * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
+        if (P.L == 1) for (int i = 0; i < P.LS; ++i) sm[M.lay + i] = P.layouts[i];
+        for (int el = 0; el < P.E; ++el) {
+            if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, M, el, n0);
+            else pm_phaseA_static<MODE>(P, sm, M, el, n0);
+        }
+        if (!P.obs) continue;
+        for (int k0 = 0; k0 < 4; k0 += P.KB) {
+            for (int tid = 0; tid < EMU_THREADS; ++tid) pm_phaseB1<MODE>(P, sm, M, tid, EMU_THREADS, magic, k0);
+            for (int w = 0; w < EMU_THREADS / 32; ++w)
+                for (int lane = 0; lane < 32; ++lane) pm_phaseB2(P, sm, M, w, EMU_THREADS / 32, lane, n0, k0);
+        }
+    }
+}
+
+extern "C" int emu_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, int64_t stride, uint8_t *legal, int E, int KB) {
+    PmParams P; fill(d, P, E, KB);
+    P.mask = mask; P.obs = obs; P.obs_agent_stride = stride; P.legal = legal;
+    run<PM_MODE_RESET>(P);
+    return 0;
+}
+extern "C" int emu_observe(const pm_env_desc *d, float *obs, int64_t stride, int E, int KB) {
+    PmParams P; fill(d, P, E, KB);
+    P.obs = obs; P.obs_agent_stride = stride;
+    run<PM_MODE_OBSERVE>(P);
+    return 0;
+}
+extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize, const pm_step_out *out, int E, int KB) {
+    PmParams P; fill(d, P, E, KB);
+    P.actions = actions; P.act_size = itemsize;
+    P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
+    P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
+    P.shaping = out->shaping; P.shaped = out->shaped_reward;
+    run<PM_MODE_STEP>(P);
+    return 0;
+}
+// host mirror of pm_get_state_kernel
+extern "C" int emu_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc) {
+    PmParams P; fill(d, P, 64, 4);
+    const int64_t NP = pm_np(P.N);
+    for (int64_t n = 0; n < P.N; ++n) {
+        const pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
+        const pm_u4 B = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agB(P.N))[n];
+        const pm_u4 Mi = reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n];
+        const uint32_t a[4] = {A.x, A.y, A.z, A.w}, b[4] = {B.x, B.y, B.z, B.w};
+        for (int i = 0; i < 4; ++i) {
+            int32_t *o = agents + (n * 4 + i) * 7;
+            o[0] = a[i] & 0xff; o[1] = (a[i] >> 8) & 0xff; o[2] = (a[i] >> 16) & 7; o[3] = (a[i] >> 19) & 1;
+            o[4] = (a[i] >> 20) & 0xff; o[5] = b[i] & 0xffff; o[6] = b[i] >> 16;
+        }
+        misc[2 * n] = (int32_t)Mi.x; misc[2 * n + 1] = (int32_t)Mi.y;
+        const uint32_t *gfood = reinterpret_cast<const uint32_t *>(P.state + pm_st_food(P.N));
+        const uint32_t *gcaps = reinterpret_cast<const uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
+        for (int c = 0; c < P.HW; ++c) {
+            food[n * P.HW + c] = (gfood[(size_t)(c >> 5) * NP + n] >> (c & 31)) & 1;
+            caps[n * P.HW + c] = (gcaps[(size_t)(c >> 5) * NP + n] >> (c & 31)) & 1;
+        }
+    }
+    return 0;
+}

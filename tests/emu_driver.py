@@ -1,0 +1,115 @@
+"""TEST-ONLY numpy driver of tests/emu/libpm_emu.so (host emulation of the CUDA
+kernels' per-thread logic, see tests/emu/pm_emu.cpp).  Not a product path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pacman_marl_2025_b200 import _lib as pmlib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "emu", "pm_emu.cpp")
+_SO = os.path.join(_HERE, "emu", "libpm_emu.so")
+_CSRC = os.path.join(os.path.dirname(_HERE), "pacman_marl_2025_b200", "csrc")
+_L = None
+
+
+def lib():
+    global _L
+    if _L is None:
+        deps = [_SRC] + [os.path.join(_CSRC, f) for f in ("pm_env_core.cuh", "pm_format.h", "pm_pack.cpp")]
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(d) for d in deps):
+            subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared",
+                                   "-Wno-unknown-pragmas", "-o", _SO, _SRC, os.path.join(_CSRC, "pm_pack.cpp")])
+        _L = pmlib.declare_pack_api(C.CDLL(_SO))
+    return _L
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class EmuEnv:
+    def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True,
+                 shaping_scale=0.1, E=64, KB=4, layout_id=None, random_agent_mask=0, random_seed=0):
+        L = lib()
+        per_env = not isinstance(layouts[0], str)
+        lays = layouts if per_env else [layouts]
+        self.W, self.H = len(lays[0][0]), len(lays[0])
+        self.N, self.E, self.KB = int(n_envs), E, KB
+        self.geom = np.zeros(L.pm_geom_words(self.W, self.H), np.uint32)
+        assert L.pm_pack_geom(self.W, self.H, _p(self.geom)) == 0
+        LS = L.pm_layout_words(self.W, self.H)
+        self.layouts = np.zeros((len(lays), LS), np.uint32)
+        has_caps = 0
+        for i, rows in enumerate(lays):
+            hc = C.c_int(0)
+            rc = L.pm_pack_layout("".join(rows).encode(), self.W, self.H, _p(self.layouts[i]), C.byref(hc))
+            assert rc == 0, rc
+            has_caps |= hc.value
+        self.state = np.zeros(L.pm_state_bytes(self.W, self.H, self.N), np.uint8)
+        self.layout_id = None if layout_id is None else np.ascontiguousarray(layout_id, np.uint32)
+        self.desc = pmlib.PmEnvDesc(self.W, self.H, len(lays), has_caps, self.N, self.geom.ctypes.data,
+                                    self.layouts.ctypes.data,
+                                    None if self.layout_id is None else self.layout_id.ctypes.data,
+                                    self.state.ctypes.data, int(length), int(reward_forLegalAction),
+                                    int(defenceReward), int(random_agent_mask), float(shaping_scale), int(random_seed))
+        self.obs_shape = (8, self.H, self.W)
+
+    def reset(self, mask=None):
+        obs = np.full((4, self.N) + self.obs_shape, np.nan, np.float32)
+        legal = np.zeros((self.N, 4), np.uint8)
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+        lib().emu_reset(C.byref(self.desc), _p(m), _p(obs), C.c_int64(obs[0].size), _p(legal), self.E, self.KB)
+        return obs, legal
+
+    def observe(self):
+        obs = np.full((4, self.N) + self.obs_shape, np.nan, np.float32)
+        lib().emu_observe(C.byref(self.desc), _p(obs), C.c_int64(obs[0].size), self.E, self.KB)
+        return obs
+
+    def step(self, actions, dtype=np.uint8):
+        a = np.ascontiguousarray(np.asarray(actions).reshape(self.N, 4), dtype)
+        o = dict(obs=np.full((4, self.N) + self.obs_shape, np.nan, np.float32), reward=np.zeros((2, self.N)),
+                 done=np.zeros(self.N, np.uint8), legal=np.zeros((self.N, 4), np.uint8),
+                 score_change=np.zeros(self.N, np.int32), shaping=np.zeros((4, self.N)),
+                 shaped=np.zeros((4, self.N), np.float32))
+        so = pmlib.PmStepOut(o["obs"].ctypes.data, o["obs"][0].size, o["reward"].ctypes.data, o["done"].ctypes.data,
+                             o["legal"].ctypes.data, o["score_change"].ctypes.data, o["shaping"].ctypes.data,
+                             o["shaped"].ctypes.data)
+        lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
+        return o
+
+    def get_state(self):
+        HW = self.W * self.H
+        ag = np.zeros((self.N, 4, 7), np.int32)
+        food = np.zeros((self.N, HW), np.uint8)
+        caps = np.zeros((self.N, HW), np.uint8)
+        misc = np.zeros((self.N, 2), np.int32)
+        lib().emu_get_state(C.byref(self.desc), _p(ag), _p(food), _p(caps), _p(misc))
+        return dict(agents=ag, food=food, caps=caps, score=misc[:, 0], steps=misc[:, 1])
+
+
+class SingleEnvDriver:
+    """Adapts a batched env (emu or CUDA) to helpers.replay, looking at env `n`
+    of the batch while every env receives the same actions."""
+
+    def __init__(self, env, n=0):
+        self.env, self.n = env, n
+
+    def reset(self):
+        obs, legal = self.env.reset()
+        return np.asarray(obs)[:, self.n], np.asarray(legal)[self.n]
+
+    def step(self, a):
+        o = self.env.step(np.tile(np.asarray(a, np.uint8), (self.env.N, 1)))
+        n = self.n
+        return dict(obs=np.asarray(o["obs"])[:, n], reward=np.asarray(o["reward"])[:, n], done=o["done"][n],
+                    legal=np.asarray(o["legal"])[n], score_change=o["score_change"][n],
+                    shaping=np.asarray(o["shaping"])[:, n], shaped=np.asarray(o["shaped"])[:, n])
+
+    def state(self):
+        s = self.env.get_state()
+        n = self.n
+        return dict(agents=s["agents"][n], food=s["food"][n], caps=s["caps"][n], score=int(s["score"][n]))

@@ -1,0 +1,134 @@
+"""Backend-agnostic bodies of the batched parity tests.  `make_env(layouts, n_envs,
+**kw)` returns an object with reset(mask) / step(actions, dtype) / get_state()
+returning numpy arrays: tests/emu_driver.EmuEnv (host emulation of the kernel
+logic, CPU CI) or tests/test_gpu_parity.CudaEnv (the real C ABI on a B200)."""
+import os
+
+import numpy as np
+
+import helpers
+from oracle import oracle
+
+LAYDIR = os.path.join(os.path.dirname(helpers.GOLDEN), "..", "pacman_marl_2025_b200", "layouts")
+
+
+def lay_rows(name):
+    return [ln.strip() for ln in open(os.path.join(LAYDIR, name + ".lay"))]
+
+
+def biased_actions(rng, N, p_forward=0.45, t=None):
+    """Random actions that drift red east and blue west so teams meet, eat and die;
+    with `t`, every env alternates raid / retreat phases so pellets get returned."""
+    a = rng.integers(0, 5, size=(N, 4))
+    p_home = 0.12
+    if t is not None and (t % 50) >= 30:
+        p_forward, p_home = 0.08, 0.6
+    fwd = rng.random((N, 4)) < p_forward
+    a[:, 0::2] = np.where(fwd[:, 0::2], 1, a[:, 0::2])
+    a[:, 1::2] = np.where(fwd[:, 1::2], 3, a[:, 1::2])
+    home = rng.random((N, 4)) < p_home
+    a[:, 0::2] = np.where(home[:, 0::2], 3, a[:, 0::2])
+    a[:, 1::2] = np.where(home[:, 1::2], 1, a[:, 1::2])
+    return a.astype(np.uint8)
+
+
+def compare_batch(o, ref, t, obs_envs):
+    np.testing.assert_array_equal(o["reward"].view(np.uint64), ref["reward"].T.copy().view(np.uint64), err_msg=f"t={t} reward")
+    np.testing.assert_array_equal(o["done"], ref["done"], err_msg=f"t={t} done")
+    np.testing.assert_array_equal(o["legal"], ref["legal"], err_msg=f"t={t} legal")
+    np.testing.assert_array_equal(o["score_change"], ref["score_change"], err_msg=f"t={t} score_change")
+    np.testing.assert_array_equal(o["shaping"].view(np.uint64), ref["shaping"].T.copy().view(np.uint64), err_msg=f"t={t} shaping")
+    want = (2.0 * ref["reward"][:, [0, 1, 0, 1]] + 0.1 * ref["shaping"]).astype(np.float32).T
+    np.testing.assert_array_equal(o["shaped"].view(np.uint32), want.copy().view(np.uint32), err_msg=f"t={t} shaped")
+    for n in obs_envs:
+        np.testing.assert_array_equal(o["obs"][:, n], ref["obs"][n], err_msg=f"t={t} obs env {n}")
+
+
+def body_large_batch(make_env, layname, N, T, length, state_stride=101, obs_stride=37):
+    """Many envs with independent action streams, reset-by-mask after done, every
+    output compared with the oracle at every step."""
+    rows = lay_rows(layname)
+    rng = np.random.default_rng(sum(map(ord, layname)))
+    env = make_env(rows, N, length=length)
+    ref = oracle.OracleBatch(rows, N, length=length)
+    obs, legal = env.reset()
+    robs, rlegal = ref.reset()
+    np.testing.assert_array_equal(legal, rlegal)
+    np.testing.assert_array_equal(obs.transpose(1, 0, 2, 3, 4), robs)
+    events = dict(done=0, score=0)
+    for t in range(T):
+        a = biased_actions(rng, N, 0.6, t)
+        o = env.step(a)
+        r = ref.step(a, with_obs=True, nthreads=0)
+        compare_batch(o, r, t, range(N) if t % 16 == 0 else range(0, N, obs_stride))
+        events["done"] += int(o["done"].sum())
+        events["score"] += int((o["score_change"] != 0).sum())
+        if t % 20 == 0 or t == T - 1:
+            s = env.get_state()
+            for n in range(0, N, state_stride):
+                rs = ref.state(n)
+                np.testing.assert_array_equal(s["agents"][n], rs["agents"])
+                np.testing.assert_array_equal(s["food"][n], rs["food"])
+                assert s["score"][n] == rs["score"] and s["steps"][n] == rs["steps"]
+        d = o["done"].astype(bool)
+        if d.any():
+            obs2, legal2 = env.reset(mask=d)
+            idx = np.nonzero(d)[0]
+            for n in idx:
+                ref.reset_one(int(n))
+            ro, rl = ref.reset_outputs_for(idx)
+            np.testing.assert_array_equal(legal2[d], rl)
+            np.testing.assert_array_equal(obs2[:, d].transpose(1, 0, 2, 3, 4), ro)
+    assert events["done"] > 0 and events["score"] > 0, events
+
+
+def body_per_env_mazes(make_env, N, T):
+    """BASELINE config 4: one mazeGenerator board per env (L = N)."""
+    from pacman_marl_2025_b200 import mazeGenerator
+    mazes = [mazeGenerator.generateMaze(1000 + s).split("\n") for s in range(N)]
+    env = make_env(mazes, N, length=100)
+    ref = oracle.OracleBatch(mazes, N, length=100)
+    obs, legal = env.reset()
+    robs, rlegal = ref.reset()
+    np.testing.assert_array_equal(legal, rlegal)
+    np.testing.assert_array_equal(obs.transpose(1, 0, 2, 3, 4), robs)
+    rng = np.random.default_rng(5)
+    for t in range(T):
+        a = biased_actions(rng, N, 0.6)
+        o = env.step(a)
+        r = ref.step(a, with_obs=True, nthreads=0, auto_reset=True)
+        compare_batch(o, r, t, range(N))
+        d = o["done"].astype(bool)
+        if d.any():
+            env.reset(mask=d)
+
+
+def body_int64_out_of_range(make_env):
+    rows = lay_rows("smallCapture")
+    N = 64
+    env = make_env(rows, N)
+    ref = oracle.OracleBatch(rows, N)
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(3)
+    for t in range(40):
+        a = rng.integers(-2, 8, size=(N, 4))
+        o = env.step(a, dtype=np.int64)
+        r = ref.step(a, with_obs=True)
+        compare_batch(o, r, t, range(N))
+
+
+def body_observe_current_state(make_env):
+    rows = lay_rows("smallCapture")
+    N = 33
+    env = make_env(rows, N)
+    ref = oracle.OracleBatch(rows, N)
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(9)
+    for t in range(25):
+        a = biased_actions(rng, N, 0.7)
+        env.step(a); ref.step(a, with_obs=False)
+    cur = env.observe()
+    for n in range(N):
+        for i in range(4):
+            np.testing.assert_array_equal(cur[i, n], ref.observe(n, i))
+    return env, rng

@@ -1,0 +1,245 @@
+"""Parity tests proper: the CUDA path through the C ABI (libpacman_b200.so) vs
+the golden fixtures recorded from the reference and vs the CPU oracle on the
+same seeded inputs.  Bit-exact for integer state, masks, fp64 rewards, fp32 obs
+and GAE; 1e-5 for advantage normalisation.  Run on the B200 box: -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from emu_driver import SingleEnvDriver
+from parity_bodies import (biased_actions, body_int64_out_of_range, body_large_batch, body_observe_current_state,
+                           body_per_env_mazes, lay_rows, LAYDIR)
+
+pytestmark = pytest.mark.gpu
+
+class CudaEnv:
+    """Thin numpy-returning adapter over the product class (same surface as tests/emu_driver.EmuEnv)."""
+
+    def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True, **kw):
+        from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+        per_env = not isinstance(layouts[0], str)
+        lays = layouts if per_env else [layouts]
+        self.env = gymPacMan_parallel_env(length=length, reward_forLegalAction=reward_forLegalAction,
+                                          defenceReward=defenceReward, self_play=True, num_envs=n_envs,
+                                          layouts=lays, **kw)
+        self.N = n_envs
+
+    def reset(self, mask=None):
+        m = None if mask is None else torch.as_tensor(np.asarray(mask, np.uint8))
+        obs, legal = self.env.reset_batched(m)
+        return obs.cpu().numpy(), legal.cpu().numpy()
+
+    def step(self, actions, dtype=np.uint8):
+        a = torch.as_tensor(np.ascontiguousarray(np.asarray(actions).reshape(self.N, 4), dtype)).cuda()
+        o = self.env.step_batched(a)
+        return dict(obs=o["obs"].cpu().numpy(), reward=o["reward"].cpu().numpy(), done=o["done"].cpu().numpy(),
+                    legal=o["legal"].cpu().numpy(), score_change=o["score_change"].cpu().numpy(),
+                    shaping=o["shaping"].cpu().numpy(), shaped=o["shaped_reward"].cpu().numpy())
+
+    def get_state(self):
+        return self.env.export_state()
+
+    def observe(self):
+        return self.env.observe_batched().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", helpers.traj_names())
+def test_cuda_matches_reference_fixture(name):
+    fx = helpers.load_traj(name)
+    env = CudaEnv(fx["layout"], 3, length=int(fx["length"]), reward_forLegalAction=bool(fx["reward_forLegalAction"]),
+                  defenceReward=bool(fx["defenceReward"]))
+    helpers.replay(fx, SingleEnvDriver(env, n=2), where=name)
+
+
+@pytest.mark.parametrize("layname,N,T,length", [("tinyCapture", 2048, 140, 60), ("smallCapture", 4096, 310, 300),
+                                                ("bloxCapture", 1024, 130, 120)])
+def test_large_batch_vs_oracle(layname, N, T, length):
+    body_large_batch(CudaEnv, layname, N, T, length)
+
+
+def test_per_env_distinct_mazes_vs_oracle():
+    body_per_env_mazes(CudaEnv, 96, 150)
+
+
+def test_int64_actions_and_out_of_range():
+    body_int64_out_of_range(CudaEnv)
+
+
+def test_observe_current_state_and_set_state_roundtrip():
+    env, rng = body_observe_current_state(CudaEnv)
+    s = env.get_state()
+    env2 = CudaEnv(lay_rows("smallCapture"), env.N)
+    env2.env.import_state(s["agents"], s["food"], s["caps"], s["score"], s["steps"])
+    s2 = env2.get_state()
+    for k in s:
+        np.testing.assert_array_equal(s[k], s2[k])
+    a = biased_actions(rng, env.N)
+    o1, o2 = env.step(a), env2.step(a)
+    for k in ("obs", "reward", "done", "legal", "score_change"):
+        np.testing.assert_array_equal(o1[k], o2[k])
+
+
+def test_step_host_entry_matches_device_entry():
+    """pm_step_host (host buffers, copies inside the call) == pm_step (device buffers)."""
+    rows = lay_rows("tinyCapture")
+    N = 257
+    e1, e2 = CudaEnv(rows, N), CudaEnv(rows, N)
+    e1.reset(); e2.reset()
+    rng = np.random.default_rng(1)
+    for t in range(30):
+        a = biased_actions(rng, N)
+        o1 = e1.step(a)
+        h = e2.env.step_host(torch.as_tensor(a).pin_memory(), want_obs=True)
+        for k in ("obs", "reward", "done", "legal", "score_change"):
+            np.testing.assert_array_equal(h[k].numpy(), o1[k], err_msg=f"t={t} {k}")
+        np.testing.assert_array_equal(h["shaped_reward"].numpy(), o1["shaped"])
+
+
+def test_properties_at_full_size():
+    """BASELINE config 2 size (65,536 envs, smallCapture): size-independent
+    invariants — pellet conservation, legal mask == open neighbours, obs plane
+    sums, and shard invariance (two half batches == one full batch)."""
+    rows = lay_rows("smallCapture")
+    N = 65536
+    env = CudaEnv(rows, N, length=300)
+    half = [CudaEnv(rows, N // 2, length=300) for _ in range(2)]
+    env.reset(); [h.reset() for h in half]
+    from pacman_marl_2025_b200.layout import Layout
+    lay = Layout(rows)
+    walls = lay.walls.array
+    total = lay.totalFood
+    rng = np.random.default_rng(77)
+    for t in range(48):
+        a = biased_actions(rng, N, 0.6)
+        A = torch.as_tensor(a).cuda()
+        o = env.env.step_batched(A)
+        oh = [half[i].env.step_batched(A[i * N // 2:(i + 1) * N // 2].contiguous()) for i in range(2)]
+        for k in ("obs", "reward", "done", "legal", "score_change", "shaped_reward"):
+            full = o[k]
+            cat = torch.cat([oh[0][k], oh[1][k]], dim=1 if k in ("obs", "reward", "shaped_reward") else 0)
+            assert torch.equal(full, cat), f"shard invariance broken for {k} at t={t}"
+        if t % 12 == 11:
+            s = env.get_state()
+            on_board = s["food"].sum(1)
+            carried = s["agents"][:, :, 5].sum(1)
+            returned = s["agents"][:, :, 6].sum(1)
+            np.testing.assert_array_equal(on_board + carried + returned, total)
+            x, y = s["agents"][:, :, 0], s["agents"][:, :, 1]
+            want = ((~walls[x, y + 1]).astype(np.uint8) | (~walls[x + 1, y]).astype(np.uint8) << 1
+                    | (~walls[x, y - 1]).astype(np.uint8) << 2 | (~walls[x - 1, y]).astype(np.uint8) << 3 | 16)
+            np.testing.assert_array_equal(o["legal"].cpu().numpy(), want)
+            obs = o["obs"]
+            assert torch.equal(obs[:, :, 0].sum((2, 3)), torch.full((4, N), float(walls.sum()), device="cuda"))
+            assert torch.equal(obs[:, :, 4].sum((2, 3)), torch.ones((4, N), device="cuda"))
+            food_planes = (obs[3, :, 6] + obs[3, :, 7]).sum((1, 2)).cpu().numpy()
+            np.testing.assert_array_equal(food_planes, on_board)
+
+
+def test_random_team_opponent_in_kernel():
+    """self_play=False: agents 0 and 2 draw uniform legal actions in-kernel (randomTeam).
+    Legal by construction -> the red team always earns the legal-action bonus twice."""
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    N = 512
+    mk = lambda: gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, "smallCapture.lay"), self_play=False,
+                                        num_envs=N, opponent_seed=123)
+    e1, e2 = mk(), mk()
+    g = torch.Generator().manual_seed(0)
+    moved = 0
+    for t in range(50):
+        a = torch.randint(0, 5, (N, 4), generator=g).cuda()
+        p0 = torch.as_tensor(e1.export_state()["agents"][:, 0, :2])
+        o1, o2 = e1.step_batched(a), e2.step_batched(a.clone())
+        assert torch.equal(o1["obs"], o2["obs"])            # counter-based RNG: reproducible
+        assert (o1["reward"][0].cpu().numpy() >= 0.02 - 1e-12).all()     # two legal red moves per step
+        moved += int((torch.as_tensor(e1.export_state()["agents"][:, 0, :2]) != p0).any(1).sum())
+    assert moved > N    # bots do move
+
+
+@pytest.mark.parametrize("name", helpers.dist_names())
+def test_bfs_distances_match_reference(name):
+    from pacman_marl_2025_b200.distanceCalculator import compute_distances, Distancer
+    from pacman_marl_2025_b200.layout import Layout
+    rows, nodes, dist = helpers.load_dist(name)
+    lay = Layout(rows)
+    t = compute_distances([lay])
+    np.testing.assert_array_equal(t.matrix(0), dist)
+    assert int(t.n_open[0]) == len(nodes)
+    node_of = t.node_of_cell[0].cpu().numpy()
+    for i, (x, y) in enumerate(nodes):
+        assert node_of[y * lay.width + x] == i
+    d = Distancer(lay)
+    d.getMazeDistances()
+    a, b = tuple(int(v) for v in nodes[0]), tuple(int(v) for v in nodes[-1])
+    assert d.getDistance(a, b) == dist[0, -1]
+
+
+def test_bfs_batch_of_random_mazes_vs_oracle():
+    from oracle import oracle
+    from pacman_marl_2025_b200 import mazeGenerator
+    from pacman_marl_2025_b200.distanceCalculator import compute_distances
+    from pacman_marl_2025_b200.layout import Layout
+    texts = [mazeGenerator.generateMaze(s).split("\n") for s in range(300, 364)]
+    t = compute_distances([Layout(x) for x in texts])
+    for l in range(0, 64, 7):
+        _, od = oracle.distances(texts[l])
+        np.testing.assert_array_equal(t.matrix(l), od)
+    # symmetry + zero diagonal for every table
+    n = t.n_open.cpu().numpy()
+    D = (t.dist.to(torch.int32) & 0xFFFF)
+    assert torch.equal(D, D.transpose(1, 2))
+    for l in range(64):
+        assert int(torch.diagonal(D[l])[: n[l]].sum()) == 0
+
+
+def test_gae_bit_exact_vs_reference_and_oracle():
+    from oracle import oracle
+    from pacman_marl_2025_b200.mappo_ops import compute_gae
+    z = np.load(helpers.GOLDEN + "/gae.npz")
+    for ci in range(int(z["n_cases"])):
+        adv, ret = compute_gae(torch.as_tensor(z[f"c{ci}_rew"]).cuda(), torch.as_tensor(z[f"c{ci}_val"]).cuda(),
+                               torch.as_tensor(z[f"c{ci}_done"]).cuda(), torch.as_tensor(z[f"c{ci}_last"]).cuda(),
+                               float(z["gamma"]), float(z["lam"]))
+        np.testing.assert_array_equal(adv.cpu().numpy().view(np.uint32), z[f"c{ci}_adv"].view(np.uint32))
+        np.testing.assert_array_equal(ret.cpu().numpy().view(np.uint32), z[f"c{ci}_ret"].view(np.uint32))
+    adv, ret = compute_gae(torch.as_tensor(z["kat_rew"]).cuda(), torch.as_tensor(z["kat_val"]).cuda(),
+                           torch.as_tensor(z["kat_done"]).cuda(), 0.37, 0.99, 0.95)
+    np.testing.assert_array_equal(adv.cpu().numpy().view(np.uint32), z["kat_adv"].view(np.uint32))
+    # rollout-sized case vs the oracle: T = 2048, 4096 columns
+    rng = np.random.default_rng(0)
+    T, M = 2048, 4096
+    r = rng.standard_normal((T, M)).astype(np.float32)
+    v = rng.standard_normal((T, M)).astype(np.float32)
+    d = (rng.random((T, M)) < 0.01).astype(np.float32)
+    lv = rng.standard_normal(M).astype(np.float32)
+    oa, orr = oracle.gae(r, v, d, lv)
+    adv, ret = compute_gae(torch.as_tensor(r).cuda(), torch.as_tensor(v).cuda(), torch.as_tensor(d).cuda(),
+                           torch.as_tensor(lv).cuda())
+    np.testing.assert_array_equal(adv.cpu().numpy().view(np.uint32), oa.view(np.uint32))
+    np.testing.assert_array_equal(ret.cpu().numpy().view(np.uint32), orr.view(np.uint32))
+
+
+def test_adv_norm_vs_reference():
+    from pacman_marl_2025_b200.mappo_ops import normalize_advantages
+    z = np.load(helpers.GOLDEN + "/gae.npz")
+    out = normalize_advantages(torch.as_tensor(z["norm_adv"]).cuda(), torch.as_tensor(z["norm_inds"]).cuda(),
+                               int(z["norm_mb"]))
+    np.testing.assert_allclose(out.cpu().numpy(), z["norm_out"], rtol=1e-5, atol=1e-6)   # north_star tolerance
+
+
+def test_reference_shaped_single_env_api():
+    """num_envs=1 returns the reference's shapes: dict of [8,H,W] tensors, float rewards, bool dones, int lists."""
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    env = gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, "tinyCapture.lay"), self_play=True, length=300)
+    obs, info = env.reset()
+    assert info["legal_actions"] == {0: [1, 3, 4], 1: [1, 4], 2: [3, 4], 3: [1, 3, 4]}
+    assert obs[0].shape == (8, 7, 20) and obs[0].dtype == torch.float32
+    obs, rew, term, info = env.step({0: 1, 1: "East", 2: 1, 3: 1})
+    assert isinstance(rew[0], float) and isinstance(term[0], bool) and isinstance(info["score_change"], int)
+    # obs[0] is a mid-step snapshot (enemies not yet moved)
+    assert obs[0][5].nonzero().tolist() == [[1, 12], [1, 13]]
+    assert env.game.state.getAgentPosition(1) == (13, 1)
+    assert env.game.state.data.score == 0 and env.max_score == 11
+    assert env.get_Observation(0).shape == (8, 7, 20)
