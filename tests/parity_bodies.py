@@ -44,7 +44,7 @@ def compare_batch(o, ref, t, obs_envs):
         np.testing.assert_array_equal(o["obs"][:, n], ref["obs"][n], err_msg=f"t={t} obs env {n}")
 
 
-def body_large_batch(make_env, layname, N, T, length, state_stride=101, obs_stride=37):
+def body_large_batch(make_env, layname, N, T, length, state_stride=101, obs_stride=37, expect_score=True):
     """Many envs with independent action streams, reset-by-mask after done, every
     output compared with the oracle at every step."""
     rows = lay_rows(layname)
@@ -79,7 +79,7 @@ def body_large_batch(make_env, layname, N, T, length, state_stride=101, obs_stri
             ro, rl = ref.reset_outputs_for(idx)
             np.testing.assert_array_equal(legal2[d], rl)
             np.testing.assert_array_equal(obs2[:, d].transpose(1, 0, 2, 3, 4), ro)
-    assert events["done"] > 0 and events["score"] > 0, events
+    assert events["done"] > 0 and (events["score"] > 0 or not expect_score), events
 
 
 def body_per_env_mazes(make_env, N, T):
