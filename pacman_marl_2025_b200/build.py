@@ -39,7 +39,8 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return OUT
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    extra = os.environ.get("PM_NVCC_EXTRA", "").split()      # tuning sweeps: -DPM_CONS_WARPS=.. -DPM_CTAS_PER_SM=..
+    cmd = [nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
           [os.path.join(CSRC, f) for f in SOURCES]
     subprocess.check_call(cmd)
     return OUT

@@ -3,12 +3,15 @@
 // pm_env_core.cuh; this file owns the CTA choreography, launch geometry and the
 // ABI glue (include/pacman_b200.h).
 //
-// CTA choreography (one CTA = E consecutive envs):
+// CTA choreography (one CTA = PM_E consecutive envs, 8 warps):
 //   stage geometry masks (+ the layout record when the batch has one layout)
-//   into shared memory -> phase A (thread el < E steps env n0+el, leaves four
-//   snapshots in smem) -> for each pass of KB agents: phase B1 (all threads
-//   build observation bit-string words) -> phase B2 (each warp streams whole
-//   observations to HBM with 128-bit stores).
+//   into shared memory -> phase A (lane el of warp 0 steps env n0+el and leaves
+//   four snapshots in smem) -> phase B (every warp builds the observation bit
+//   string of one (env, agent) at a time in registers and streams it to HBM as
+//   fp32 planes with 128-bit stores).  Several CTAs are resident per SM, so the
+//   latency-bound phase A of one CTA runs underneath the HBM-bound phase B of
+//   the others.  (A persistent producer/consumer variant with named barriers
+//   was measured slower on B200 at every warp split — DESIGN.md §4.)
 // HBM traffic per env-step: ~2 x (64 + 4*NW) B of state, 4 B actions, ~70 B of
 // small outputs, and 4 * 32*H*W B of observations (98+ % of all bytes).
 #include <cuda_runtime.h>
@@ -20,13 +23,19 @@
 #include "pm_env_core.cuh"
 
 #define PM_THREADS 256
+#ifndef PM_MIN_CTAS
+#define PM_MIN_CTAS 3
+#endif
+#ifndef PM_E
+#define PM_E 32                                   // envs per CTA (power of two <= PM_THREADS)
+#endif
 
 template <int MODE>
-__global__ void __launch_bounds__(PM_THREADS) pm_env_kernel(const PmParams P, const uint32_t magic) {
+__global__ void __launch_bounds__(PM_THREADS, PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
-    const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, P.E, P.KB, P.has_caps, P.L);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L);
     const int tid = threadIdx.x;
-    const int64_t n0 = (int64_t)blockIdx.x * P.E;
+    const int64_t n0 = (int64_t)blockIdx.x * PM_E;
 
     // ---- stage per-batch tables ----
     if (tid < 16) {
@@ -39,21 +48,15 @@ __global__ void __launch_bounds__(PM_THREADS) pm_env_kernel(const PmParams P, co
     __syncthreads();
 
     // ---- phase A: rules, one thread per env ----
-    if (tid < P.E) {
-        if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, M, tid, n0);
-        else pm_phaseA_static<MODE>(P, sm, M, tid, n0);
+    if (tid < PM_E) {
+        if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, sm, M, tid, n0);
+        else pm_phaseA_static<MODE>(P, sm, sm, M, tid, n0);
     }
     if (P.obs == nullptr) return;
     __syncthreads();
 
-    // ---- phase B: observations ----
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int k0 = 0; k0 < 4; k0 += P.KB) {
-        pm_phaseB1<MODE>(P, sm, M, tid, PM_THREADS, magic, k0);
-        __syncthreads();
-        pm_phaseB2(P, sm, M, warp, PM_THREADS / 32, lane, n0, k0);
-        if (k0 + P.KB < 4) __syncthreads();
-    }
+    // ---- phase B: observations, one warp per (env, agent) ----
+    pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
 }
 
 // ---- state export / import (GameState accessors; tests, checkpoints) ---------
@@ -125,24 +128,6 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-// Launch geometry: E envs per CTA and KB agents per observation pass, chosen so
-// that >= 3 CTAs of 256 threads fit in the 227 KB of shared memory per SM.
-// PM_E / PM_KB override (tuning hook used by bench sweeps).
-static void pick_geometry(PmParams &P) {
-    int E = env_int("PM_E", 0), KB = env_int("PM_KB", 0);
-    if (E <= 0) E = 64;
-    if (KB != 1 && KB != 2 && KB != 4) KB = P.NCAT <= 48 ? 4 : 2;
-    while (E > 1 && (E & (E - 1))) E &= E - 1;           // power of two
-    if (E > PM_THREADS) E = PM_THREADS;
-    for (;;) {
-        const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, E, KB, P.has_caps, P.L);
-        if ((size_t)M.total * 4 <= 72 * 1024 || (E <= 8 && KB == 1)) break;
-        if (KB > 1) KB >>= 1; else E >>= 1;
-    }
-    P.E = E; P.KB = KB; P.lgE = 0;
-    while ((1 << P.lgE) < E) ++P.lgE;
-}
-
 static int fill_params(const pm_env_desc *d, PmParams &P) {
     if (!d || !d->geom || !d->layouts || !d->state || d->n_envs <= 0 || d->n_layouts <= 0) return PM_EINVAL;
     if (d->W < 3 || d->H < 3) return PM_EINVAL;
@@ -155,13 +140,14 @@ static int fill_params(const pm_env_desc *d, PmParams &P) {
     P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
     P.shaping_scale = d->shaping_scale;
     P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
-    pick_geometry(P);
+    P.E = PM_E; P.lgE = 0;
+    while ((1 << P.lgE) < PM_E) ++P.lgE;
     return 0;
 }
 
 template <int MODE>
 static int launch_env(const PmParams &P, cudaStream_t st) {
-    const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, P.E, P.KB, P.has_caps, P.L);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L);
     const size_t smem = (size_t)M.total * 4;
     static size_t configured[64][3];                   // per device, per kernel instance
     int dev = 0;
@@ -169,11 +155,14 @@ static int launch_env(const PmParams &P, cudaStream_t st) {
     if (smem > configured[dev & 63][MODE]) {
         cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+        // the kernel streams its output and keeps its working set in shared memory: prefer smem over L1
+        e = cudaFuncSetAttribute(pm_env_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
         configured[dev & 63][MODE] = smem;
     }
-    const uint32_t magic = (uint32_t)((0x100000000ull / (uint64_t)P.NCAT) + 1);
-    const unsigned grid = (unsigned)((P.N + P.E - 1) / P.E);
-    pm_env_kernel<MODE><<<grid, PM_THREADS, smem, st>>>(P, magic);
+    const unsigned grid = (unsigned)((P.N + PM_E - 1) / PM_E);
+    pm_env_kernel<MODE><<<grid, PM_THREADS, smem, st>>>(P);
     return (int)cudaGetLastError();
 }
 

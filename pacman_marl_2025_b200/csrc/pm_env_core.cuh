@@ -10,10 +10,9 @@
 //            compact SNAPSHOT (board bitsets + four cell positions) in shared
 //            memory, because the reference observes agent i right after ITS
 //            sub-move (gymPacMan.py:166).
-//   phase B1 (all threads)          snapshot -> observation bit string words
-//            (see pm_format.h) in shared memory.
-//   phase B2 (one warp per observation) bit string -> fp32 planes with
-//            coalesced 128-bit stores; this is the HBM-bound part.
+//   phase B  (one warp per observation) snapshot -> observation bit string
+//            (see pm_format.h) in registers -> fp32 planes with coalesced
+//            128-bit stores; this is the HBM-bound part.
 //
 // The functions are PM_HD (host + device) on purpose: tests/emu compiles the
 // very same code with g++ and replays the golden fixtures through it without a
@@ -66,7 +65,7 @@ PM_HD uint32_t pm_funnel_r(uint32_t lo, uint32_t hi, int r) {
 struct PmParams {
     int W, H, HW, NW, NCAT, ND, LS;
     int L, has_caps;                    // layouts in table, capsules anywhere
-    int E, lgE, KB;                     // envs per CTA (power of two), log2(E), agents per B pass (1, 2 or 4)
+    int E, lgE;                         // envs per CTA (power of two), log2(E)
     int64_t N;
     const uint32_t *geom, *layouts, *layout_id;
     uint8_t *state;
@@ -81,17 +80,29 @@ struct PmParams {
 };
 
 // ---- shared-memory map (u32 word offsets) ----------------------------------
+// Per-env arrays are [..][E1] with E1 odd, so both the per-env phase (consecutive
+// threads = consecutive envs) and the per-observation phase (consecutive lanes =
+// consecutive words of one env) are bank-conflict free.
+//   food[k], caps[k] : board bitsets (c-indexed, NW words) after sub-move k —
+//                      slot k is the working copy during sub-move k and the
+//                      snapshot agent k is observed from afterwards
+//   posA/posB/patch[k] : the four agent bit positions and the own-cell patch
 struct PmSmem {
-    int lut, masks, lay, lid, posA, posB, patch, food, caps, cat, total;
-    int E1;                             // padded env stride (odd -> conflict-free both ways)
+    int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, food, caps, total;
+    int E1;                             // padded env stride
 };
-PM_HD PmSmem pm_smem_map(int NW, int NCAT, int LS, int E, int KB, int has_caps, int L) {
+PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L) {
+    const int NW = pm_nw(HW), NCAT = pm_ncat(HW);
     PmSmem m;
     m.E1 = E | 1;
     int o = 0;
+    // static tables (one copy per CTA)
     m.lut = o; o += 64;                 // 16 x float4
     m.masks = o; o += 4 * NCAT;
     m.lay = o; o += (L == 1) ? LS : 0;
+    o = (o + 3) & ~3;
+    m.blk0 = o;
+    // per-block buffer
     m.lid = o; o += E;
     m.posA = o; o += 4 * m.E1;
     m.posB = o; o += 4 * m.E1;
@@ -99,7 +110,7 @@ PM_HD PmSmem pm_smem_map(int NW, int NCAT, int LS, int E, int KB, int has_caps, 
     m.food = o; o += 4 * NW * m.E1;
     m.caps = o; o += has_caps ? 4 * NW * m.E1 : 0;
     o = (o + 3) & ~3;
-    m.cat = o; o += KB * E * NCAT;
+    m.blk_words = o - m.blk0;
     m.total = o;
     return m;
 }
@@ -134,6 +145,15 @@ PM_NOINLINE uint32_t pm_dump(int W, int H, int ND, const uint32_t *dumptab, cons
         --todo;
     }
     return added;
+}
+
+// 32 bits of an NW-word bitset (word stride st) starting at bit s; s may be
+// negative or run past the end (missing bits read as zero).
+PM_HD uint32_t pm_extract32(const uint32_t *w, int st, int NW, int s) {
+    const int k = s >> 5, r = s & 31;
+    const uint32_t lo = ((unsigned)k < (unsigned)NW) ? w[k * st] : 0u;
+    const uint32_t hi = ((unsigned)(k + 1) < (unsigned)NW) ? w[(k + 1) * st] : 0u;
+    return pm_funnel_r(lo, hi, r);
 }
 
 // Agents of one env, unpacked into registers (all loops over agents unroll).
@@ -230,12 +250,12 @@ PM_HD void pm_pack_agents(const PmAgents &g, pm_u4 &A, pm_u4 &B) {
 // ============================================================================
 // phase A, MODE_STEP
 // ============================================================================
-PM_HD void pm_phaseA_step(const PmParams &P, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
+PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
     if (n >= P.N) { sm[M.lid + el] = 0xffffffffu; return; }
     const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
     sm[M.lid + el] = lid;
-    const uint32_t *lay = (P.L == 1) ? sm + M.lay : P.layouts + (size_t)lid * P.LS;
+    const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
     const uint32_t *walls = lay + pm_l_walls(P.HW);
     const uint32_t *tail = lay + pm_l_tail(P.HW);
     const uint32_t *dumptab = P.geom + pm_g_dump_off(P.HW);
@@ -413,12 +433,12 @@ PM_HD void pm_phaseA_step(const PmParams &P, uint32_t *sm, const PmSmem &M, int 
 // phase A, MODE_RESET / MODE_OBSERVE: one state, four observations of it
 // ============================================================================
 template <int MODE>
-PM_HD void pm_phaseA_static(const PmParams &P, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
+PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
     if (n >= P.N || (MODE == PM_MODE_RESET && P.mask && !P.mask[n])) { sm[M.lid + el] = 0xffffffffu; return; }
     const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
     sm[M.lid + el] = lid;
-    const uint32_t *lay = (P.L == 1) ? sm + M.lay : P.layouts + (size_t)lid * P.LS;
+    const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
     const uint32_t *tail = lay + pm_l_tail(P.HW);
     const int NW = P.NW, E1 = M.E1, W = P.W;
     const int64_t NP = pm_np(P.N);
@@ -471,78 +491,107 @@ PM_HD void pm_phaseA_static(const PmParams &P, uint32_t *sm, const PmSmem &M, in
 }
 
 // ============================================================================
-// phase B1: snapshot -> observation bit-string words in shared memory
+// phase B: snapshot -> observation planes, one warp per observation ("unit")
 // ============================================================================
-// 32 bits of an NW-word bitset (word stride st) starting at bit s; s may be
-// negative or run past the end (missing bits read as zero).
-PM_HD uint32_t pm_extract32(const uint32_t *w, int st, int NW, int s) {
-    const int k = s >> 5, r = s & 31;
-    const uint32_t lo = ((unsigned)k < (unsigned)NW) ? w[k * st] : 0u;
-    const uint32_t hi = ((unsigned)(k + 1) < (unsigned)NW) ? w[(k + 1) * st] : 0u;
-    return pm_funnel_r(lo, hi, r);
-}
+// Per-observation constants, loaded once per unit.
+struct PmUnit {
+    const uint32_t *food, *caps;                // snapshot bitsets (caps == nullptr: batch has no capsules)
+    uint32_t lid;
+    uint32_t p_own, p_ally, p_e1, p_e2;         // bit positions of the four agents in the bit string
+    uint32_t patch;                             // own-cell element | (1+carrying) << 16, or 0xffffffff
+};
 
 template <int MODE>
-PM_HD void pm_phaseB1(const PmParams &P, uint32_t *sm, const PmSmem &M, int tid, int nthreads, uint32_t magic, int k0) {
-    const int NCAT = P.NCAT, NW = P.NW, HW = P.HW, E = P.E, E1 = M.E1;
-    const int total = P.KB * E * NCAT;
-    const uint32_t *m2 = sm + M.masks, *m3 = m2 + NCAT, *m6 = m3 + NCAT, *m7 = m6 + NCAT;
-    for (int idx = tid; idx < total; idx += nthreads) {
-#if defined(__CUDA_ARCH__)
-        const int u = (int)__umulhi((uint32_t)idx, magic);
-#else
-        const int u = (int)(((uint64_t)(uint32_t)idx * magic) >> 32);
-#endif
-        const int j = idx - u * NCAT;
-        const int k = k0 + (u >> P.lgE), el = u & (E - 1);
-        const uint32_t lid = sm[M.lid + el];
-        if (lid == 0xffffffffu) continue;
-        const uint32_t *lay = (P.L == 1) ? sm + M.lay : P.layouts + (size_t)lid * P.LS;
-        const int slot = (MODE == PM_MODE_STEP) ? k : 0;
-        const uint32_t *food = sm + M.food + (size_t)slot * NW * E1 + el;
-        const int b0 = 32 * j;
-        uint32_t w = lay[pm_l_wallcat(HW) + j];
-        w |= pm_extract32(food, E1, NW, b0 - 6 * HW) & m6[j];
-        w |= pm_extract32(food, E1, NW, b0 - 7 * HW) & m7[j];
-        if (P.has_caps) {
-            const uint32_t *caps = sm + M.caps + (size_t)slot * NW * E1 + el;
-            w |= pm_extract32(caps, E1, NW, b0 - 2 * HW) & m2[j];
-            w |= pm_extract32(caps, E1, NW, b0 - 3 * HW) & m3[j];
-        }
-        const uint32_t pa = sm[M.posA + k * E1 + el], pb = sm[M.posB + k * E1 + el];
-        unsigned d;
-        d = (pa & 0xffff) - (unsigned)b0; if (d < 32u) w |= 1u << d;
-        d = (pa >> 16) - (unsigned)b0;    if (d < 32u) w |= 1u << d;
-        d = (pb & 0xffff) - (unsigned)b0; if (d < 32u) w |= 1u << d;
-        d = (pb >> 16) - (unsigned)b0;    if (d < 32u) w |= 1u << d;
-        sm[M.cat + idx] = w;
-    }
+PM_HD bool pm_unit_load(const PmParams &P, const uint32_t *sm, const PmSmem &M, int k, int el, PmUnit &U) {
+    U.lid = sm[M.lid + el];
+    if (U.lid == 0xffffffffu) return false;
+    const int slot = (MODE == PM_MODE_STEP) ? k : 0;
+    U.food = sm + M.food + (size_t)slot * P.NW * M.E1 + el;
+    U.caps = P.has_caps ? sm + M.caps + (size_t)slot * P.NW * M.E1 + el : nullptr;
+    const uint32_t pa = sm[M.posA + k * M.E1 + el], pb = sm[M.posB + k * M.E1 + el];
+    U.p_own = pa & 0xffff; U.p_ally = pa >> 16; U.p_e1 = pb & 0xffff; U.p_e2 = pb >> 16;
+    U.patch = sm[M.patch + k * M.E1 + el];
+    return true;
 }
 
-// ============================================================================
-// phase B2: bit string -> fp32 planes, one warp per observation
-// ============================================================================
-PM_HD void pm_phaseB2(const PmParams &P, uint32_t *sm, const PmSmem &M, int warp, int nwarps, int lane, int64_t n0, int k0) {
-    const int NCAT = P.NCAT, E = P.E, E1 = M.E1;
+// Word j (bits 32j .. 32j+31) of the observation bit string of one unit:
+// static wall plane | food planes 6,7 | capsule planes 2,3 | the four agent bits.
+PM_HD uint32_t pm_cat_word(const PmParams &P, const uint32_t *st, const PmSmem &M, const PmUnit &U, int j) {
+    const int NCAT = P.NCAT, NW = P.NW, HW = P.HW, E1 = M.E1;
+    const uint32_t *m2 = st + M.masks, *m3 = m2 + NCAT, *m6 = m3 + NCAT, *m7 = m6 + NCAT;
+    const int woff = pm_l_wallcat(HW) + j;
+    uint32_t w;
+    if (P.L == 1) w = st[M.lay + woff];
+    else {
+#if defined(__CUDA_ARCH__)
+        w = __ldg(P.layouts + (size_t)U.lid * P.LS + woff);
+#else
+        w = P.layouts[(size_t)U.lid * P.LS + woff];
+#endif
+    }
+    const int b0 = 32 * j;
+    w |= pm_extract32(U.food, E1, NW, b0 - 6 * HW) & m6[j];
+    w |= pm_extract32(U.food, E1, NW, b0 - 7 * HW) & m7[j];
+    if (U.caps) {
+        w |= pm_extract32(U.caps, E1, NW, b0 - 2 * HW) & m2[j];
+        w |= pm_extract32(U.caps, E1, NW, b0 - 3 * HW) & m3[j];
+    }
+    unsigned d;
+    d = U.p_own - (unsigned)b0;  if (d < 32u) w |= 1u << d;
+    d = U.p_ally - (unsigned)b0; if (d < 32u) w |= 1u << d;
+    d = U.p_e1 - (unsigned)b0;   if (d < 32u) w |= 1u << d;
+    d = U.p_e2 - (unsigned)b0;   if (d < 32u) w |= 1u << d;
+    return w;
+}
+
+// One warp turns whole observations into fp32 planes.  Per group of 32 bit-string
+// words: lane L builds word 32g+L, then 8 store rounds follow in which lane L
+// writes float4 number 256g + 32r + L of the observation; its four floats are
+// nibble (L & 7) of word 32g + 4r + (L >> 3), fetched with one shuffle and turned
+// into a float4 by a 16-entry shared-memory table.  A warp store covers 512
+// contiguous bytes.  The own-cell value 1+numCarrying (gymPacMan.py:205) is
+// patched by one lane after the warp's stores (ordered by __syncwarp).
+template <int MODE>
+PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps, int lane, int64_t n0) {
+    const int NCAT = P.NCAT, E = P.E;
     const int nf4 = 2 * P.HW;                          // float4s per observation (8*HW/4)
-    const pm_f4 *lut = reinterpret_cast<const pm_f4 *>(sm + M.lut);
-    const int sh = (lane & 7) * 4;
-    for (int u = warp; u < P.KB * E; u += nwarps) {
-        const int k = k0 + (u >> P.lgE), el = u & (E - 1);
-        if (sm[M.lid + el] == 0xffffffffu) continue;
-        const uint32_t patch = sm[M.patch + k * E1 + el];
-        const int pf = patch == 0xffffffffu ? -1 : (int)((patch & 0xffff) >> 2);
-        const uint32_t *cat = sm + M.cat + (size_t)u * NCAT;
-        pm_f4 *dst = reinterpret_cast<pm_f4 *>(P.obs + (size_t)k * P.obs_agent_stride + (size_t)(n0 + el) * 8 * P.HW);
-        for (int f = lane; f < nf4; f += 32) {
-            const uint32_t nib = (cat[f >> 3] >> sh) & 15u;
-            pm_f4 v = lut[nib];
-            if (f == pf) {                             // own cell carries 1 + numCarrying (gymPacMan.py:205)
-                const float val = (float)(patch >> 16);
-                const int comp = patch & 3;
-                if (comp == 0) v.x = val; else if (comp == 1) v.y = val; else if (comp == 2) v.z = val; else v.w = val;
+    const pm_f4 *lut = reinterpret_cast<const pm_f4 *>(st + M.lut);
+    const int ngroups = (NCAT + 31) >> 5;
+    for (int u = warp; u < 4 * E; u += nwarps) {
+        const int k = u >> P.lgE, el = u & (E - 1);
+        PmUnit U;
+        if (!pm_unit_load<MODE>(P, sm, M, k, el, U)) continue;
+        float *dstf = P.obs + (size_t)k * P.obs_agent_stride + (size_t)(n0 + el) * 8 * P.HW;
+        pm_f4 *dst = reinterpret_cast<pm_f4 *>(dstf);
+#if defined(__CUDA_ARCH__)
+        const int sh = (lane & 7) * 4, src = lane >> 3;
+        for (int g = 0; g < ngroups; ++g) {
+            const int j = 32 * g + lane;
+            const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
+            const int fbase = 256 * g + lane;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t w = __shfl_sync(0xffffffffu, word, 4 * r + src);
+                const int f = fbase + 32 * r;
+                if (f < nf4) dst[f] = lut[(w >> sh) & 15u];
             }
-            dst[f] = v;
         }
+        if (U.patch != 0xffffffffu) {
+            __syncwarp();
+            if (lane == 0) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
+        }
+#else
+        if (lane != 0) continue;                        // host emulation: lane 0 plays the whole warp
+        for (int g = 0; g < ngroups; ++g) {
+            uint32_t words[32];
+            for (int L = 0; L < 32; ++L) { const int j = 32 * g + L; words[L] = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u; }
+            for (int r = 0; r < 8; ++r)
+                for (int L = 0; L < 32; ++L) {
+                    const int f = 256 * g + 32 * r + L;
+                    if (f < nf4) dst[f] = lut[(words[4 * r + (L >> 3)] >> ((L & 7) * 4)) & 15u];
+                }
+        }
+        if (U.patch != 0xffffffffu) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
+#endif
     }
 }

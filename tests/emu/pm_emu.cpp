@@ -15,7 +15,7 @@
 
 static const int EMU_THREADS = 256;
 
-static int fill(const pm_env_desc *d, PmParams &P, int E, int KB) {
+static int fill(const pm_env_desc *d, PmParams &P, int E, int /*KB*/) {
     memset(&P, 0, sizeof(P));
     P.W = d->W; P.H = d->H; P.HW = d->W * d->H; P.NW = pm_nw(P.HW); P.NCAT = pm_ncat(P.HW);
     P.ND = pm_nd(P.W, P.H); P.LS = pm_layout_words_(P.HW);
@@ -24,17 +24,16 @@ static int fill(const pm_env_desc *d, PmParams &P, int E, int KB) {
     P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
     P.shaping_scale = d->shaping_scale;
     P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
-    P.E = E; P.KB = KB; P.lgE = 0;
+    P.E = E; P.lgE = 0;
     while ((1 << P.lgE) < E) ++P.lgE;
     return 0;
 }
 
 template <int MODE>
 static void run(const PmParams &P) {
-    const PmSmem M = pm_smem_map(P.NW, P.NCAT, P.LS, P.E, P.KB, P.has_caps, P.L);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L);
     std::vector<uint32_t> smv((size_t)M.total + 4);
     uint32_t *sm = smv.data();
-    const uint32_t magic = (uint32_t)((0x100000000ull / (uint64_t)P.NCAT) + 1);
     const int64_t nblk = (P.N + P.E - 1) / P.E;
     for (int64_t b = 0; b < nblk; ++b) {
         std::fill(smv.begin(), smv.end(), 0xdeadbeefu);            // catch reads of unwritten smem
@@ -46,15 +45,12 @@ static void run(const PmParams &P) {
         for (int i = 0; i < 4 * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
         if (P.L == 1) for (int i = 0; i < P.LS; ++i) sm[M.lay + i] = P.layouts[i];
         for (int el = 0; el < P.E; ++el) {
-            if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, M, el, n0);
-            else pm_phaseA_static<MODE>(P, sm, M, el, n0);
+            if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, sm, M, el, n0);
+            else pm_phaseA_static<MODE>(P, sm, sm, M, el, n0);
         }
         if (!P.obs) continue;
-        for (int k0 = 0; k0 < 4; k0 += P.KB) {
-            for (int tid = 0; tid < EMU_THREADS; ++tid) pm_phaseB1<MODE>(P, sm, M, tid, EMU_THREADS, magic, k0);
-            for (int w = 0; w < EMU_THREADS / 32; ++w)
-                for (int lane = 0; lane < 32; ++lane) pm_phaseB2(P, sm, M, w, EMU_THREADS / 32, lane, n0, k0);
-        }
+        for (int w = 0; w < EMU_THREADS / 32; ++w)
+            for (int lane = 0; lane < 32; ++lane) pm_phaseB<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0);
     }
 }
 
