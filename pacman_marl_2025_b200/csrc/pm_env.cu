@@ -3,7 +3,7 @@
 // pm_env_core.cuh; this file owns the CTA choreography, launch geometry and the
 // ABI glue (include/pacman_b200.h).
 //
-// CTA choreography (one CTA = PM_E consecutive envs, 8 warps):
+// CTA choreography (one CTA = PM_E = 32 consecutive envs, 4 warps; B200 sweep in DESIGN.md §4):
 //   stage geometry masks (+ the layout record when the batch has one layout)
 //   into shared memory -> phase A (lane el of warp 0 steps env n0+el and leaves
 //   four snapshots in smem) -> phase B (every warp builds the observation bit
@@ -22,9 +22,11 @@
 #include "../../include/pacman_b200.h"
 #include "pm_env_core.cuh"
 
-#define PM_THREADS 256
+#ifndef PM_THREADS
+#define PM_THREADS 128
+#endif
 #ifndef PM_MIN_CTAS
-#define PM_MIN_CTAS 3
+#define PM_MIN_CTAS 8                             // 64 registers/thread: 8 CTAs x 4 warps per SM
 #endif
 #ifndef PM_E
 #define PM_E 32                                   // envs per CTA (power of two <= PM_THREADS)
