@@ -4,10 +4,10 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
                     [--layout tinyCapture] [--envs 65536]
 
-One "step" = one pass of the hot path over the whole batch: pm_step (rules of
-4 ordered sub-moves + four fp32 [8,H,W] observations per env, rewards, done,
-legal masks, shaping) followed by pm_reset on the envs that just finished, so
-episodes keep cycling.  Default workload = the configuration BASELINE.json's
+One "step" = one pass of the hot path over the whole batch: ONE pm_step launch
+(rules of 4 ordered sub-moves + four fp32 [8,H,W] observations per env, rewards,
+done, legal masks, shaping) with pm_env_desc.auto_reset, i.e. envs that finish
+are re-initialised inside the same launch, so episodes keep cycling.  Default workload = the configuration BASELINE.json's
 metric is quoted on: tinyCapture, 65,536 envs per GPU, uniform random actions
 (self-play, all four agents driven by the caller), length 300.  Envs shard per
 GPU with no data-path collective ("weak" scaling: per-GPU batch fixed).
@@ -146,14 +146,14 @@ def run_reference(args, rank, world):
 
 def measure_layout(torch, env_cls, layout, n_envs, steps, warmup, length, device, pool=8):
     """-> dict(step_ms total loop, kernel_ms step kernel alone) for one layout on this rank."""
-    env = env_cls(layout_file=layout_path(layout), self_play=True, length=length, num_envs=n_envs, device=device)
+    env = env_cls(layout_file=layout_path(layout), self_play=True, length=length, num_envs=n_envs, device=device,
+                  auto_reset=True)
     g = torch.Generator(device="cpu").manual_seed(1234)
     acts = torch.randint(0, 5, (pool, n_envs, 4), generator=g, dtype=torch.uint8).to(device)
     env.reset_batched()
 
     def one(i):
-        o = env.step_batched(acts[i % pool])
-        env.reset_batched(mask=o["done"])
+        env.step_batched(acts[i % pool])
     for i in range(warmup):
         one(i)
     return env, acts, one
@@ -219,9 +219,8 @@ def main():
         torch.cuda.synchronize()
         for i in range(KK):
             evs[i][0].record()
-            o = env.step_batched(acts[i % pool])
+            env.step_batched(acts[i % pool])
             evs[i][1].record()
-            env.reset_batched(mask=o["done"])
         torch.cuda.synchronize()
         kern_ms = sum(a.elapsed_time(b) for a, b in evs) / KK
 
@@ -229,14 +228,13 @@ def main():
         #          rewards/done/legal/score_change/shaped rewards out, obs stay in HBM for the policy ----
         acts_host = [acts[i].cpu().pin_memory() for i in range(pool)]
         for i in range(3):
-            env.step_host(acts_host[i % pool]); env.reset_batched(mask=env._done)
+            env.step_host(acts_host[i % pool])
         KE = min(K, 200)
         barrier()
         t0 = time.perf_counter()
         ev0.record()
         for i in range(KE):
             env.step_host(acts_host[i % pool])
-            env.reset_batched(mask=env._done)
         ev1.record()
         barrier()
         e2e_ms = max(ev0.elapsed_time(ev1), 0.0)
@@ -254,7 +252,6 @@ def main():
             t0 = time.perf_counter()
             for i in range(5):
                 env.step_host(acts_host[i % pool], want_obs=True)
-                env.reset_batched(mask=env._done)
             torch.cuda.synchronize()
             e2e_obs = 4.0 * N * 5 / (time.perf_counter() - t0)
     clocks = clk.summary()
@@ -275,7 +272,7 @@ def main():
         "steps": K, "warmup": W, "ms_per_step": loop_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 bitsets + f64 rewards -> f32 obs", "data": "synthetic (uniform random actions, seeded)",
         "config": {"workload": f"{args.layout}, {N} envs/GPU x 4 agents, self-play random actions, length {args.length}, "
-                               "auto-reset by done mask", "envs_per_gpu": N, "layout": args.layout,
+                               "finished envs restart inside the step launch (auto_reset)", "envs_per_gpu": N, "layout": args.layout,
                    "obs_bytes_per_step_per_gpu": 4 * N * 32 * H * Wd,
                    "l2": "no flush: each step writes %.2f GB of observations per GPU (>> 126 MB L2)" % (4 * N * 32 * H * Wd / 1e9),
                    "parallelism": f"env-sharded x{world}, no data-path collective"},
@@ -287,7 +284,7 @@ def main():
                 "note": "pm_step_host: pinned host actions in, rewards/done/legal/score_change/shaped rewards to pinned "
                         "host memory, stream sync every step; observations stay in HBM for the policy net",
                 "with_obs_to_host_agent_steps_per_s": e2e_obs},
-        "gpu_launches": 2 * K,
+        "gpu_launches": K,
         "clocks": clocks,
     }
 
@@ -314,8 +311,7 @@ def main():
             torch.cuda.synchronize()
             ev0.record()
             for i in range(kk):
-                ee[i][0].record(); o = e2.step_batched(a2[i % a2.shape[0]]); ee[i][1].record()
-                e2.reset_batched(mask=o["done"])
+                ee[i][0].record(); e2.step_batched(a2[i % a2.shape[0]]); ee[i][1].record()
             ev1.record()
             torch.cuda.synchronize()
             km = sum(a.elapsed_time(b) for a, b in ee) / kk

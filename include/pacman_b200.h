@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 1
+#define PM_ABI_VERSION 2
 
 /* argument errors */
 #define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
@@ -77,7 +77,20 @@ typedef struct pm_env_desc {
        its own sub-move (the randomTeam opponent, agents/randomTeam.py:94-100; gymPacMan.py:157)      */
     int32_t random_agent_mask;
     double shaping_scale;         /* SHAPING_SCALE, pacman_mappo_resnet.py:34       */
-    uint64_t random_seed;         /* counter-based: draw = hash(seed, env, step, agent) */
+    uint64_t random_seed;         /* counter-based: draw = hash(seed, global env, episode, step, agent) */
+    /* ---- ABI 2 ---- */
+    /* pm_step only: an env whose step terminates is re-initialised inside the same launch
+       (the caller-side `if done: env.reset()` of pacman_mappo_resnet.py:524-538 folded in).
+       reward / done / score_change / shaping describe the terminal step; obs / legal and the
+       stored state are those of the fresh episode.                                         */
+    int32_t auto_reset;
+    int32_t reserved0;
+    int64_t env_index_base;       /* global index of env 0 of this batch (rank offset when the batch is a
+                                     shard): keys the in-kernel random draws, so trajectories do not
+                                     depend on how envs are partitioned over GPUs                      */
+    /* launch only envs [env_begin, env_begin + env_count) of the batch; env_count 0 = all.
+       env_begin must be a multiple of 32.  Outputs are still indexed by the batch-wide env number. */
+    int64_t env_begin, env_count;
 } pm_env_desc;
 
 /* Outputs of one step; any pointer may be NULL to skip that output. */

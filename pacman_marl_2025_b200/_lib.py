@@ -32,6 +32,9 @@ class PmEnvDesc(C.Structure):
         ("random_agent_mask", C.c_int32),
         ("shaping_scale", C.c_double),
         ("random_seed", C.c_uint64),
+        # ABI 2
+        ("auto_reset", C.c_int32), ("reserved0", C.c_int32), ("env_index_base", C.c_int64),
+        ("env_begin", C.c_int64), ("env_count", C.c_int64),
     ]
 
 
@@ -93,7 +96,7 @@ def load():
     L.pm_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, i32, i64, vp]
     L.pm_adv_norm.restype = i32
     L.pm_adv_norm.argtypes = [vp, vp, vp, i64, i32, vp]
-    if L.pm_abi_version() != 1:
+    if L.pm_abi_version() != 2:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

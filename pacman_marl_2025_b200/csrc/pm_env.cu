@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MIN_CTAS) pm_env_kernel(const P
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L);
     const int tid = threadIdx.x;
-    const int64_t n0 = (int64_t)blockIdx.x * PM_E;
+    const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * PM_E;
 
     // ---- stage per-batch tables ----
     if (tid < 16) {
@@ -130,22 +130,7 @@ static int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-static int fill_params(const pm_env_desc *d, PmParams &P) {
-    if (!d || !d->geom || !d->layouts || !d->state || d->n_envs <= 0 || d->n_layouts <= 0) return PM_EINVAL;
-    if (d->W < 3 || d->H < 3) return PM_EINVAL;
-    if (d->W > 255 || d->H > 255 || d->W * d->H > PM_MAX_CELLS) return PM_ETOOBIG;
-    memset(&P, 0, sizeof(P));
-    P.W = d->W; P.H = d->H; P.HW = d->W * d->H; P.NW = pm_nw(P.HW); P.NCAT = pm_ncat(P.HW);
-    P.ND = pm_nd(P.W, P.H); P.LS = pm_layout_words_(P.HW);
-    P.L = d->n_layouts; P.has_caps = d->has_caps != 0; P.N = d->n_envs;
-    P.geom = d->geom; P.layouts = d->layouts; P.layout_id = d->layout_id; P.state = (uint8_t *)d->state;
-    P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
-    P.shaping_scale = d->shaping_scale;
-    P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
-    P.E = PM_E; P.lgE = 0;
-    while ((1 << P.lgE) < PM_E) ++P.lgE;
-    return 0;
-}
+static int fill_params(const pm_env_desc *d, PmParams &P) { return pm_fill_params(d, P, PM_E); }
 
 template <int MODE>
 static int launch_env(const PmParams &P, cudaStream_t st) {
@@ -163,7 +148,7 @@ static int launch_env(const PmParams &P, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         configured[dev & 63][MODE] = smem;
     }
-    const unsigned grid = (unsigned)((P.N + PM_E - 1) / PM_E);
+    const unsigned grid = (unsigned)((P.n_end - P.n_begin + PM_E - 1) / PM_E);
     pm_env_kernel<MODE><<<grid, PM_THREADS, smem, st>>>(P);
     return (int)cudaGetLastError();
 }

@@ -72,6 +72,9 @@ struct PmParams {
     int length, reward_legal, defence;
     double shaping_scale;
     int bot_mask; unsigned long long bot_seed;   // in-kernel uniform-random-legal agents
+    int auto_reset;                     // step: terminal envs restart inside the launch
+    int64_t n_base;                     // global index of env 0 (keys the random draws)
+    int64_t n_begin, n_end;             // env range of this launch
     // step inputs / outputs (see pm_step_out in pacman_b200.h)
     const void *actions; int act_size;
     float *obs; int64_t obs_agent_stride;
@@ -193,9 +196,10 @@ PM_HD int pm_legal_mask(const uint32_t *walls, int W, int c) {   // game.py:335-
 
 // Uniform draw from the set bits of `legal` (randomTeam: random.choice(legal actions),
 // agents/randomTeam.py:94-100).  Counter-based so a trajectory depends only on
-// (seed, env index, step, agent) and not on launch geometry or sharding.
-PM_HD int pm_random_legal(int legal, unsigned long long seed, unsigned long long n, unsigned ctr) {
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (n + 1) + 0xD1B54A32D192ED03ull * (unsigned long long)(ctr + 1);
+// (seed, global env index, episode, step, agent) and not on launch geometry or sharding.
+PM_HD int pm_random_legal(int legal, unsigned long long seed, unsigned long long n, unsigned episode, unsigned ctr) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (n + 1) +
+                           0xD1B54A32D192ED03ull * (((unsigned long long)episode << 32) + ctr + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
@@ -252,7 +256,7 @@ PM_HD void pm_pack_agents(const PmAgents &g, pm_u4 &A, pm_u4 &B) {
 // ============================================================================
 PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
-    if (n >= P.N) { sm[M.lid + el] = 0xffffffffu; return; }
+    if (n >= P.n_end) { sm[M.lid + el] = 0xffffffffu; return; }
     const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
     sm[M.lid + el] = lid;
     const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
@@ -279,6 +283,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     pm_unpack_agents(g, A, B, tail);
     int score = (int)Mi.x, steps = (int)Mi.y;
     int rf = (int)(Mi.z & 0xffff), bf = (int)(Mi.z >> 16);       // pellets on the red / blue food half
+    uint32_t episode = Mi.w;                                      // restarts of this env (keys the random draws)
     uint32_t snap[4] = {S.x, S.y, S.z, S.w};
 
     uint32_t act4;
@@ -312,7 +317,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         int c = g.y[a] * W + g.x[a];
         const int legal = pm_legal_mask(walls, W, c);
         int u = (act4 >> (8 * a)) & 0xff;
-        if ((P.bot_mask >> a) & 1) u = pm_random_legal(legal, P.bot_seed, (unsigned long long)n, (unsigned)steps * 4u + a);
+        if ((P.bot_mask >> a) & 1) u = pm_random_legal(legal, P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + a);
         const bool req_legal = u <= 4 && ((legal >> u) & 1);
         if (!req_legal) u = 4;
         const int dx = (u == 1) - (u == 3), dy = (u == 0) - (u == 2);
@@ -399,6 +404,35 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     }
     steps += 1;
 
+    // ---- fused restart (pm_env_desc.auto_reset): the trainer's `if done: env.reset()`
+    // (pacman_mappo_resnet.py:524-538) without a second launch.  Rewards / done / shaping above
+    // belong to the terminal step; state, the four observations and the legal masks below are
+    // CaptureRules.newGame's (capture.py:369-382, game.py:490-508). ----
+    if (term && P.auto_reset) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t s0 = tail[PM_L_START + i];
+            g.x[i] = g.sx[i]; g.y[i] = g.sy[i]; g.dir[i] = 4; g.pac[i] = (s0 >> 16) & 1; g.scared[i] = 0;
+            g.carry[i] = 0; g.ret[i] = 0;
+            snap[i] = s0 & 0xffff;
+        }
+        score = 0; steps = 0; episode += 1;
+        rf = (int)(tail[PM_L_FOODCNT] & 0xffff); bf = (int)(tail[PM_L_FOODCNT] >> 16);
+        for (int w = 0; w < NW; ++w) {
+            const uint32_t f = lay[pm_l_food(P.HW) + w];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) food[(k * NW + w) * E1] = f;
+            if (caps) {
+                const uint32_t cp = lay[pm_l_caps(P.HW) + w];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) caps[(k * NW + w) * E1] = cp;
+            }
+        }
+        food_dirty = true; caps_dirty = caps != nullptr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pm_store_snapshot(sm, M, P, k, el, g);
+    }
+
     // ---- outputs ----
     if (P.reward) { P.reward[n] = red_r; P.reward[P.N + n] = blue_r; }
     if (P.done) P.done[n] = term ? 1 : 0;
@@ -423,7 +457,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
     S.x = snap[0]; S.y = snap[1]; S.z = snap[2]; S.w = snap[3];
     reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
-    Mi.x = (uint32_t)score; Mi.y = (uint32_t)steps; Mi.z = (uint32_t)rf | (uint32_t)bf << 16;
+    Mi.x = (uint32_t)score; Mi.y = (uint32_t)steps; Mi.z = (uint32_t)rf | (uint32_t)bf << 16; Mi.w = episode;
     reinterpret_cast<pm_u4 *>(P.state + pm_st_misc(P.N))[n] = Mi;
     if (food_dirty) for (int w = 0; w < NW; ++w) gfood[(size_t)w * NP + n] = food[(3 * NW + w) * E1];
     if (caps_dirty) for (int w = 0; w < NW; ++w) gcaps[(size_t)w * NP + n] = caps[(3 * NW + w) * E1];
@@ -435,7 +469,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
 template <int MODE>
 PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
-    if (n >= P.N || (MODE == PM_MODE_RESET && P.mask && !P.mask[n])) { sm[M.lid + el] = 0xffffffffu; return; }
+    if (n >= P.n_end || (MODE == PM_MODE_RESET && P.mask && !P.mask[n])) { sm[M.lid + el] = 0xffffffffu; return; }
     const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
     sm[M.lid + el] = lid;
     const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
@@ -460,7 +494,9 @@ PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm,
         A.x = a[0]; A.y = a[1]; A.z = a[2]; A.w = a[3];
         B.x = B.y = B.z = B.w = 0;
         S.x = s[0]; S.y = s[1]; S.z = s[2]; S.w = s[3];
-        Mi.x = 0; Mi.y = 0; Mi.z = tail[PM_L_FOODCNT]; Mi.w = 0;
+        // episode counter: a full reset (mask == NULL) restarts it, a masked reset of an initialised batch advances it
+        Mi.x = 0; Mi.y = 0; Mi.z = tail[PM_L_FOODCNT];
+        Mi.w = P.mask ? reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n].w + 1u : 0u;
         reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
         reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
         reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
@@ -595,3 +631,29 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
 #endif
     }
 }
+
+// ---- pm_env_desc -> PmParams (shared by the C ABI glue and the test emulation) ----
+#ifdef PACMAN_B200_H
+static inline int pm_fill_params(const pm_env_desc *d, PmParams &P, int E) {
+    if (!d || !d->geom || !d->layouts || !d->state || d->n_envs <= 0 || d->n_layouts <= 0) return PM_EINVAL;
+    if (d->W < 3 || d->H < 3) return PM_EINVAL;
+    if (d->W > 255 || d->H > 255 || d->W * d->H > PM_MAX_CELLS) return PM_ETOOBIG;
+    if (d->env_begin < 0 || d->env_count < 0 || (d->env_begin & 31) || d->env_begin + d->env_count > d->n_envs ||
+        (d->env_count == 0 && d->env_begin != 0))
+        return PM_EINVAL;
+    P = PmParams();
+    P.W = d->W; P.H = d->H; P.HW = d->W * d->H; P.NW = pm_nw(P.HW); P.NCAT = pm_ncat(P.HW);
+    P.ND = pm_nd(P.W, P.H); P.LS = pm_layout_words_(P.HW);
+    P.L = d->n_layouts; P.has_caps = d->has_caps != 0; P.N = d->n_envs;
+    P.geom = d->geom; P.layouts = d->layouts; P.layout_id = d->layout_id; P.state = (uint8_t *)d->state;
+    P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
+    P.shaping_scale = d->shaping_scale;
+    P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
+    P.auto_reset = d->auto_reset != 0;
+    P.n_base = d->env_index_base;
+    P.n_begin = d->env_begin; P.n_end = d->env_count ? d->env_begin + d->env_count : d->n_envs;
+    P.E = E; P.lgE = 0;
+    while ((1 << P.lgE) < E) ++P.lgE;
+    return 0;
+}
+#endif

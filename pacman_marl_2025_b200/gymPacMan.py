@@ -222,7 +222,8 @@ class gymPacMan_parallel_env:
     def __init__(self, layout_file=f"{file_path}/layouts/smallCapture.lay", display=False, length=299,
                  reward_forLegalAction=True, defenceReward=True, random_layout=False, enemieName="randomTeam",
                  self_play=False, *, num_envs: int = 1, device=None, layouts: Optional[Sequence] = None,
-                 shaping_scale: float = 0.1, opponent_seed: int = 0):
+                 shaping_scale: float = 0.1, opponent_seed: int = 0, auto_reset: bool = False,
+                 env_index_base: int = 0):
         if display:
             raise NotImplementedError("display=True (tkinter viewer) is outside the batched GPU path")
         if not torch.cuda.is_available():
@@ -256,6 +257,10 @@ class gymPacMan_parallel_env:
                 f"enemieName={enemieName!r}: only the on-device randomTeam opponent exists; CPU bot teams "
                 "(agents/*.py) are outside the GPU path (SURVEY §8 row f1)")
         self._opponent_seed = int(opponent_seed)
+        # batched extensions: restart finished envs inside the step launch; global index of env 0 when
+        # this batch is one shard of a larger one (keys the on-device opponent's random draws)
+        self.auto_reset = bool(auto_reset)
+        self.env_index_base = int(env_index_base)
 
         if layouts is not None:
             lays = [l if isinstance(l, _layout.Layout) else _layout.Layout(list(l)) for l in layouts]
@@ -286,7 +291,8 @@ class gymPacMan_parallel_env:
         self._desc = _lib.PmEnvDesc(W, H, len(lays), int(has_caps), N, self._geom.data_ptr(), self._table.data_ptr(),
                                     None, self._state.data_ptr(), int(self.length), int(bool(self.reward_forLegalAction)),
                                     int(bool(self.defenceReward)), 0 if self.self_play else 0b0101,
-                                    self.shaping_scale, int(self._opponent_seed))
+                                    self.shaping_scale, int(self._opponent_seed), int(self.auto_reset), 0,
+                                    self.env_index_base, 0, 0)
         self.obs_shape = (8, H, W)
         self._obs = torch.empty((4, N, 8, H, W), dtype=torch.float32, device=dev)
         self._reward = torch.zeros((2, N), dtype=torch.float64, device=dev)

@@ -15,29 +15,17 @@
 
 static const int EMU_THREADS = 256;
 
-static int fill(const pm_env_desc *d, PmParams &P, int E, int /*KB*/) {
-    memset(&P, 0, sizeof(P));
-    P.W = d->W; P.H = d->H; P.HW = d->W * d->H; P.NW = pm_nw(P.HW); P.NCAT = pm_ncat(P.HW);
-    P.ND = pm_nd(P.W, P.H); P.LS = pm_layout_words_(P.HW);
-    P.L = d->n_layouts; P.has_caps = d->has_caps != 0; P.N = d->n_envs;
-    P.geom = d->geom; P.layouts = d->layouts; P.layout_id = d->layout_id; P.state = (uint8_t *)d->state;
-    P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
-    P.shaping_scale = d->shaping_scale;
-    P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
-    P.E = E; P.lgE = 0;
-    while ((1 << P.lgE) < E) ++P.lgE;
-    return 0;
-}
+static int fill(const pm_env_desc *d, PmParams &P, int E, int /*KB*/) { return pm_fill_params(d, P, E); }
 
 template <int MODE>
 static void run(const PmParams &P) {
     const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L);
     std::vector<uint32_t> smv((size_t)M.total + 4);
     uint32_t *sm = smv.data();
-    const int64_t nblk = (P.N + P.E - 1) / P.E;
+    const int64_t nblk = (P.n_end - P.n_begin + P.E - 1) / P.E;
     for (int64_t b = 0; b < nblk; ++b) {
         std::fill(smv.begin(), smv.end(), 0xdeadbeefu);            // catch reads of unwritten smem
-        const int64_t n0 = b * P.E;
+        const int64_t n0 = P.n_begin + b * P.E;
         for (int t = 0; t < 16; ++t) {
             float *v = reinterpret_cast<float *>(sm + M.lut) + 4 * t;
             v[0] = (t & 1) ? 1.f : 0.f; v[1] = (t & 2) ? 1.f : 0.f; v[2] = (t & 4) ? 1.f : 0.f; v[3] = (t & 8) ? 1.f : 0.f;
@@ -55,19 +43,19 @@ static void run(const PmParams &P) {
 }
 
 extern "C" int emu_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, int64_t stride, uint8_t *legal, int E, int KB) {
-    PmParams P; fill(d, P, E, KB);
+    PmParams P; if (int rc = fill(d, P, E, KB)) return rc;
     P.mask = mask; P.obs = obs; P.obs_agent_stride = stride; P.legal = legal;
     run<PM_MODE_RESET>(P);
     return 0;
 }
 extern "C" int emu_observe(const pm_env_desc *d, float *obs, int64_t stride, int E, int KB) {
-    PmParams P; fill(d, P, E, KB);
+    PmParams P; if (int rc = fill(d, P, E, KB)) return rc;
     P.obs = obs; P.obs_agent_stride = stride;
     run<PM_MODE_OBSERVE>(P);
     return 0;
 }
 extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize, const pm_step_out *out, int E, int KB) {
-    PmParams P; fill(d, P, E, KB);
+    PmParams P; if (int rc = fill(d, P, E, KB)) return rc;
     P.actions = actions; P.act_size = itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
@@ -77,7 +65,7 @@ extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize,
 }
 // host mirror of pm_get_state_kernel
 extern "C" int emu_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc) {
-    PmParams P; fill(d, P, 64, 4);
+    PmParams P; if (int rc = fill(d, P, 64, 4)) return rc;
     const int64_t NP = pm_np(P.N);
     for (int64_t n = 0; n < P.N; ++n) {
         const pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];

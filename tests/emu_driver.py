@@ -32,7 +32,8 @@ def _p(a):
 
 class EmuEnv:
     def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True,
-                 shaping_scale=0.1, E=64, KB=4, layout_id=None, random_agent_mask=0, random_seed=0):
+                 shaping_scale=0.1, E=64, KB=4, layout_id=None, random_agent_mask=0, random_seed=0,
+                 auto_reset=False, env_index_base=0):
         L = lib()
         per_env = not isinstance(layouts[0], str)
         lays = layouts if per_env else [layouts]
@@ -54,7 +55,8 @@ class EmuEnv:
                                     self.layouts.ctypes.data,
                                     None if self.layout_id is None else self.layout_id.ctypes.data,
                                     self.state.ctypes.data, int(length), int(reward_forLegalAction),
-                                    int(defenceReward), int(random_agent_mask), float(shaping_scale), int(random_seed))
+                                    int(defenceReward), int(random_agent_mask), float(shaping_scale), int(random_seed),
+                                    int(auto_reset), 0, int(env_index_base), 0, 0)
         self.obs_shape = (8, self.H, self.W)
 
     def reset(self, mask=None):
@@ -69,6 +71,9 @@ class EmuEnv:
         lib().emu_observe(C.byref(self.desc), _p(obs), C.c_int64(obs[0].size), self.E, self.KB)
         return obs
 
+    def set_range(self, begin=0, count=0):
+        self.desc.env_begin, self.desc.env_count = int(begin), int(count)
+
     def step(self, actions, dtype=np.uint8):
         a = np.ascontiguousarray(np.asarray(actions).reshape(self.N, 4), dtype)
         o = dict(obs=np.full((4, self.N) + self.obs_shape, np.nan, np.float32), reward=np.zeros((2, self.N)),
@@ -78,7 +83,8 @@ class EmuEnv:
         so = pmlib.PmStepOut(o["obs"].ctypes.data, o["obs"][0].size, o["reward"].ctypes.data, o["done"].ctypes.data,
                              o["legal"].ctypes.data, o["score_change"].ctypes.data, o["shaping"].ctypes.data,
                              o["shaped"].ctypes.data)
-        lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
+        rc = lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
+        assert rc == 0, rc
         return o
 
     def get_state(self):

@@ -132,3 +132,101 @@ def body_observe_current_state(make_env):
         for i in range(4):
             np.testing.assert_array_equal(cur[i, n], ref.observe(n, i))
     return env, rng
+
+
+def body_auto_reset(make_env, layname="tinyCapture", N=80, T=170, length=40):
+    """pm_env_desc.auto_reset: an env whose step terminates restarts inside the same launch.
+    Terminal-step outputs (reward, done, score_change, shaping) are the oracle's step outputs;
+    obs / legal / state of a finished env are the oracle's reset outputs."""
+    rows = layname if isinstance(layname, list) else lay_rows(layname)
+    rng = np.random.default_rng(11)
+    env = make_env(rows, N, length=length, auto_reset=True)
+    ref = oracle.OracleBatch(rows, N, length=length)
+    env.reset(); ref.reset()
+    n_done = 0
+    for t in range(T):
+        a = biased_actions(rng, N, 0.6, t)
+        o = env.step(a)
+        r = ref.step(a, with_obs=True, nthreads=0, auto_reset=True)     # oracle: reset after done, outputs = terminal step
+        d = r["done"].astype(bool)
+        np.testing.assert_array_equal(o["done"], r["done"], err_msg=f"t={t}")
+        np.testing.assert_array_equal(o["reward"].view(np.uint64), r["reward"].T.copy().view(np.uint64), err_msg=f"t={t}")
+        np.testing.assert_array_equal(o["score_change"], r["score_change"])
+        np.testing.assert_array_equal(o["shaping"].view(np.uint64), r["shaping"].T.copy().view(np.uint64), err_msg=f"t={t}")
+        want_obs, want_legal = r["obs"].copy(), r["legal"].copy()
+        if d.any():
+            idx = np.nonzero(d)[0]
+            ro, rl = ref.reset_outputs_for(idx)
+            want_obs[idx], want_legal[idx] = ro, rl
+            n_done += len(idx)
+        np.testing.assert_array_equal(o["legal"], want_legal, err_msg=f"t={t} legal")
+        np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4), want_obs, err_msg=f"t={t} obs")
+        if t % 13 == 0 or d.any():
+            s = env.get_state()
+            for n in list(np.nonzero(d)[0][:4]) + [0, N - 1]:
+                rs = ref.state(int(n))
+                np.testing.assert_array_equal(s["agents"][n], rs["agents"])
+                np.testing.assert_array_equal(s["food"][n], rs["food"])
+                np.testing.assert_array_equal(s["caps"][n], rs["caps"])
+                assert s["score"][n] == rs["score"] and s["steps"][n] == rs["steps"]
+    assert n_done >= N
+
+
+def body_env_ranges(make_env, set_range, N=96):
+    """pm_env_desc.env_begin / env_count: launching the batch as consecutive ranges gives
+    the same outputs and state as one launch over all envs."""
+    rows = lay_rows("smallCapture")
+    rng = np.random.default_rng(21)
+    whole, parts = make_env(rows, N, length=30, auto_reset=True), make_env(rows, N, length=30, auto_reset=True)
+    whole.reset(); parts.reset()
+    cuts = [0, 32, 64, N]
+    for t in range(70):
+        a = biased_actions(rng, N, 0.6, t)
+        o = whole.step(a)
+        acc = None
+        for b, e in zip(cuts[:-1], cuts[1:]):
+            set_range(parts, b, e - b)
+            p = parts.step(a)
+            if acc is None:
+                acc = {k: np.array(v, copy=True) for k, v in p.items()}
+            else:
+                for k, v in p.items():
+                    if k in ("obs", "reward", "shaping", "shaped"):
+                        acc[k][:, b:e] = v[:, b:e]
+                    else:
+                        acc[k][b:e] = v[b:e]
+        set_range(parts, 0, 0)
+        for k in o:
+            np.testing.assert_array_equal(o[k], acc[k], err_msg=f"t={t} {k}")
+    s1, s2 = whole.get_state(), parts.get_state()
+    for k in s1:
+        np.testing.assert_array_equal(s1[k], s2[k])
+
+
+def body_shard_invariant_random_agents(make_env, N=64):
+    """env_index_base: the on-device randomTeam draws are keyed by the GLOBAL env index, so
+    two shards [0,N/2) and [N/2,N) reproduce one batch of N."""
+    rows = lay_rows("smallCapture")
+    kw = dict(length=25, auto_reset=True, random_agent_mask=0b0101, random_seed=99)
+    full = make_env(rows, N, **kw)
+    sh = [make_env(rows, N // 2, env_index_base=i * (N // 2), **kw) for i in range(2)]
+    full.reset(); [s.reset() for s in sh]
+    rng = np.random.default_rng(4)
+    for t in range(80):
+        a = biased_actions(rng, N, 0.6, t)
+        o = full.step(a)
+        os_ = [sh[i].step(a[i * N // 2:(i + 1) * N // 2]) for i in range(2)]
+        for k in ("obs", "reward", "shaped"):
+            np.testing.assert_array_equal(o[k], np.concatenate([os_[0][k], os_[1][k]], axis=1), err_msg=f"t={t} {k}")
+        for k in ("done", "legal", "score_change"):
+            np.testing.assert_array_equal(o[k], np.concatenate([os_[0][k], os_[1][k]], axis=0), err_msg=f"t={t} {k}")
+    # and a different base gives a different stream
+    other = make_env(rows, N // 2, env_index_base=10_000, **kw)
+    other.reset()
+    fresh = make_env(rows, N // 2, env_index_base=0, **kw)
+    fresh.reset()
+    a = biased_actions(rng, N // 2)
+    differs = False
+    for t in range(20):
+        differs |= not np.array_equal(other.step(a)["obs"], fresh.step(a)["obs"])
+    assert differs

@@ -1,0 +1,126 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every
+symbol include/pacman_b200.h declares (no compute call is made without a GPU),
+argument validation answers with PM_E* codes, the host-side layout loader and
+maze generator reproduce the reference's fixtures, and the env class refuses to
+run without CUDA instead of falling back."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "pacman_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pm_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pacman_marl_2025_b200 import _lib
+    names = declared_symbols()
+    assert len(names) >= 15 and "pm_step" in names and "pm_distances" in names
+    lib = C.CDLL(_lib.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(_lib.EXPORTS) == names, "pacman_marl_2025_b200/_lib.py EXPORTS out of sync with the header"
+    assert _lib.load().pm_abi_version() == int(re.search(r"#define PM_ABI_VERSION (\d+)", open(
+        os.path.join(ROOT, "include", "pacman_b200.h")).read()).group(1))
+
+
+def test_struct_layouts_match_the_header():
+    """ctypes mirrors of pm_env_desc / pm_step_out have the C compiler's size (checked by compiling a probe)."""
+    import subprocess, tempfile
+    from pacman_marl_2025_b200 import _lib
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "p.c")
+        open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "pacman_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",'
+                             'sizeof(pm_env_desc),sizeof(pm_step_out),offsetof(pm_env_desc,env_index_base),offsetof(pm_env_desc,shaping_scale));return 0;}\n')
+        exe = os.path.join(td, "p")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+        a, b, c, d = map(int, subprocess.check_output([exe]).split())
+    assert C.sizeof(_lib.PmEnvDesc) == a and C.sizeof(_lib.PmStepOut) == b
+    assert _lib.PmEnvDesc.env_index_base.offset == c and _lib.PmEnvDesc.shaping_scale.offset == d
+
+
+def test_argument_errors_without_touching_the_gpu():
+    from pacman_marl_2025_b200 import _lib
+    L = _lib.load()
+    assert L.pm_geom_words(300, 4) == -3            # PM_ETOOBIG
+    assert L.pm_geom_words(2, 2) == -1              # PM_EINVAL
+    buf = np.zeros(L.pm_layout_words(5, 5), np.uint32)
+    hc = C.c_int(0)
+    bad = ("%%%%%" "%1 2%" "%   %" "%3  %" "%%%%%").encode()        # only three agents
+    assert L.pm_pack_layout(bad, 5, 5, buf.ctypes.data, C.byref(hc)) == -2      # PM_ELAYOUT
+    open_border = ("%% %%" "%1 2%" "%   %" "%3 4%" "%%%%%").encode()
+    assert L.pm_pack_layout(open_border, 5, 5, buf.ctypes.data, C.byref(hc)) == -2
+    ok = ("%%%%%" "%1o2%" "% . %" "%3 4%" "%%%%%").encode()
+    assert L.pm_pack_layout(ok, 5, 5, buf.ctypes.data, C.byref(hc)) == 0 and hc.value == 1
+    # null descriptor / null pointers are rejected before any CUDA call
+    assert L.pm_step(None, None, 1, None, None) == -1
+    d = _lib.PmEnvDesc()
+    assert L.pm_reset(C.byref(d), None, None, 0, None, None) == -1
+    assert L.pm_distances(5, 5, None, 1, None, None, None, 8, None) == -1
+    assert L.pm_gae(None, None, None, None, 0.99, 0.95, None, None, 4, 4, None) == -1
+
+
+def test_env_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gymPacMan_parallel_env(self_play=True)
+    from pacman_marl_2025_b200.mappo_ops import compute_gae
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        compute_gae(torch.zeros(4, 2), torch.zeros(4, 2), torch.zeros(4, 2), 0.0)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pacman_marl_2025_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "pm_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+@pytest.mark.parametrize("seed", list(json.load(open(os.path.join(helpers.GOLDEN, "mazes.json")))))
+def test_maze_generator_text_matches_reference(seed):
+    """mazeGenerator.generateMaze(seed) (mazeGenerator.py:255-264) and capture.randomLayout() (capture.py:905-911,
+    seed drawn from the global RNG): same text as the reference."""
+    import random
+    from pacman_marl_2025_b200 import mazeGenerator
+    want = json.load(open(os.path.join(helpers.GOLDEN, "mazes.json")))[seed]
+    if seed.startswith("global"):
+        random.seed(int(seed[6:]))
+        assert mazeGenerator.randomLayout() == want
+    else:
+        assert mazeGenerator.generateMaze(int(seed)) == want
+
+
+@pytest.mark.parametrize("name", helpers.traj_names())
+def test_layout_loader_matches_reference_fixture(name):
+    """layout.Layout (layout.py:95-130): walls / food / capsules / starts of every fixture board, checked
+    against the first recorded state of the reference."""
+    from pacman_marl_2025_b200.layout import Layout
+    fx = helpers.load_traj(name)
+    lay = Layout(fx["layout"])
+    W, H = fx["W"], fx["H"]
+    assert (lay.width, lay.height) == (W, H)
+    rows = fx["layout"]
+    for x in range(W):
+        for y in range(H):
+            ch = rows[H - 1 - y][x]
+            assert bool(lay.walls[x][y]) == (ch == "%")
+            assert bool(lay.food[x][y]) == (ch == ".")
+    assert sorted(lay.capsules) == sorted((x, y) for x in range(W) for y in range(H) if rows[H - 1 - y][x] == "o")
+    for i in range(4):
+        x, y = lay.starts[i]
+        assert rows[H - 1 - y][x] == str(i + 1)

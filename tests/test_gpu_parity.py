@@ -18,13 +18,15 @@ pytestmark = pytest.mark.gpu
 class CudaEnv:
     """Thin numpy-returning adapter over the product class (same surface as tests/emu_driver.EmuEnv)."""
 
-    def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True, **kw):
+    def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True,
+                 random_agent_mask=0, random_seed=0, **kw):
         from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
         per_env = not isinstance(layouts[0], str)
         lays = layouts if per_env else [layouts]
+        assert random_agent_mask in (0, 0b0101)
         self.env = gymPacMan_parallel_env(length=length, reward_forLegalAction=reward_forLegalAction,
-                                          defenceReward=defenceReward, self_play=True, num_envs=n_envs,
-                                          layouts=lays, **kw)
+                                          defenceReward=defenceReward, self_play=random_agent_mask == 0,
+                                          num_envs=n_envs, layouts=lays, opponent_seed=random_seed, **kw)
         self.N = n_envs
 
     def reset(self, mask=None):
@@ -38,6 +40,9 @@ class CudaEnv:
         return dict(obs=o["obs"].cpu().numpy(), reward=o["reward"].cpu().numpy(), done=o["done"].cpu().numpy(),
                     legal=o["legal"].cpu().numpy(), score_change=o["score_change"].cpu().numpy(),
                     shaping=o["shaping"].cpu().numpy(), shaped=o["shaped_reward"].cpu().numpy())
+
+    def set_range(self, begin=0, count=0):
+        self.env._desc.env_begin, self.env._desc.env_count = int(begin), int(count)
 
     def get_state(self):
         return self.env.export_state()
@@ -62,6 +67,19 @@ def test_large_batch_vs_oracle(layname, N, T, length):
 
 def test_per_env_distinct_mazes_vs_oracle():
     body_per_env_mazes(CudaEnv, 96, 150)
+
+
+def test_auto_reset_fused_into_step_vs_oracle():
+    from parity_bodies import body_auto_reset
+    body_auto_reset(CudaEnv, "tinyCapture", N=1500, T=200, length=40)
+    body_auto_reset(CudaEnv, helpers.load_traj("capsSmall")["layout"], N=300, T=150, length=60)
+    body_auto_reset(CudaEnv, "bloxCapture", N=200, T=90, length=25)
+
+
+def test_env_ranges_and_shard_invariant_random_agents():
+    from parity_bodies import body_env_ranges, body_shard_invariant_random_agents
+    body_env_ranges(CudaEnv, lambda e, b, c: e.set_range(b, c), N=96)
+    body_shard_invariant_random_agents(CudaEnv, N=256)
 
 
 def test_int64_actions_and_out_of_range():

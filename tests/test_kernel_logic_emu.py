@@ -51,3 +51,15 @@ def test_emulated_random_agents_are_legal_and_reproducible():
         assert (o1["reward"][0] >= 0.02 - 1e-12).all()
         moved += int((e1.get_state()["agents"][:, 0, :2] != p0).any(1).sum())
     assert moved > 40
+
+
+def test_emulated_auto_reset_matches_oracle():
+    from parity_bodies import body_auto_reset
+    body_auto_reset(lambda rows, n, **kw: EmuEnv(rows, n, E=8, KB=1, **kw), N=40, T=120)
+    body_auto_reset(lambda rows, n, **kw: EmuEnv(rows, n, E=8, KB=1, **kw), layname=helpers.load_traj("capsSmall")["layout"], N=24, T=100)
+
+
+def test_emulated_env_ranges_and_shard_invariance():
+    from parity_bodies import body_env_ranges, body_shard_invariant_random_agents
+    body_env_ranges(lambda rows, n, **kw: EmuEnv(rows, n, E=32, KB=1, **kw), lambda e, b, c: e.set_range(b, c))
+    body_shard_invariant_random_agents(lambda rows, n, **kw: EmuEnv(rows, n, E=16, KB=1, **kw))
