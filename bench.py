@@ -99,7 +99,8 @@ def oracle_rate(layout, n_envs, steps, warmup, length, nthreads=0):
     env.reset(with_obs=False)
     rng = np.random.default_rng(12345)
     acts = rng.integers(0, 5, size=(8, n_envs, 4)).astype(np.int32)
-    threads = oracle.max_threads() if nthreads <= 0 else nthreads
+    # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which would hide them)
+    threads = len(os.sched_getaffinity(0)) if nthreads <= 0 else nthreads
     import ctypes as C
     L = oracle.lib()
     obs = np.empty((n_envs, 4, 8, env.H, env.W), np.float32)

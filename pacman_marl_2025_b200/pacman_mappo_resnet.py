@@ -214,6 +214,7 @@ class TrainConfig:
     length: int = 300
     seed: int = 0
     amp_bf16: bool = False            # networks in bf16 autocast (fp32 master weights); default = reference fp32
+    fast_math: bool = True            # cuDNN autotune + TF32 tensor-core matmuls for the fp32 networks
     selfplay_after: int = 800         # update index after which self-play opponents enter the mix (`:396-438`)
     log_every: int = 1
     checkpoint_every: int = 250
@@ -238,6 +239,10 @@ class MAPPOTrainer:
     def __init__(self, cfg: TrainConfig, device=None):
         self.cfg = cfg
         self.rank, self.world = sharding.world_info()
+        if cfg.fast_math:
+            torch.backends.cudnn.benchmark = True
+            torch.backends.cuda.matmul.allow_tf32 = True
+            torch.backends.cudnn.allow_tf32 = True
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         layout_file = cfg.layout_file or os.path.join(os.path.dirname(os.path.abspath(__file__)), "layouts",
                                                       "smallCapture.lay")
