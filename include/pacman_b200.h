@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 2
+#define PM_ABI_VERSION 3
 
 /* argument errors */
 #define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
@@ -105,7 +105,20 @@ typedef struct pm_step_out {
     double *shaping;              /* [dev] [4][N] compute_heuristic_shaping per agent (fp64)                    */
     float *shaped_reward;         /* [dev] [4][N] fp32(2*team_reward + shaping_scale*shaping), i.e. the value
                                      the trainer stores in reward_buf (pacman_mappo_resnet.py:518-522)          */
+    /* ---- ABI 3 ---- */
+    struct pm_host_record *packed; /* [dev] [N] every small per-env output in one 48-byte record, so a host-side
+                                     consumer needs ONE device-to-host copy per step (pm_step_host_pipelined)  */
 } pm_step_out;
+
+/* What a CPU-side caller of gymPacMan.step reads back every step (gymPacMan.py:184-193), one record per env. */
+typedef struct pm_host_record {
+    double reward_red, reward_blue;   /* rewards dict: agents 0,2 / agents 1,3                                  */
+    float shaped_reward[4];           /* trainer reward per agent (see pm_step_out.shaped_reward)               */
+    int32_t score_change;             /* info['score_change']                                                   */
+    uint8_t legal[4];                 /* info['legal_actions'] as bitmasks                                      */
+    uint8_t done;                     /* terminations                                                           */
+    uint8_t pad[7];
+} pm_host_record;
 
 /* ---- environment --------------------------------------------------------- */
 /* gymPacMan_parallel_env.reset (gymPacMan.py:92-141) for every env with
@@ -134,6 +147,29 @@ int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_st
  * network on the same GPU. */
 int pm_step_host(const pm_env_desc *d, const uint8_t *actions_host, uint8_t *actions_dev,
                  const pm_step_out *out_dev, const pm_step_out *out_host, pm_stream_t stream);
+
+/* The same call, pipelined: the batch is cut into `n_chunks` env ranges that alternate between two
+ * internal streams, so the device-to-host copy of one range's records overlaps the kernel of the
+ * next.  Per step: one H2D (actions), one launch and one D2H (pm_host_record) per chunk.  Work is
+ * ordered after everything already queued on `stream`, later work on `stream` is ordered after the
+ * step, and the call returns when `records_host` ([N] pm_host_record, pinned) is complete.
+ * out_dev->packed and actions_dev are required device scratch; other members of out_dev may be NULL
+ * except obs, which stays in HBM for the policy.  A pipe belongs to the CUDA device that was current
+ * when it was created and must not be used from two threads at once.                                */
+typedef struct pm_pipe pm_pipe;
+int pm_pipe_create(pm_pipe **pipe, int n_chunks);
+int pm_pipe_destroy(pm_pipe *pipe);
+int pm_step_host_pipelined(const pm_env_desc *d, pm_pipe *pipe, const uint8_t *actions_host, uint8_t *actions_dev,
+                           const pm_step_out *out_dev, struct pm_host_record *records_host, pm_stream_t stream);
+
+/* The same call with NO copy engine at all: `actions_pinned` ([N][4] uint8) and `records_pinned`
+ * ([N] pm_host_record) are page-locked host buffers (cudaHostAlloc / torch pin_memory); the step
+ * kernel reads the actions and writes the records straight across PCIe (coalesced 128-bit
+ * accesses), so one step is ONE launch plus a stream synchronise.  out_dev->packed is ignored;
+ * observations and any other non-NULL member of out_dev stay in device memory.
+ * PM_EINVAL if a buffer is not page-locked.                                                       */
+int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *out_dev,
+                        struct pm_host_record *records_pinned, pm_stream_t stream);
 
 /* Unpack the device state into plain arrays (GameState accessors,
  * capture.py:125-234): agents [N][4][7] int32 = x,y,dir,isPacman,scaredTimer,

@@ -18,7 +18,8 @@ PM_ERRORS = {-1: "PM_EINVAL (bad argument)", -2: "PM_ELAYOUT (malformed layout t
 EXPORTS = [
     "pm_abi_version", "pm_geom_words", "pm_layout_words", "pm_state_bytes", "pm_pack_geom", "pm_pack_layout",
     "pm_reset", "pm_step", "pm_observe", "pm_step_host", "pm_get_state",
-    "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm",
+    "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
+    "pm_step_host_pipelined", "pm_step_host_mapped",
 ]
 
 
@@ -43,7 +44,14 @@ class PmStepOut(C.Structure):
     _fields_ = [
         ("obs", C.c_void_p), ("obs_agent_stride", C.c_int64), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("legal", C.c_void_p), ("score_change", C.c_void_p), ("shaping", C.c_void_p), ("shaped_reward", C.c_void_p),
+        ("packed", C.c_void_p),     # ABI 3
     ]
+
+
+class PmHostRecord(C.Structure):
+    """struct pm_host_record (48 bytes)"""
+    _fields_ = [("reward_red", C.c_double), ("reward_blue", C.c_double), ("shaped_reward", C.c_float * 4),
+                ("score_change", C.c_int32), ("legal", C.c_uint8 * 4), ("done", C.c_uint8), ("pad", C.c_uint8 * 7)]
 
 
 def declare_pack_api(L):
@@ -86,6 +94,14 @@ def load():
     L.pm_observe.argtypes = [C.POINTER(PmEnvDesc), vp, i64, vp]
     L.pm_step_host.restype = i32
     L.pm_step_host.argtypes = [C.POINTER(PmEnvDesc), vp, vp, C.POINTER(PmStepOut), C.POINTER(PmStepOut), vp]
+    L.pm_pipe_create.restype = i32
+    L.pm_pipe_create.argtypes = [C.POINTER(vp), i32]
+    L.pm_pipe_destroy.restype = i32
+    L.pm_pipe_destroy.argtypes = [vp]
+    L.pm_step_host_pipelined.restype = i32
+    L.pm_step_host_pipelined.argtypes = [C.POINTER(PmEnvDesc), vp, vp, vp, C.POINTER(PmStepOut), vp, vp]
+    L.pm_step_host_mapped.restype = i32
+    L.pm_step_host_mapped.argtypes = [C.POINTER(PmEnvDesc), vp, C.POINTER(PmStepOut), vp, vp]
     L.pm_get_state.restype = i32
     L.pm_get_state.argtypes = [C.POINTER(PmEnvDesc), vp, vp, vp, vp, vp]
     L.pm_set_state.restype = i32
@@ -96,7 +112,7 @@ def load():
     L.pm_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, i32, i64, vp]
     L.pm_adv_norm.restype = i32
     L.pm_adv_norm.argtypes = [vp, vp, vp, i64, i32, vp]
-    if L.pm_abi_version() != 2:
+    if L.pm_abi_version() != 3:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MIN_CTAS) pm_env_kernel(const P
         if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, sm, M, tid, n0);
         else pm_phaseA_static<MODE>(P, sm, sm, M, tid, n0);
     }
-    if (P.obs == nullptr) return;
     __syncthreads();
+    if (MODE == PM_MODE_STEP && P.packed)
+        for (int t = tid; t < 3 * PM_E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
+    if (P.obs == nullptr) return;
 
     // ---- phase B: observations, one warp per (env, agent) ----
     pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
@@ -179,7 +181,7 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     P.actions = actions; P.act_size = action_itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
-    P.shaping = out->shaping; P.shaped = out->shaped_reward;
+    P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed;
     return launch_env<PM_MODE_STEP>(P, (cudaStream_t)stream);
 }
 
@@ -214,6 +216,85 @@ extern "C" int pm_step_host(const pm_env_desc *d, const uint8_t *actions_host, u
         }
     }
     return (int)cudaStreamSynchronize(st);
+}
+
+// ---- pipelined host-buffer step ------------------------------------------------
+struct pm_pipe {
+    int n_chunks, device;
+    cudaStream_t s[2];
+    cudaEvent_t start, done[2];
+};
+
+extern "C" int pm_pipe_create(pm_pipe **pipe, int n_chunks) {
+    if (!pipe || n_chunks < 1 || n_chunks > 64) return PM_EINVAL;
+    pm_pipe *p = new pm_pipe();
+    p->n_chunks = n_chunks;
+    if (cudaGetDevice(&p->device) != cudaSuccess) { delete p; return PM_ENOGPU; }
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&p->s[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->start, cudaEventDisableTiming);
+    if (e != cudaSuccess) { delete p; return (int)e; }
+    *pipe = p;
+    return 0;
+}
+
+extern "C" int pm_pipe_destroy(pm_pipe *p) {
+    if (!p) return PM_EINVAL;
+    for (int i = 0; i < 2; ++i) { cudaStreamDestroy(p->s[i]); cudaEventDestroy(p->done[i]); }
+    cudaEventDestroy(p->start);
+    delete p;
+    return 0;
+}
+
+extern "C" int pm_step_host_pipelined(const pm_env_desc *d, pm_pipe *p, const uint8_t *actions_host, uint8_t *actions_dev,
+                                      const pm_step_out *od, pm_host_record *records_host, pm_stream_t stream) {
+    if (!d || !p || !actions_host || !actions_dev || !od || !od->packed || !records_host) return PM_EINVAL;
+    if (d->env_begin != 0 || d->env_count != 0) return PM_EINVAL;
+    cudaStream_t caller = (cudaStream_t)stream;
+    const int64_t N = d->n_envs;
+    const int C = p->n_chunks;
+    int64_t per = ((N + C - 1) / C + 31) & ~(int64_t)31;           // chunk size, multiple of 32 envs
+    cudaError_t e = cudaEventRecord(p->start, caller);
+    if (e != cudaSuccess) return (int)e;
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamWaitEvent(p->s[i], p->start, 0)) != cudaSuccess) return (int)e;
+    pm_env_desc dc = *d;
+    int used = 0;
+    for (int64_t b = 0; b < N; b += per, ++used) {
+        const int64_t cnt = (N - b < per) ? N - b : per;
+        cudaStream_t st = p->s[used & 1];
+        e = cudaMemcpyAsync(actions_dev + 4 * b, actions_host + 4 * b, (size_t)cnt * 4, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+        dc.env_begin = b; dc.env_count = cnt;
+        if (int rc = pm_step(&dc, actions_dev, 1, od, (pm_stream_t)st)) return rc;
+        e = cudaMemcpyAsync(records_host + b, od->packed + b, (size_t)cnt * sizeof(pm_host_record), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return (int)e;
+    }
+    for (int i = 0; i < 2; ++i) {
+        if ((e = cudaEventRecord(p->done[i], p->s[i])) != cudaSuccess) return (int)e;
+        if ((e = cudaStreamWaitEvent(caller, p->done[i], 0)) != cudaSuccess) return (int)e;
+    }
+    for (int i = 0; i < 2; ++i)
+        if ((e = cudaStreamSynchronize(p->s[i])) != cudaSuccess) return (int)e;
+    return 0;
+}
+
+// ---- zero-copy host step ----------------------------------------------------------
+extern "C" int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *od,
+                                   pm_host_record *records_pinned, pm_stream_t stream) {
+    if (!d || !actions_pinned || !od || !records_pinned) return PM_EINVAL;
+    void *a_dev = nullptr, *r_dev = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&a_dev, (void *)actions_pinned, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return PM_EINVAL; }        // not pinned / not mapped
+    e = cudaHostGetDevicePointer(&r_dev, (void *)records_pinned, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return PM_EINVAL; }
+    pm_step_out o = *od;
+    o.packed = (pm_host_record *)r_dev;
+    if (int rc = pm_step(d, a_dev, 1, &o, stream)) return rc;
+    return (int)cudaStreamSynchronize((cudaStream_t)stream);
 }
 
 extern "C" int pm_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc,

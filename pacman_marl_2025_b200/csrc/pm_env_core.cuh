@@ -20,6 +20,7 @@
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "pm_format.h"
 
@@ -54,6 +55,20 @@ PM_HD double pm_dmul(double a, double b) {
     volatile double r = a * b; return r;
 #endif
 }
+PM_HD uint64_t pm_dbits(double d) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t u; memcpy(&u, &d, 8); return u;
+#endif
+}
+PM_HD uint32_t pm_fbits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
 PM_HD uint32_t pm_funnel_r(uint32_t lo, uint32_t hi, int r) {
 #if defined(__CUDA_ARCH__)
     return __funnelshift_r(lo, hi, r);
@@ -79,6 +94,7 @@ struct PmParams {
     const void *actions; int act_size;
     float *obs; int64_t obs_agent_stride;
     double *reward; uint8_t *done; uint8_t *legal; int32_t *score_change; double *shaping; float *shaped;
+    void *packed;                       // [N] pm_host_record
     const uint8_t *mask;                // reset only
 };
 
@@ -90,8 +106,9 @@ struct PmParams {
 //                      slot k is the working copy during sub-move k and the
 //                      snapshot agent k is observed from afterwards
 //   posA/posB/patch[k] : the four agent bit positions and the own-cell patch
+//   rec               : the CTA's pm_host_record block (E x 48 bytes), 16-byte aligned
 struct PmSmem {
-    int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, food, caps, total;
+    int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, total;
     int E1;                             // padded env stride
 };
 PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L) {
@@ -110,6 +127,8 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L) {
     m.posA = o; o += 4 * m.E1;
     m.posB = o; o += 4 * m.E1;
     m.patch = o; o += 4 * m.E1;
+    o = (o + 3) & ~3;
+    m.rec = o; o += 12 * E;             // pm_host_record staging: 12 words per env, written out coalesced
     m.food = o; o += 4 * NW * m.E1;
     m.caps = o; o += has_caps ? 4 * NW * m.E1 : 0;
     o = (o + 3) & ~3;
@@ -437,19 +456,28 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     if (P.reward) { P.reward[n] = red_r; P.reward[P.N + n] = blue_r; }
     if (P.done) P.done[n] = term ? 1 : 0;
     if (P.score_change) P.score_change[n] = sc_total;
-    if (P.legal) {
-        uint32_t lm = 0;
+    uint32_t lm = 0;
+    if (P.legal || P.packed) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, g.y[i] * W + g.x[i]) << (8 * i);
-        reinterpret_cast<uint32_t *>(P.legal)[n] = lm;
+        if (P.legal) reinterpret_cast<uint32_t *>(P.legal)[n] = lm;
     }
+    float shaped[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+        const double team = (i & 1) ? blue_r : red_r;          // sum over both learners = 2 * team reward
+        shaped[i] = (float)pm_dadd(pm_dadd(team, team), pm_dmul(P.shaping_scale, shap[i]));
         if (P.shaping) P.shaping[(size_t)i * P.N + n] = shap[i];
-        if (P.shaped) {
-            const double team = (i & 1) ? blue_r : red_r;      // sum over both learners = 2 * team reward
-            P.shaped[(size_t)i * P.N + n] = (float)pm_dadd(pm_dadd(team, team), pm_dmul(P.shaping_scale, shap[i]));
-        }
+        if (P.shaped) P.shaped[(size_t)i * P.N + n] = shaped[i];
+    }
+    if (P.packed) {                                             // struct pm_host_record (48 B) -> smem staging
+        pm_u4 r0, r1, r2;
+        const uint64_t rr = pm_dbits(red_r), rb = pm_dbits(blue_r);
+        r0.x = (uint32_t)rr; r0.y = (uint32_t)(rr >> 32); r0.z = (uint32_t)rb; r0.w = (uint32_t)(rb >> 32);
+        r1.x = pm_fbits(shaped[0]); r1.y = pm_fbits(shaped[1]); r1.z = pm_fbits(shaped[2]); r1.w = pm_fbits(shaped[3]);
+        r2.x = (uint32_t)sc_total; r2.y = lm; r2.z = term ? 1u : 0u; r2.w = 0u;
+        pm_u4 *rec = reinterpret_cast<pm_u4 *>(sm + M.rec) + 3 * el;
+        rec[0] = r0; rec[1] = r1; rec[2] = r2;
     }
     // ---- state write-back ----
     pm_pack_agents(g, A, B);
@@ -524,6 +552,17 @@ PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm,
         for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, g.y[i] * W + g.x[i]) << (8 * i);
         reinterpret_cast<uint32_t *>(P.legal)[n] = lm;
     }
+}
+
+// Copy the CTA's record block from shared memory to P.packed with 128-bit stores, consecutive
+// threads = consecutive 16-byte pieces (a warp writes 512 contiguous bytes).  P.packed may be
+// device memory or MAPPED PINNED HOST memory (pm_step_host_mapped): coalescing is what turns the
+// latter into full-size PCIe writes.
+PM_HD void pm_records_out(const PmParams &P, const uint32_t *sm, const PmSmem &M, int tid, int64_t n0) {
+    const int64_t left = P.n_end - n0;
+    const int valid = (int)(left < P.E ? left : P.E);
+    if (tid >= 3 * valid) return;
+    reinterpret_cast<pm_u4 *>(P.packed)[3 * (size_t)n0 + tid] = reinterpret_cast<const pm_u4 *>(sm + M.rec)[tid];
 }
 
 // ============================================================================

@@ -377,6 +377,78 @@ class gymPacMan_parallel_env:
         self.steps += 1
         return self._host
 
+    def step_host_pipelined(self, actions_host: torch.Tensor, n_chunks: int = 4):
+        """One step with HOST buffers through ``pm_step_host_pipelined``: the batch is cut into
+        ``n_chunks`` env ranges on two internal streams so the copy-back of one range overlaps the
+        kernel of the next, and every small output travels in ONE 48-byte record per env
+        (``struct pm_host_record``).  Returns a dict of views into the pinned record buffer:
+        reward [N,2] f64 (red, blue), shaped_reward [N,4] f32, score_change [N] i32, legal [N,4] u8,
+        done [N] u8.  Observations stay in HBM (``self._obs``)."""
+        if actions_host.device.type != "cpu" or actions_host.dtype != torch.uint8 or not actions_host.is_contiguous():
+            raise ValueError("actions_host must be a contiguous CPU uint8 [N,4] tensor")
+        if actions_host.numel() != 4 * self.num_envs:
+            raise ValueError(f"expected {self.num_envs}x4 actions")
+        N = self.num_envs
+        if getattr(self, "_pipe_chunks", None) != n_chunks:
+            if getattr(self, "_pipe", None):
+                self._L.pm_pipe_destroy(self._pipe)
+            pipe = C.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pm_pipe_create(C.byref(pipe), int(n_chunks)), "pm_pipe_create")
+            self._pipe, self._pipe_chunks = pipe, n_chunks
+        if not hasattr(self, "_rec_host"):
+            self._rec_dev = torch.empty((N, 48), dtype=torch.uint8, device=self.device)
+            self._rec_host = torch.empty((N, 48), dtype=torch.uint8).pin_memory()
+            if not hasattr(self, "_act_dev"):
+                self._act_dev = torch.empty((N, 4), dtype=torch.uint8, device=self.device)
+            so = self._step_out
+            self._pipe_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None,
+                                            self._rec_dev.data_ptr())
+            self._rec_views = self._record_views(self._rec_host)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_step_host_pipelined(C.byref(self._desc), self._pipe, actions_host.data_ptr(),
+                                                      self._act_dev.data_ptr(), C.byref(self._pipe_out),
+                                                      self._rec_host.data_ptr(), self._stream()),
+                       "pm_step_host_pipelined")
+        self._version += 1
+        self.steps += 1
+        return self._rec_views
+
+    def _record_views(self, r):
+        return dict(reward=r.view(torch.float64)[:, 0:2], shaped_reward=r.view(torch.float32)[:, 4:8],
+                    score_change=r.view(torch.int32)[:, 8], legal=r[:, 36:40], done=r[:, 40])
+
+    def step_host_mapped(self, actions_host: torch.Tensor):
+        """One step with HOST buffers and no copy engine (``pm_step_host_mapped``): the kernel reads the
+        pinned ``actions_host`` ([N,4] uint8) and writes one ``pm_host_record`` per env into a pinned host
+        buffer straight across PCIe; the call returns after a stream synchronise.  Same return value as
+        :meth:`step_host_pipelined`."""
+        if (actions_host.device.type != "cpu" or actions_host.dtype != torch.uint8 or not actions_host.is_contiguous()
+                or not actions_host.is_pinned()):
+            raise ValueError("actions_host must be a contiguous, pinned CPU uint8 [N,4] tensor")
+        if actions_host.numel() != 4 * self.num_envs:
+            raise ValueError(f"expected {self.num_envs}x4 actions")
+        if not hasattr(self, "_rec_mapped"):
+            self._rec_mapped = torch.zeros((self.num_envs, 48), dtype=torch.uint8).pin_memory()
+            self._rec_mapped_views = self._record_views(self._rec_mapped)
+            so = self._step_out
+            self._mapped_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None, None)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_step_host_mapped(C.byref(self._desc), actions_host.data_ptr(),
+                                                   C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
+                                                   self._stream()), "pm_step_host_mapped")
+        self._version += 1
+        self.steps += 1
+        return self._rec_mapped_views
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pipe", None):
+                self._L.pm_pipe_destroy(self._pipe)
+                self._pipe = None
+        except Exception:
+            pass
+
     def observe_batched(self, out: Optional[torch.Tensor] = None):
         """get_Observation for all four agents of every env on the CURRENT state."""
         if out is None:

@@ -36,6 +36,8 @@ static void run(const PmParams &P) {
             if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, sm, M, el, n0);
             else pm_phaseA_static<MODE>(P, sm, sm, M, el, n0);
         }
+        if (MODE == PM_MODE_STEP && P.packed)
+            for (int t = 0; t < 3 * P.E; ++t) pm_records_out(P, sm, M, t, n0);
         if (!P.obs) continue;
         for (int w = 0; w < EMU_THREADS / 32; ++w)
             for (int lane = 0; lane < 32; ++lane) pm_phaseB<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0);
@@ -59,7 +61,7 @@ extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize,
     P.actions = actions; P.act_size = itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
-    P.shaping = out->shaping; P.shaped = out->shaped_reward;
+    P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed;
     run<PM_MODE_STEP>(P);
     return 0;
 }

@@ -80,9 +80,10 @@ class EmuEnv:
                  done=np.zeros(self.N, np.uint8), legal=np.zeros((self.N, 4), np.uint8),
                  score_change=np.zeros(self.N, np.int32), shaping=np.zeros((4, self.N)),
                  shaped=np.zeros((4, self.N), np.float32))
+        self.last_packed = np.zeros((self.N, 48), np.uint8)           # struct pm_host_record per env
         so = pmlib.PmStepOut(o["obs"].ctypes.data, o["obs"][0].size, o["reward"].ctypes.data, o["done"].ctypes.data,
                              o["legal"].ctypes.data, o["score_change"].ctypes.data, o["shaping"].ctypes.data,
-                             o["shaped"].ctypes.data)
+                             o["shaped"].ctypes.data, self.last_packed.ctypes.data)
         rc = lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
         assert rc == 0, rc
         return o

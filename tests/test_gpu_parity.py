@@ -2,6 +2,7 @@
 the golden fixtures recorded from the reference and vs the CPU oracle on the
 same seeded inputs.  Bit-exact for integer state, masks, fp64 rewards, fp32 obs
 and GAE; 1e-5 for advantage normalisation.  Run on the B200 box: -m gpu."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -114,6 +115,44 @@ def test_step_host_entry_matches_device_entry():
         for k in ("obs", "reward", "done", "legal", "score_change"):
             np.testing.assert_array_equal(h[k].numpy(), o1[k], err_msg=f"t={t} {k}")
         np.testing.assert_array_equal(h["shaped_reward"].numpy(), o1["shaped"])
+
+
+def test_step_host_pipelined_matches_device_entry():
+    """pm_step_host_pipelined (chunked, two streams, packed 48-byte records) == pm_step."""
+    rows = lay_rows("tinyCapture")
+    for N, chunks in ((1000, 4), (257, 3), (64, 1), (4096, 8), (3001, 1)):
+        e1, e2 = CudaEnv(rows, N, length=40, auto_reset=True), CudaEnv(rows, N, length=40, auto_reset=True)
+        e1.reset(); e2.reset()
+        rng = np.random.default_rng(N)
+        for t in range(60):
+            a = biased_actions(rng, N, 0.6, t)
+            o1 = e1.step(a)
+            if chunks == 1:          # the zero-copy entry: kernel reads pinned actions / writes pinned records over PCIe
+                h = e2.env.step_host_mapped(torch.as_tensor(a).pin_memory())
+            else:
+                h = e2.env.step_host_pipelined(torch.as_tensor(a).pin_memory(), n_chunks=chunks)
+            np.testing.assert_array_equal(h["reward"].numpy().T, o1["reward"], err_msg=f"N={N} t={t}")
+            np.testing.assert_array_equal(h["shaped_reward"].numpy().T, o1["shaped"])
+            np.testing.assert_array_equal(h["score_change"].numpy(), o1["score_change"])
+            np.testing.assert_array_equal(h["legal"].numpy(), o1["legal"])
+            np.testing.assert_array_equal(h["done"].numpy(), o1["done"])
+            assert torch.equal(e2.env._obs, e1.env._obs)
+        s1, s2 = e1.get_state(), e2.get_state()
+        for k in s1:
+            np.testing.assert_array_equal(s1[k], s2[k])
+
+
+def test_step_host_mapped_rejects_pageable_memory():
+    from pacman_marl_2025_b200 import _lib
+    env = CudaEnv(lay_rows("tinyCapture"), 64).env
+    a = torch.zeros((64, 4), dtype=torch.uint8)
+    with pytest.raises(ValueError):
+        env.step_host_mapped(a)
+    rec = torch.zeros((64, 48), dtype=torch.uint8).pin_memory()
+    rc = env._L.pm_step_host_mapped(C.byref(env._desc), a.data_ptr(), C.byref(env._step_out), rec.data_ptr(), None)
+    assert rc == -1                                     # PM_EINVAL: actions not page-locked
+    torch.cuda.synchronize()
+    env.step_host_mapped(a.pin_memory())                # and the context is still healthy
 
 
 def test_properties_at_full_size():

@@ -63,3 +63,25 @@ def test_emulated_env_ranges_and_shard_invariance():
     from parity_bodies import body_env_ranges, body_shard_invariant_random_agents
     body_env_ranges(lambda rows, n, **kw: EmuEnv(rows, n, E=32, KB=1, **kw), lambda e, b, c: e.set_range(b, c))
     body_shard_invariant_random_agents(lambda rows, n, **kw: EmuEnv(rows, n, E=16, KB=1, **kw))
+
+
+def test_emulated_packed_host_record_matches_separate_outputs():
+    """struct pm_host_record (one 48-byte record per env) carries exactly the separate small outputs."""
+    import ctypes as C
+    from pacman_marl_2025_b200 import _lib
+    assert C.sizeof(_lib.PmHostRecord) == 48
+    rows = lay_rows("tinyCapture")
+    N = 70
+    env = EmuEnv(rows, N, length=30, auto_reset=True, E=16, KB=1)
+    env.reset()
+    rng = np.random.default_rng(2)
+    from parity_bodies import biased_actions
+    for t in range(60):
+        o = env.step(biased_actions(rng, N, 0.6, t))
+        p = env.last_packed
+        np.testing.assert_array_equal(p[:, 0:16].copy().view(np.float64), o["reward"].T)
+        np.testing.assert_array_equal(p[:, 16:32].copy().view(np.float32), o["shaped"].T)
+        np.testing.assert_array_equal(p[:, 32:36].copy().view(np.int32)[:, 0], o["score_change"])
+        np.testing.assert_array_equal(p[:, 36:40], o["legal"])
+        np.testing.assert_array_equal(p[:, 40], o["done"])
+        assert not p[:, 41:].any()
