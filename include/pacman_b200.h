@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 3
+#define PM_ABI_VERSION 4
 
 /* argument errors */
 #define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
@@ -91,7 +91,20 @@ typedef struct pm_env_desc {
     /* launch only envs [env_begin, env_begin + env_count) of the batch; env_count 0 = all.
        env_begin must be a multiple of 32.  Outputs are still indexed by the batch-wide env number. */
     int64_t env_begin, env_count;
+    /* ---- ABI 4: on-device opponents (the team interface of gymPacMan.py:33-40,157) ---- */
+    /* one nibble per agent: 0 = plays `actions`; 1 = randomTeam (same as random_agent_mask);
+       2 / 3 = baselineTeam's OffensiveReflexAgent / DefensiveReflexAgent
+       (agents/baselineTeam.py:56-187): one-step look-ahead over the legal actions with
+       integer features and maze distances, evaluated at the agent's own sub-move.        */
+    int32_t bot_kind;
+    int32_t bot_first_best;        /* baselineTeam tie-break: 0 = uniform over the best actions (random.choice,
+                                      counter-based draw), 1 = first best in N,S,E,W,Stop order (parity tests) */
+    const uint16_t *dist;          /* [dev] pm_distances output [L][nmax][nmax]; required for kinds 2, 3        */
+    const int16_t *node_of_cell;   /* [dev] pm_distances output [L][H*W]                                        */
+    int32_t dist_nmax, reserved1;
 } pm_env_desc;
+
+enum { PM_BOT_NONE = 0, PM_BOT_RANDOM = 1, PM_BOT_BASELINE_OFFENSE = 2, PM_BOT_BASELINE_DEFENSE = 3 };
 
 /* Outputs of one step; any pointer may be NULL to skip that output. */
 typedef struct pm_step_out {
@@ -108,6 +121,9 @@ typedef struct pm_step_out {
     /* ---- ABI 3 ---- */
     struct pm_host_record *packed; /* [dev] [N] every small per-env output in one 48-byte record, so a host-side
                                      consumer needs ONE device-to-host copy per step (pm_step_host_pipelined)  */
+    /* ---- ABI 4 ---- */
+    uint8_t *actions_used;         /* [dev] [N][4] the action every agent actually played (illegal requests
+                                     appear as Stop, bot agents as the bot's choice)                          */
 } pm_step_out;
 
 /* What a CPU-side caller of gymPacMan.step reads back every step (gymPacMan.py:184-193), one record per env. */

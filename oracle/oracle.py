@@ -38,6 +38,11 @@ def lib():
         L.pmo_reset_outputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pmo_get_state.argtypes = [C.c_void_p] * 5
         L.pmo_step_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int, C.c_int]
+        L.pmo_step_batch_bots.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10 + [C.c_int, C.c_int]
+        L.pmo_sizeof_dist_table.restype = C.c_size_t
+        L.pmo_build_dist_table.restype = C.c_int
+        L.pmo_build_dist_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.pmo_set_distances.argtypes = [C.c_void_p, C.c_void_p]
         L.pmo_max_threads.restype = C.c_int
         L.pmo_distances.restype = C.c_int
         L.pmo_distances.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -115,6 +120,39 @@ class OracleBatch:
         L.pmo_step_batch(C.c_void_p(self.buf.ctypes.data), self.N, _p(a), _p(out["obs"]), _p(out["reward"]),
                          _p(out["done"]), _p(out["legal"]), _p(out["score_change"]), _p(out["shaping"]),
                          int(auto_reset), int(nthreads))
+        return out
+
+    def set_bots(self, bot_kind):
+        """bot_kind[4]: 0 = driven by the caller's actions, 2 / 3 = baselineTeam Offensive / Defensive reflex
+        agent.  Builds the maze-distance table(s) the bots look up (one per distinct board)."""
+        L = lib()
+        self.bot_kind = np.ascontiguousarray(bot_kind, np.uint8)
+        self._tables = {}
+        cap = self.W * self.H
+        for n in range(self.N):
+            key = bytes(self.buf[n * self.esz:(n + 1) * self.esz][:8 + 64 * 64])       # W, H, walls
+            if key not in self._tables:
+                t = np.zeros(int(L.pmo_sizeof_dist_table()), np.uint8)
+                d = np.zeros(cap * cap, np.int32)
+                assert L.pmo_build_dist_table(self._env(n), _p(t), _p(d), cap) > 0
+                self._tables[key] = (t, d)
+            L.pmo_set_distances(self._env(n), _p(self._tables[key][0]))
+
+    def step_bots(self, actions, with_obs=True, auto_reset=False, nthreads=1):
+        """Like step(), with the agents flagged by set_bots() choosing their own action at their sub-move
+        (ties -> first best).  Adds actions_used [N,4] and best_masks [N,4] (bit a = action a is a best action)."""
+        L = lib()
+        a = np.ascontiguousarray(np.asarray(actions, dtype=np.int32).reshape(self.N, 4))
+        out = dict(
+            obs=np.empty((self.N, 4) + self.obs_shape, np.float32) if with_obs else None,
+            reward=np.zeros((self.N, 2), np.float64), done=np.zeros(self.N, np.uint8),
+            legal=np.zeros((self.N, 4), np.uint8), score_change=np.zeros(self.N, np.int32),
+            shaping=np.zeros((self.N, 4), np.float64), actions_used=np.zeros((self.N, 4), np.int32),
+            best_masks=np.zeros((self.N, 4), np.uint8))
+        L.pmo_step_batch_bots(C.c_void_p(self.buf.ctypes.data), self.N, _p(a), _p(self.bot_kind), _p(out["obs"]),
+                              _p(out["reward"]), _p(out["done"]), _p(out["legal"]), _p(out["score_change"]),
+                              _p(out["shaping"]), _p(out["actions_used"]), _p(out["best_masks"]), int(auto_reset),
+                              int(nthreads))
         return out
 
     def observe(self, n, agent):

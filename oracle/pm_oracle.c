@@ -74,7 +74,17 @@ typedef struct {
     int reward_legal, defence_reward;
     /* own-cell plane of the last observation handed out per agent (for shaping) */
     int snap_x[4], snap_y[4], snap_carry[4];
+    /* bot support (agents/baselineTeam.py): shared all-pairs table, set by pmo_set_distances */
+    const struct pmo_dist_table *dt;
 } pmo_env;
+
+/* distanceCalculator.Distancer as the bots use it (distanceCalculator.py:38-62): a lookup
+ * keyed by two grid points.  dist[i * n + j], nodes numbered x-major / y-minor.            */
+typedef struct pmo_dist_table {
+    int n;
+    int16_t node_of[PMO_MAXW][PMO_MAXH];
+    int32_t *dist;
+} pmo_dist_table;
 
 size_t pmo_sizeof_env(void) { return sizeof(pmo_env); }
 
@@ -351,12 +361,24 @@ static double shaping_value(int py, int px, int pcarry, int ny, int nx) {
 /* gymPacMan.py:143-193.
  * obs: [4][8][H][W] fp32 or NULL; reward[2] = {red, blue}; legal[4] bitmasks from
  * the FINAL state; shaping[4] vs. the previous observation of each agent.       */
-void pmo_step(pmo_env *e, const int32_t *actions, float *obs, double *reward, uint8_t *done,
-              uint8_t *legal, int32_t *score_change, double *shaping) {
+static int baseline_choose(const pmo_env *e, int idx, int kind, int *best_mask);
+
+/* bot_kind[4] (or NULL): 0 = agent plays actions_in[idx]; 2 / 3 = baselineTeam Offensive / Defensive reflex agent
+ * choosing at its own sub-move from the live state (gymPacMan.py:157), ties -> FIRST best action in the
+ * reference's action order.  actions_used[4] / best_masks[4] (optional) report what was played.            */
+void pmo_step_bots(pmo_env *e, const int32_t *actions_in, const uint8_t *bot_kind, float *obs, double *reward,
+                   uint8_t *done, uint8_t *legal, int32_t *score_change, double *shaping, int32_t *actions_used,
+                   uint8_t *best_masks) {
     double blue_reward = 0, red_reward = 0;
     int sc = 0, blue_sc = 0, red_sc = 0;
     int HW = e->W * e->H;
+    int32_t actions[4];
     for (int idx = 0; idx < 4; ++idx) {
+        actions[idx] = actions_in[idx];
+        int bm = 0;
+        if (bot_kind && bot_kind[idx] >= 2) actions[idx] = baseline_choose(e, idx, bot_kind[idx], &bm);
+        if (actions_used) actions_used[idx] = actions[idx];
+        if (best_masks) best_masks[idx] = (uint8_t)bm;
         pmo_env next = *e;
         successor(&next, idx, actions[idx]);
         if (idx == 1 || idx == 3) {
@@ -390,6 +412,92 @@ void pmo_step(pmo_env *e, const int32_t *actions, float *obs, double *reward, ui
     *done = (uint8_t)term;
     for (int i = 0; i < 4; ++i) legal[i] = (uint8_t)legal_mask(e, i);
     *score_change = sc;
+}
+
+void pmo_step(pmo_env *e, const int32_t *actions, float *obs, double *reward, uint8_t *done,
+              uint8_t *legal, int32_t *score_change, double *shaping) {
+    pmo_step_bots(e, actions, NULL, obs, reward, done, legal, score_change, shaping, NULL, NULL);
+}
+
+/* ------------------------------------------------------------------- bots */
+/* agents/baselineTeam.py:56-187 on top of captureAgents.py (getFood :176-187, getOpponents :211-220,
+ * getMazeDistance :250-258).  All feature values and weights are integers, so Q-values are exact.   */
+static int maze_dist(const pmo_env *e, int x1, int y1, int x2, int y2) {
+    const pmo_dist_table *t = e->dt;
+    int a = t->node_of[x1][y1], b = t->node_of[x2][y2];
+    if (a < 0 || b < 0) abort();                       /* 'Positions not in grid' */
+    int d = t->dist[a * t->n + b];
+    return d < 0 ? 65535 : d;                          /* unreachable: sys.maxsize in the reference; only the order matters */
+}
+
+/* self.getFood(state): the food this agent's team eats = the OTHER side's half grid */
+static int food_to_eat(const pmo_env *s, int red, int *fx, int *fy) {
+    int halfway = (int)(s->W / 2.0), n = 0;
+    int x0 = red ? halfway : 0, x1 = red ? s->W : halfway;       /* red eats getBlueFood (x >= W//2) */
+    for (int x = x0; x < x1; ++x) for (int y = 0; y < s->H; ++y)   /* Grid.asList order: x-major */
+        if (s->food[x][y]) { if (fx) { fx[n] = x; fy[n] = y; } n++; }
+    return n;
+}
+
+static const int REF_ORDER[5] = {A_NORTH, A_SOUTH, A_EAST, A_WEST, A_STOP};   /* game.py:295-299 */
+static const int REVERSE[5] = {A_SOUTH, A_WEST, A_NORTH, A_EAST, A_STOP};      /* game.py:60-64   */
+
+static long evaluate_action(const pmo_env *e, int idx, int kind, int action) {
+    pmo_env s = *e;
+    successor(&s, idx, action);                        /* getSuccessor: positions are always grid points */
+    int red = e->team_red[idx];
+    const pmo_agent *me = &s.ag[idx];
+    if (kind == 2) {                                   /* OffensiveReflexAgent :132-150 */
+        static _Thread_local int fx[PMO_MAXW * PMO_MAXH], fy[PMO_MAXW * PMO_MAXH];
+        int n = food_to_eat(&s, red, fx, fy);
+        long v = 100L * -n;
+        if (n > 0) {
+            int best = maze_dist(&s, me->x, me->y, fx[0], fy[0]);
+            for (int k = 1; k < n; ++k) { int d = maze_dist(&s, me->x, me->y, fx[k], fy[k]); if (d < best) best = d; }
+            v += -1L * best;
+        }
+        return v;
+    }
+    /* DefensiveReflexAgent :159-187 */
+    long v = 0;
+    v += 100L * (me->is_pacman ? 0 : 1);
+    int ninv = 0, best = 0;
+    for (int o = 0; o < 4; ++o) {
+        if (s.team_red[o] == red || !s.ag[o].is_pacman) continue;
+        int d = maze_dist(&s, me->x, me->y, s.ag[o].x, s.ag[o].y);
+        if (ninv == 0 || d < best) best = d;
+        ninv++;
+    }
+    v += -1000L * ninv;
+    if (ninv > 0) v += -10L * best;
+    if (action == A_STOP) v += -100;
+    if (action == REVERSE[e->ag[idx].dir]) v += -2;
+    return v;
+}
+
+/* ReflexCaptureAgent.chooseAction :65-92 */
+static int baseline_choose(const pmo_env *e, int idx, int kind, int *best_mask) {
+    if (!e->dt) abort();
+    int legal = legal_mask(e, idx), red = e->team_red[idx];
+    int acts[5], na = 0;
+    for (int k = 0; k < 5; ++k) if ((legal >> REF_ORDER[k]) & 1) acts[na++] = REF_ORDER[k];
+    long vals[5], mx = 0;
+    for (int k = 0; k < na; ++k) { vals[k] = evaluate_action(e, idx, kind, acts[k]); if (k == 0 || vals[k] > mx) mx = vals[k]; }
+    int first = -1, mask = 0;
+    for (int k = 0; k < na; ++k) if (vals[k] == mx) { if (first < 0) first = acts[k]; mask |= 1 << acts[k]; }
+    if (food_to_eat(e, red, NULL, NULL) <= 0) {        /* nothing left to eat: head for the start cell */
+        int bestd = 9999, besta = -1;
+        for (int k = 0; k < na; ++k) {
+            pmo_env s = *e;
+            successor(&s, idx, acts[k]);
+            int d = maze_dist(&s, e->ag[idx].sx, e->ag[idx].sy, s.ag[idx].x, s.ag[idx].y);
+            if (d < bestd) { besta = acts[k]; bestd = d; }
+        }
+        if (best_mask) *best_mask = 1 << besta;
+        return besta;
+    }
+    if (best_mask) *best_mask = mask;
+    return first;
 }
 
 /* reset outputs: obs[4][8][H][W] (all from the initial state) and legal masks */
@@ -434,6 +542,23 @@ void pmo_step_batch(pmo_env *envs, int64_t N, const int32_t *actions, float *obs
     for (int64_t n = 0; n < N; ++n) {
         pmo_step(&envs[n], actions + 4 * n, obs ? obs + per * n : NULL, reward + 2 * n, done + n,
                  legal + 4 * n, score_change + n, shaping ? shaping + 4 * n : NULL);
+        if (auto_reset && done[n]) pmo_reset(&envs[n]);
+    }
+}
+
+void pmo_step_batch_bots(pmo_env *envs, int64_t N, const int32_t *actions, const uint8_t *bot_kind, float *obs,
+                         double *reward, uint8_t *done, uint8_t *legal, int32_t *score_change, double *shaping,
+                         int32_t *actions_used, uint8_t *best_masks, int auto_reset, int nthreads) {
+    if (N <= 0) return;
+    size_t per = (size_t)4 * 8 * envs[0].W * envs[0].H;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t n = 0; n < N; ++n) {
+        pmo_step_bots(&envs[n], actions + 4 * n, bot_kind, obs ? obs + per * n : NULL, reward + 2 * n, done + n,
+                      legal + 4 * n, score_change + n, shaping ? shaping + 4 * n : NULL,
+                      actions_used ? actions_used + 4 * n : NULL, best_masks ? best_masks + 4 * n : NULL);
         if (auto_reset && done[n]) pmo_reset(&envs[n]);
     }
 }
@@ -550,3 +675,20 @@ void pmo_adv_norm(const float *adv, const int64_t *inds, float *out, int n, int 
         for (int i = 0; i < k; ++i) out[s + i] = (adv[inds[s + i]] - mean_f) / (std_f + 1e-8f);
     }
 }
+
+/* ---------------------------------------------------------------- bot distance tables */
+int pmo_distances(const pmo_env *e, int32_t *out, int out_cap, int16_t *nodes_xy);
+size_t pmo_sizeof_dist_table(void) { return sizeof(pmo_dist_table); }
+/* Fill `t` (caller-allocated, pmo_sizeof_dist_table bytes) for env e's board; `buf` holds n*n int32 and must
+ * outlive every env that points at the table. */
+int pmo_build_dist_table(const pmo_env *e, pmo_dist_table *t, int32_t *buf, int cap) {
+    int16_t *nodes = (int16_t *)malloc(sizeof(int16_t) * 2 * PMO_MAXW * PMO_MAXH);
+    int n = pmo_distances(e, buf, cap, nodes);
+    if (n < 0) { free(nodes); return -1; }
+    for (int x = 0; x < PMO_MAXW; ++x) for (int y = 0; y < PMO_MAXH; ++y) t->node_of[x][y] = -1;
+    for (int k = 0; k < n; ++k) t->node_of[nodes[2 * k]][nodes[2 * k + 1]] = (int16_t)k;
+    t->n = n; t->dist = buf;
+    free(nodes);
+    return n;
+}
+void pmo_set_distances(pmo_env *e, const pmo_dist_table *t) { e->dt = t; }

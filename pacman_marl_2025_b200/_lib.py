@@ -36,6 +36,9 @@ class PmEnvDesc(C.Structure):
         # ABI 2
         ("auto_reset", C.c_int32), ("reserved0", C.c_int32), ("env_index_base", C.c_int64),
         ("env_begin", C.c_int64), ("env_count", C.c_int64),
+        # ABI 4
+        ("bot_kind", C.c_int32), ("bot_first_best", C.c_int32), ("dist", C.c_void_p), ("node_of_cell", C.c_void_p),
+        ("dist_nmax", C.c_int32), ("reserved1", C.c_int32),
     ]
 
 
@@ -45,6 +48,7 @@ class PmStepOut(C.Structure):
         ("obs", C.c_void_p), ("obs_agent_stride", C.c_int64), ("reward", C.c_void_p), ("done", C.c_void_p),
         ("legal", C.c_void_p), ("score_change", C.c_void_p), ("shaping", C.c_void_p), ("shaped_reward", C.c_void_p),
         ("packed", C.c_void_p),     # ABI 3
+        ("actions_used", C.c_void_p),   # ABI 4
     ]
 
 
@@ -112,7 +116,7 @@ def load():
     L.pm_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, i32, i64, vp]
     L.pm_adv_norm.restype = i32
     L.pm_adv_norm.argtypes = [vp, vp, vp, i64, i32, vp]
-    if L.pm_abi_version() != 3:
+    if L.pm_abi_version() != 4:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

@@ -32,10 +32,12 @@
 #define PM_E 32                                   // envs per CTA (power of two <= PM_THREADS)
 #endif
 
-template <int MODE>
-__global__ void __launch_bounds__(PM_THREADS, PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
+// BOTS = 1: the variant with the baselineTeam look-ahead compiled in (one more bitset slot of shared
+// memory as scratch); the plain variant pays nothing for it.
+template <int MODE, int BOTS>
+__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
-    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, BOTS ? 5 : 4);
     const int tid = threadIdx.x;
     const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * PM_E;
 
@@ -51,7 +53,7 @@ __global__ void __launch_bounds__(PM_THREADS, PM_MIN_CTAS) pm_env_kernel(const P
 
     // ---- phase A: rules, one thread per env ----
     if (tid < PM_E) {
-        if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, sm, M, tid, n0);
+        if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS>(P, sm, sm, M, tid, n0);
         else pm_phaseA_static<MODE>(P, sm, sm, M, tid, n0);
     }
     __syncthreads();
@@ -134,25 +136,30 @@ static int env_int(const char *name, int dflt) {
 
 static int fill_params(const pm_env_desc *d, PmParams &P) { return pm_fill_params(d, P, PM_E); }
 
-template <int MODE>
+template <int MODE, int BOTS>
 static int launch_env(const PmParams &P, cudaStream_t st) {
-    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, BOTS ? 5 : 4);
     const size_t smem = (size_t)M.total * 4;
-    static size_t configured[64][3];                   // per device, per kernel instance
+    static size_t configured[64][3][2];                // per device, per kernel instance
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
-    if (smem > configured[dev & 63][MODE]) {
-        cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > configured[dev & 63][MODE][BOTS]) {
+        cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         // the kernel streams its output and keeps its working set in shared memory: prefer smem over L1
-        e = cudaFuncSetAttribute(pm_env_kernel<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        configured[dev & 63][MODE] = smem;
+        configured[dev & 63][MODE][BOTS] = smem;
     }
     const unsigned grid = (unsigned)((P.n_end - P.n_begin + PM_E - 1) / PM_E);
-    pm_env_kernel<MODE><<<grid, PM_THREADS, smem, st>>>(P);
+    pm_env_kernel<MODE, BOTS><<<grid, PM_THREADS, smem, st>>>(P);
     return (int)cudaGetLastError();
+}
+
+static bool has_lookahead_bots(const PmParams &P) {
+    for (int i = 0; i < 4; ++i) if (((P.bot_kind >> (4 * i)) & 15) >= 2) return true;
+    return false;
 }
 
 extern "C" int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, int64_t obs_agent_stride, uint8_t *legal,
@@ -161,7 +168,7 @@ extern "C" int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, i
     if (int rc = fill_params(d, P)) return rc;
     if (obs && (obs_agent_stride & 3)) return PM_EINVAL;
     P.mask = mask; P.obs = obs; P.obs_agent_stride = obs_agent_stride; P.legal = legal;
-    return launch_env<PM_MODE_RESET>(P, (cudaStream_t)stream);
+    return launch_env<PM_MODE_RESET, 0>(P, (cudaStream_t)stream);
 }
 
 extern "C" int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream) {
@@ -169,7 +176,7 @@ extern "C" int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_st
     if (int rc = fill_params(d, P)) return rc;
     if (!obs || (obs_agent_stride & 3)) return PM_EINVAL;
     P.obs = obs; P.obs_agent_stride = obs_agent_stride;
-    return launch_env<PM_MODE_OBSERVE>(P, (cudaStream_t)stream);
+    return launch_env<PM_MODE_OBSERVE, 0>(P, (cudaStream_t)stream);
 }
 
 extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
@@ -181,8 +188,9 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     P.actions = actions; P.act_size = action_itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
-    P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed;
-    return launch_env<PM_MODE_STEP>(P, (cudaStream_t)stream);
+    P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
+    return has_lookahead_bots(P) ? launch_env<PM_MODE_STEP, 1>(P, (cudaStream_t)stream)
+                                 : launch_env<PM_MODE_STEP, 0>(P, (cudaStream_t)stream);
 }
 
 // ---- host-buffer step ------------------------------------------------------

@@ -86,7 +86,9 @@ struct PmParams {
     uint8_t *state;
     int length, reward_legal, defence;
     double shaping_scale;
-    int bot_mask; unsigned long long bot_seed;   // in-kernel uniform-random-legal agents
+    int bot_kind; unsigned long long bot_seed;   // per-agent nibble: 0 caller's action, 1 random legal, 2/3 baselineTeam
+    int bot_first_best;                 // baselineTeam tie-break: first best action instead of a random one
+    const uint16_t *dist; const int16_t *node_of_cell; int dist_nmax;   // maze-distance tables (pm_distances)
     int auto_reset;                     // step: terminal envs restart inside the launch
     int64_t n_base;                     // global index of env 0 (keys the random draws)
     int64_t n_begin, n_end;             // env range of this launch
@@ -95,6 +97,7 @@ struct PmParams {
     float *obs; int64_t obs_agent_stride;
     double *reward; uint8_t *done; uint8_t *legal; int32_t *score_change; double *shaping; float *shaped;
     void *packed;                       // [N] pm_host_record
+    uint8_t *act_used;                  // [N][4] the action each agent actually played
     const uint8_t *mask;                // reset only
 };
 
@@ -111,7 +114,7 @@ struct PmSmem {
     int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, total;
     int E1;                             // padded env stride
 };
-PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L) {
+PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots = 4) {
     const int NW = pm_nw(HW), NCAT = pm_ncat(HW);
     PmSmem m;
     m.E1 = E | 1;
@@ -129,8 +132,8 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L) {
     m.patch = o; o += 4 * m.E1;
     o = (o + 3) & ~3;
     m.rec = o; o += 12 * E;             // pm_host_record staging: 12 words per env, written out coalesced
-    m.food = o; o += 4 * NW * m.E1;
-    m.caps = o; o += has_caps ? 4 * NW * m.E1 : 0;
+    m.food = o; o += nslots * NW * m.E1;   // slots 0-3: per-agent snapshots; slot 4 (bots): look-ahead scratch
+    m.caps = o; o += has_caps ? nslots * NW * m.E1 : 0;
     o = (o + 3) & ~3;
     m.blk_words = o - m.blk0;
     m.total = o;
@@ -216,15 +219,19 @@ PM_HD int pm_legal_mask(const uint32_t *walls, int W, int c) {   // game.py:335-
 // Uniform draw from the set bits of `legal` (randomTeam: random.choice(legal actions),
 // agents/randomTeam.py:94-100).  Counter-based so a trajectory depends only on
 // (seed, global env index, episode, step, agent) and not on launch geometry or sharding.
-PM_HD int pm_random_legal(int legal, unsigned long long seed, unsigned long long n, unsigned episode, unsigned ctr) {
+PM_HD uint32_t pm_random_u32(unsigned long long seed, unsigned long long n, unsigned episode, unsigned ctr) {
     unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (n + 1) +
                            0xD1B54A32D192ED03ull * (((unsigned long long)episode << 32) + ctr + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+PM_HD int pm_random_legal(int legal, unsigned long long seed, unsigned long long n, unsigned episode, unsigned ctr) {
+    const unsigned long long z32 = pm_random_u32(seed, n, episode, ctr);
     int cnt = 0;
     for (int b = 0; b < 5; ++b) cnt += (legal >> b) & 1;
-    int pick = (int)(((z >> 32) * (unsigned long long)cnt) >> 32);
+    int pick = (int)((z32 * (unsigned long long)cnt) >> 32);
     for (int b = 0; b < 5; ++b)
         if ((legal >> b) & 1) { if (pick == 0) return b; --pick; }
     return 4;
@@ -273,6 +280,247 @@ PM_HD void pm_pack_agents(const PmAgents &g, pm_u4 &A, pm_u4 &B) {
 // ============================================================================
 // phase A, MODE_STEP
 // ============================================================================
+// Per-env constants of a step, and the mutable board counters a sub-move touches.
+struct PmCtx {
+    int W, H, NW, E1, ND, HW;
+    const uint32_t *walls, *dumptab;
+    uint32_t teams;
+};
+struct PmBoard {
+    int rf, bf;                        // pellets on the red (x < W//2) / blue food half
+    bool food_dirty, caps_dirty;
+};
+
+// GameState.generateSuccessor for agent A playing the (already legalised) gym action u:
+// AgentRules.applyAction + consume + checkDeath + decrementTimer (capture.py:107-123, 468-728)
+// on agents `g` and the bitsets fk / ck (word stride X.E1).  Returns the score change.
+template <int A>
+PM_HD int pm_submove(const PmCtx &X, PmAgents &g, uint32_t *fk, uint32_t *ck, PmBoard &b, int u) {
+    const int W = X.W, E1 = X.E1;
+    const uint32_t teams = X.teams;
+    // ---- AgentRules.applyAction (capture.py:468-517) ----
+    const int dx = (u == 1) - (u == 3), dy = (u == 0) - (u == 2);
+    g.x[A] += dx; g.y[A] += dy;
+    const int c = g.y[A] * W + g.x[A];
+    if (u != 4) g.dir[A] = u;                          // Stop keeps the heading, game.py:115-117
+    const int is_red = (teams >> A) & 1;
+    g.pac[A] = is_red ^ (2 * g.x[A] < W ? 1 : 0);
+    int pacflag = g.pac[A];
+    int sc = 0;
+    if (g.carry[A] > 0 && !g.pac[A]) {
+        sc = is_red ? g.carry[A] : -g.carry[A];
+        g.ret[A] += g.carry[A];
+        g.carry[A] = 0;
+        pacflag = g.pac[3];                            // the rebinding quirk: capture.py:505 -> :514
+    }
+    if (pacflag) {                                     // AgentRules.consume (capture.py:519-560)
+        if (pm_sbit(fk, E1, c)) {
+            bool given = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (!given && (int)((teams >> i) & 1) == is_red && g.x[i] == g.x[A] && g.y[i] == g.y[A]) { g.carry[i] += 1; given = true; }
+            fk[(c >> 5) * E1] &= ~(1u << (c & 31));
+            b.food_dirty = true;
+            if (g.x[A] < (W >> 1)) --b.rf; else --b.bf;
+        }
+        if (ck && pm_sbit(ck, E1, c) && (is_red ? (2 * g.x[A] > W) : (2 * g.x[A] <= W))) {
+            ck[(c >> 5) * E1] &= ~(1u << (c & 31));
+            b.caps_dirty = true;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if ((int)((teams >> i) & 1) != is_red) g.scared[i] = PM_SCARED_TIME;
+        }
+    }
+    // ---- AgentRules.checkDeath (capture.py:670-728) ----
+    // The branch (mover is pacman / ghost) is chosen once; enemies are then
+    // visited in index order against live positions and timers.
+    const bool mover_is_pac = g.pac[A] != 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (e == A) continue;
+        if ((int)((teams >> e) & 1) == is_red) continue;
+        if (g.x[e] != g.x[A] || g.y[e] != g.y[A]) continue;
+        uint32_t added = 0;
+        if (mover_is_pac) {
+            if (!g.pac[e]) added = pm_collide(g, A, e, W, X.H, X.ND, X.dumptab, X.walls, fk, ck, E1);   // A = pacman, e = ghost
+        } else {
+            if (g.pac[e]) added = pm_collide(g, e, A, W, X.H, X.ND, X.dumptab, X.walls, fk, ck, E1);    // e = pacman, A = ghost
+        }
+        if (added) { b.rf += (int)(added & 0xffff); b.bf += (int)(added >> 16); b.food_dirty = true; }
+    }
+    g.scared[A] = g.scared[A] > 0 ? g.scared[A] - 1 : 0;      // decrementTimer, capture.py:562-567
+    return sc;
+}
+
+// ---- on-device baselineTeam (agents/baselineTeam.py:56-187) -------------------
+// Maze distances come from the table pm_distances built for this env's board
+// (Distancer.getDistance, distanceCalculator.py:38-62): dist[node(a) * nmax + node(b)].
+struct PmDist {
+    const uint16_t *dist; const int16_t *node_of; int nmax;
+};
+PM_HD int pm_maze_dist(const PmDist &D, int ca, int cb) {
+    return (int)D.dist[(size_t)D.node_of[ca] * D.nmax + D.node_of[cb]];
+}
+
+// Q(s, a) of ReflexCaptureAgent.evaluate for the successor state (g2, fs): integer features x integer weights.
+template <int A>
+PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2, const uint32_t *fs, const PmBoard &b2,
+                            int kind, int u, int dir_before) {
+    const int W = X.W, is_red = (X.teams >> A) & 1;
+    const int me = g2.y[A] * W + g2.x[A];
+    if (kind == 2) {                                   // OffensiveReflexAgent.getFeatures / getWeights (:132-150)
+        const int n = is_red ? b2.bf : b2.rf;          // len(self.getFood(successor).asList()): the half this team eats
+        int v = -100 * n;
+        if (n > 0) {
+            int best = 0x7fffffff;
+            const int half = W >> 1;
+            for (int w = 0; w < X.NW; ++w) {
+                uint32_t bits = fs[w * X.E1];
+                while (bits) {
+#if defined(__CUDA_ARCH__)
+                    const int bpos = __ffs((int)bits) - 1;
+#else
+                    const int bpos = __builtin_ctz(bits);
+#endif
+                    bits &= bits - 1;
+                    const int c = 32 * w + bpos, x = c % W;
+                    if ((x >= half) != (is_red != 0)) continue;            // red eats x >= W//2, blue eats x < W//2
+                    const int d = pm_maze_dist(D, me, c);
+                    best = d < best ? d : best;
+                }
+            }
+            v -= best;
+        }
+        return v;
+    }
+    // DefensiveReflexAgent.getFeatures / getWeights (:159-187)
+    int v = g2.pac[A] ? 0 : 100;                       // onDefense
+    int ninv = 0, best = 0;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        if ((int)((X.teams >> o) & 1) == is_red || !g2.pac[o]) continue;
+        const int d = pm_maze_dist(D, me, g2.y[o] * W + g2.x[o]);
+        if (ninv == 0 || d < best) best = d;
+        ++ninv;
+    }
+    v -= 1000 * ninv;
+    if (ninv > 0) v -= 10 * best;
+    if (u == 4) v -= 100;                              // stop
+    const int rev = dir_before == 4 ? 4 : (dir_before ^ 2);   // Directions.REVERSE on gym ints: N0<->S2, E1<->W3
+    if (u == rev) v -= 2;
+    return v;
+}
+
+// ReflexCaptureAgent.chooseAction (:65-92): evaluate every legal action on a scratch copy of the
+// state, keep the best set, break ties with `rnd` (random.choice) or take the first (test hook).
+// fs / cs: scratch bitsets (slot 4).  Returns the gym action; *best_mask = the best set.
+template <int A>
+PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAgents &g, const uint32_t *fk, const uint32_t *ck,
+                             uint32_t *fs, uint32_t *cs, const PmBoard &b, int legal, int kind, uint32_t rnd,
+                             bool first_best) {
+    const int order[5] = {0, 2, 1, 3, 4};              // Actions.getPossibleActions: N, S, E, W, Stop (game.py:295-299)
+    const int is_red = (X.teams >> A) & 1;
+    const bool go_home = (is_red ? b.bf : b.rf) <= 0;  // foodLeft <= 0: walk towards self.start (:79-90)
+    const int start_c = g.sy[A] * X.W + g.sx[A];
+    int vals[5], bestv = -0x7fffffff, home_a = 4, home_d = 9999;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int u = order[k];
+        vals[k] = -0x7fffffff;
+        if (!((legal >> u) & 1)) continue;
+        for (int w = 0; w < X.NW; ++w) fs[w * X.E1] = fk[w * X.E1];
+        if (ck) for (int w = 0; w < X.NW; ++w) cs[w * X.E1] = ck[w * X.E1];
+        PmAgents g2 = g;
+        PmBoard b2 = b;
+        pm_submove<A>(X, g2, fs, ck ? cs : nullptr, b2, u);
+        if (go_home) {
+            const int d = pm_maze_dist(D, start_c, g2.y[A] * X.W + g2.x[A]);
+            if (d < home_d) { home_d = d; home_a = u; }
+        } else {
+            vals[k] = pm_baseline_value<A>(X, D, g2, fs, b2, kind, u, g.dir[A]);
+            bestv = vals[k] > bestv ? vals[k] : bestv;
+        }
+    }
+    if (go_home) return home_a;
+    int nb = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) nb += (vals[k] == bestv && ((legal >> order[k]) & 1)) ? 1 : 0;
+    int pick = first_best ? 0 : (int)(((unsigned long long)rnd * (unsigned)nb) >> 32);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (vals[k] == bestv && ((legal >> order[k]) & 1)) { if (pick == 0) return order[k]; --pick; }
+    return 4;
+}
+
+// Everything a step accumulates across the four turns.
+struct PmStepAcc {
+    PmBoard b;
+    int score, sc_total, red_sc, blue_sc;
+    double red_r, blue_r, shap[4];
+    uint32_t snap[4];
+    uint32_t act_used;                 // the action each agent actually played, one byte per agent
+};
+
+// One turn of gymPacMan.step's loop for agent A (gymPacMan.py:149-167): pick the action (caller's,
+// random legal, or baselineTeam), get_reward bookkeeping, the sub-move, the observation snapshot.
+template <int A, int BOTS>
+PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const PmSmem &M, int el, int64_t n, uint32_t lid,
+                         PmAgents &g, uint32_t *food, uint32_t *caps, PmStepAcc &S, uint32_t act4, int steps,
+                         uint32_t episode) {
+    const int NW = X.NW, E1 = X.E1, W = X.W;
+    uint32_t *fk = food + (size_t)A * NW * E1;
+    uint32_t *ck = caps ? caps + (size_t)A * NW * E1 : nullptr;
+    if (A > 0) {                                       // working copy for this sub-move; slot A-1 stays as snapshot
+        for (int w = 0; w < NW; ++w) fk[w * E1] = fk[(w - NW) * E1];
+        if (ck) for (int w = 0; w < NW; ++w) ck[w * E1] = ck[(w - NW) * E1];
+    }
+    // ---- get_reward pre-state (gymPacMan.py:231-259) ----
+    const bool gym_red = (A & 1) == 0;
+    const int o1 = gym_red ? 1 : 0, o2 = o1 + 2;
+    const int mine_before = gym_red ? S.b.rf : S.b.bf, theirs_before = gym_red ? S.b.bf : S.b.rf;
+    const int pb1 = g.pac[o1], pb2 = g.pac[o2];
+
+    const int legal = pm_legal_mask(X.walls, W, g.y[A] * W + g.x[A]);
+    int u = (act4 >> (8 * A)) & 0xff;
+    const int kind = (P.bot_kind >> (4 * A)) & 15;
+    if (kind == 1) {
+        u = pm_random_legal(legal, P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
+    } else if (BOTS && kind >= 2) {
+        PmDist D;
+        D.nmax = P.dist_nmax;
+        D.dist = P.dist + (size_t)lid * P.dist_nmax * P.dist_nmax;
+        D.node_of = P.node_of_cell + (size_t)lid * X.HW;
+        const uint32_t rnd = pm_random_u32(P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
+        u = pm_baseline_choose<A>(X, D, g, fk, ck, food + (size_t)4 * NW * E1, caps ? caps + (size_t)4 * NW * E1 : nullptr,
+                                  S.b, legal, kind, rnd, P.bot_first_best != 0);
+    }
+    const bool req_legal = u <= 4 && ((legal >> u) & 1);
+    if (!req_legal) u = 4;                             // illegal -> Stop, capture.py:472-475
+    S.act_used |= (uint32_t)u << (8 * A);
+
+    const int sc = pm_submove<A>(X, g, fk, ck, S.b, u);
+    S.score += sc;
+    S.sc_total += sc;
+    if (gym_red) S.red_sc += sc; else S.blue_sc -= sc;
+
+    // ---- get_reward post-state ----
+    double r = gym_red ? S.red_r : S.blue_r;
+    const int mine_after = gym_red ? S.b.rf : S.b.bf, theirs_after = gym_red ? S.b.bf : S.b.rf;
+    if (mine_before < mine_after) r = pm_dadd(r, 1.0);
+    if (theirs_before > theirs_after) r = pm_dadd(r, 0.1);
+    if (P.defence) {
+        if (pb1 && !g.pac[o1] && g.x[o1] == g.sx[o1] && g.y[o1] == g.sy[o1]) r = pm_dadd(r, 0.25);
+        if (pb2 && !g.pac[o2] && g.x[o2] == g.sx[o2] && g.y[o2] == g.sy[o2]) r = pm_dadd(r, 0.25);
+    }
+    if (P.reward_legal && req_legal) r = pm_dadd(r, 0.01);
+    if (gym_red) S.red_r = r; else S.blue_r = r;
+
+    // ---- observation snapshot for agent A (gymPacMan.py:166) + shaping ----
+    pm_store_snapshot(sm, M, P, A, el, g);
+    S.shap[A] = pm_shaping((int)(S.snap[A] & 0xff), (int)((S.snap[A] >> 8) & 0xff), (int)(S.snap[A] >> 16), g.x[A], g.y[A]);
+    S.snap[A] = (uint32_t)g.x[A] | (uint32_t)g.y[A] << 8 | (uint32_t)g.carry[A] << 16;
+}
+
+template <int BOTS>
 PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
     if (n >= P.n_end) { sm[M.lid + el] = 0xffffffffu; return; }
@@ -281,15 +529,16 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
     const uint32_t *walls = lay + pm_l_walls(P.HW);
     const uint32_t *tail = lay + pm_l_tail(P.HW);
-    const uint32_t *dumptab = P.geom + pm_g_dump_off(P.HW);
-    const int W = P.W, H = P.H, NW = P.NW, E1 = M.E1;
+    const int W = P.W, NW = P.NW, E1 = M.E1;
     const int64_t NP = pm_np(P.N);
-    const uint32_t teams = tail[PM_L_TEAMS];
+    PmCtx X;
+    X.W = W; X.H = P.H; X.NW = NW; X.E1 = E1; X.ND = P.ND; X.HW = P.HW;
+    X.walls = walls; X.dumptab = P.geom + pm_g_dump_off(P.HW); X.teams = tail[PM_L_TEAMS];
 
     // ---- load state (128-bit loads, coalesced across the env dimension) ----
     pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
     pm_u4 B = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agB(P.N))[n];
-    pm_u4 S = reinterpret_cast<const pm_u4 *>(P.state + pm_st_snap(P.N))[n];
+    pm_u4 Sn = reinterpret_cast<const pm_u4 *>(P.state + pm_st_snap(P.N))[n];
     pm_u4 Mi = reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n];
     uint32_t *gfood = reinterpret_cast<uint32_t *>(P.state + pm_st_food(P.N));
     uint32_t *gcaps = reinterpret_cast<uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
@@ -300,10 +549,14 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
 
     PmAgents g;
     pm_unpack_agents(g, A, B, tail);
-    int score = (int)Mi.x, steps = (int)Mi.y;
-    int rf = (int)(Mi.z & 0xffff), bf = (int)(Mi.z >> 16);       // pellets on the red / blue food half
+    int steps = (int)Mi.y;
     uint32_t episode = Mi.w;                                      // restarts of this env (keys the random draws)
-    uint32_t snap[4] = {S.x, S.y, S.z, S.w};
+    PmStepAcc S;
+    S.score = (int)Mi.x;
+    S.b.rf = (int)(Mi.z & 0xffff); S.b.bf = (int)(Mi.z >> 16);
+    S.b.food_dirty = false; S.b.caps_dirty = false;
+    S.sc_total = 0; S.red_sc = 0; S.blue_sc = 0; S.red_r = 0.0; S.blue_r = 0.0; S.act_used = 0;
+    S.snap[0] = Sn.x; S.snap[1] = Sn.y; S.snap[2] = Sn.z; S.snap[3] = Sn.w;
 
     uint32_t act4;
     if (P.act_size == 1) act4 = reinterpret_cast<const uint32_t *>(P.actions)[n];
@@ -314,104 +567,21 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         for (int i = 0; i < 4; ++i) { long long v = a8[i]; act4 |= (uint32_t)((v < 0 || v > 4) ? 255 : (int)v) << (8 * i); }
     }
 
-    double red_r = 0.0, blue_r = 0.0, shap[4];
-    int sc_total = 0, red_sc = 0, blue_sc = 0;
-    bool food_dirty = false, caps_dirty = false;
+    pm_agent_turn<0, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<1, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<2, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<3, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
 
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        uint32_t *fk = food + (size_t)a * NW * E1;
-        uint32_t *ck = caps ? caps + (size_t)a * NW * E1 : nullptr;
-        if (a > 0) {                                   // working copy for this sub-move; slot a-1 stays as snapshot
-            for (int w = 0; w < NW; ++w) fk[w * E1] = fk[(w - NW) * E1];
-            if (ck) for (int w = 0; w < NW; ++w) ck[w * E1] = ck[(w - NW) * E1];
-        }
-        // ---- get_reward pre-state (gymPacMan.py:231-259) ----
-        const bool gym_red = (a & 1) == 0;
-        const int o1 = gym_red ? 1 : 0, o2 = o1 + 2;
-        const int mine_before = gym_red ? rf : bf, theirs_before = gym_red ? bf : rf;
-        const int pb1 = g.pac[o1], pb2 = g.pac[o2];
-
-        // ---- AgentRules.applyAction (capture.py:468-517) ----
-        int c = g.y[a] * W + g.x[a];
-        const int legal = pm_legal_mask(walls, W, c);
-        int u = (act4 >> (8 * a)) & 0xff;
-        if ((P.bot_mask >> a) & 1) u = pm_random_legal(legal, P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + a);
-        const bool req_legal = u <= 4 && ((legal >> u) & 1);
-        if (!req_legal) u = 4;
-        const int dx = (u == 1) - (u == 3), dy = (u == 0) - (u == 2);
-        g.x[a] += dx; g.y[a] += dy; c += dx + dy * W;
-        if (u != 4) g.dir[a] = u;                      // Stop keeps the heading, game.py:115-117
-        const int is_red = (teams >> a) & 1;
-        g.pac[a] = is_red ^ (2 * g.x[a] < W ? 1 : 0);
-        int pacflag = g.pac[a];
-        int sc = 0;
-        if (g.carry[a] > 0 && !g.pac[a]) {
-            sc = is_red ? g.carry[a] : -g.carry[a];
-            g.ret[a] += g.carry[a];
-            g.carry[a] = 0;
-            pacflag = g.pac[3];                        // the rebinding quirk: capture.py:505 -> :514
-        }
-        if (pacflag) {                                 // AgentRules.consume (capture.py:519-560)
-            if (pm_sbit(fk, E1, c)) {
-                bool given = false;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (!given && (int)((teams >> i) & 1) == is_red && g.x[i] == g.x[a] && g.y[i] == g.y[a]) { g.carry[i] += 1; given = true; }
-                fk[(c >> 5) * E1] &= ~(1u << (c & 31));
-                food_dirty = true;
-                if (g.x[a] < (W >> 1)) --rf; else --bf;
-            }
-            if (ck && pm_sbit(ck, E1, c) && (is_red ? (2 * g.x[a] > W) : (2 * g.x[a] <= W))) {
-                ck[(c >> 5) * E1] &= ~(1u << (c & 31));
-                caps_dirty = true;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) if ((int)((teams >> i) & 1) != is_red) g.scared[i] = PM_SCARED_TIME;
-            }
-        }
-        // ---- AgentRules.checkDeath (capture.py:670-728) ----
-        // The branch (mover is pacman / ghost) is chosen once; enemies are then
-        // visited in index order against live positions and timers.
-        const bool mover_is_pac = g.pac[a] != 0;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            if (e == a) continue;
-            if ((int)((teams >> e) & 1) == is_red) continue;
-            if (g.x[e] != g.x[a] || g.y[e] != g.y[a]) continue;
-            uint32_t added = 0;
-            if (mover_is_pac) {
-                if (!g.pac[e]) added = pm_collide(g, a, e, W, H, P.ND, dumptab, walls, fk, ck, E1);   // a = pacman, e = ghost
-            } else {
-                if (g.pac[e]) added = pm_collide(g, e, a, W, H, P.ND, dumptab, walls, fk, ck, E1);    // e = pacman, a = ghost
-            }
-            if (added) { rf += (int)(added & 0xffff); bf += (int)(added >> 16); food_dirty = true; }
-        }
-        g.scared[a] = g.scared[a] > 0 ? g.scared[a] - 1 : 0;      // decrementTimer, capture.py:562-567
-        score += sc;
-        sc_total += sc;
-        if (gym_red) red_sc += sc; else blue_sc -= sc;
-
-        // ---- get_reward post-state ----
-        double r = gym_red ? red_r : blue_r;
-        const int mine_after = gym_red ? rf : bf, theirs_after = gym_red ? bf : rf;
-        if (mine_before < mine_after) r = pm_dadd(r, 1.0);
-        if (theirs_before > theirs_after) r = pm_dadd(r, 0.1);
-        if (P.defence) {
-            if (pb1 && !g.pac[o1] && g.x[o1] == g.sx[o1] && g.y[o1] == g.sy[o1]) r = pm_dadd(r, 0.25);
-            if (pb2 && !g.pac[o2] && g.x[o2] == g.sx[o2] && g.y[o2] == g.sy[o2]) r = pm_dadd(r, 0.25);
-        }
-        if (P.reward_legal && req_legal) r = pm_dadd(r, 0.01);
-        if (gym_red) red_r = r; else blue_r = r;
-
-        // ---- observation snapshot for agent a (gymPacMan.py:166) + shaping ----
-        pm_store_snapshot(sm, M, P, a, el, g);
-        shap[a] = pm_shaping((int)(snap[a] & 0xff), (int)((snap[a] >> 8) & 0xff), (int)(snap[a] >> 16), g.x[a], g.y[a]);
-        snap[a] = (uint32_t)g.x[a] | (uint32_t)g.y[a] << 8 | (uint32_t)g.carry[a] << 16;
-    }
+    int score = S.score, rf = S.b.rf, bf = S.b.bf;
+    const int sc_total = S.sc_total;
+    double red_r = S.red_r, blue_r = S.blue_r;
+    bool food_dirty = S.b.food_dirty, caps_dirty = S.b.caps_dirty;
+    uint32_t *snap = S.snap;
+    const double *shap = S.shap;
 
     // ---- step epilogue (gymPacMan.py:171-193) ----
-    blue_r = pm_dadd(blue_r, (double)(blue_sc > 0 ? blue_sc : 0));
-    red_r = pm_dadd(red_r, (double)(red_sc > 0 ? red_sc : 0));
+    blue_r = pm_dadd(blue_r, (double)(S.blue_sc > 0 ? S.blue_sc : 0));
+    red_r = pm_dadd(red_r, (double)(S.red_sc > 0 ? S.red_sc : 0));
     bool term = false;
     if (bf == 0 && g.carry[0] == 0 && g.carry[2] == 0) term = true;      // check_termination, :261-270
     if (rf == 0 && g.carry[1] == 0 && g.carry[3] == 0) term = true;
@@ -470,6 +640,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         if (P.shaping) P.shaping[(size_t)i * P.N + n] = shap[i];
         if (P.shaped) P.shaped[(size_t)i * P.N + n] = shaped[i];
     }
+    if (P.act_used) reinterpret_cast<uint32_t *>(P.act_used)[n] = S.act_used;
     if (P.packed) {                                             // struct pm_host_record (48 B) -> smem staging
         pm_u4 r0, r1, r2;
         const uint64_t rr = pm_dbits(red_r), rb = pm_dbits(blue_r);
@@ -483,8 +654,8 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     pm_pack_agents(g, A, B);
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
-    S.x = snap[0]; S.y = snap[1]; S.z = snap[2]; S.w = snap[3];
-    reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
+    Sn.x = snap[0]; Sn.y = snap[1]; Sn.z = snap[2]; Sn.w = snap[3];
+    reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = Sn;
     Mi.x = (uint32_t)score; Mi.y = (uint32_t)steps; Mi.z = (uint32_t)rf | (uint32_t)bf << 16; Mi.w = episode;
     reinterpret_cast<pm_u4 *>(P.state + pm_st_misc(P.N))[n] = Mi;
     if (food_dirty) for (int w = 0; w < NW; ++w) gfood[(size_t)w * NP + n] = food[(3 * NW + w) * E1];
@@ -687,7 +858,16 @@ static inline int pm_fill_params(const pm_env_desc *d, PmParams &P, int E) {
     P.geom = d->geom; P.layouts = d->layouts; P.layout_id = d->layout_id; P.state = (uint8_t *)d->state;
     P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
     P.shaping_scale = d->shaping_scale;
-    P.bot_mask = d->random_agent_mask & 15; P.bot_seed = d->random_seed;
+    P.bot_kind = 0;
+    for (int i = 0; i < 4; ++i) {
+        int k = (d->bot_kind >> (4 * i)) & 15;
+        if ((d->random_agent_mask >> i) & 1) k = 1;
+        if (k > 3) return PM_EINVAL;
+        if (k >= 2 && (!d->dist || !d->node_of_cell || d->dist_nmax <= 0)) return PM_EINVAL;
+        P.bot_kind |= k << (4 * i);
+    }
+    P.bot_seed = d->random_seed; P.bot_first_best = d->bot_first_best;
+    P.dist = d->dist; P.node_of_cell = d->node_of_cell; P.dist_nmax = d->dist_nmax;
     P.auto_reset = d->auto_reset != 0;
     P.n_base = d->env_index_base;
     P.n_begin = d->env_begin; P.n_end = d->env_count ? d->env_begin + d->env_count : d->n_envs;

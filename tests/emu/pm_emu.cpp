@@ -19,7 +19,9 @@ static int fill(const pm_env_desc *d, PmParams &P, int E, int /*KB*/) { return p
 
 template <int MODE>
 static void run(const PmParams &P) {
-    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L);
+    bool bots = false;
+    for (int i = 0; i < 4; ++i) bots |= ((P.bot_kind >> (4 * i)) & 15) >= 2;
+    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L, bots ? 5 : 4);
     std::vector<uint32_t> smv((size_t)M.total + 4);
     uint32_t *sm = smv.data();
     const int64_t nblk = (P.n_end - P.n_begin + P.E - 1) / P.E;
@@ -33,7 +35,7 @@ static void run(const PmParams &P) {
         for (int i = 0; i < 4 * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
         if (P.L == 1) for (int i = 0; i < P.LS; ++i) sm[M.lay + i] = P.layouts[i];
         for (int el = 0; el < P.E; ++el) {
-            if (MODE == PM_MODE_STEP) pm_phaseA_step(P, sm, sm, M, el, n0);
+            if (MODE == PM_MODE_STEP) { if (bots) pm_phaseA_step<1>(P, sm, sm, M, el, n0); else pm_phaseA_step<0>(P, sm, sm, M, el, n0); }
             else pm_phaseA_static<MODE>(P, sm, sm, M, el, n0);
         }
         if (MODE == PM_MODE_STEP && P.packed)
@@ -61,7 +63,7 @@ extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize,
     P.actions = actions; P.act_size = itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
-    P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed;
+    P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
     run<PM_MODE_STEP>(P);
     return 0;
 }

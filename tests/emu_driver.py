@@ -33,7 +33,7 @@ def _p(a):
 class EmuEnv:
     def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True,
                  shaping_scale=0.1, E=64, KB=4, layout_id=None, random_agent_mask=0, random_seed=0,
-                 auto_reset=False, env_index_base=0):
+                 auto_reset=False, env_index_base=0, bot_kind=None, bot_first_best=True):
         L = lib()
         per_env = not isinstance(layouts[0], str)
         lays = layouts if per_env else [layouts]
@@ -57,6 +57,23 @@ class EmuEnv:
                                     self.state.ctypes.data, int(length), int(reward_forLegalAction),
                                     int(defenceReward), int(random_agent_mask), float(shaping_scale), int(random_seed),
                                     int(auto_reset), 0, int(env_index_base), 0, 0)
+        if bot_kind is not None and any(k >= 2 for k in bot_kind):
+            # maze-distance tables in pm_distances' output format, built here by the ORACLE (the CUDA BFS kernel
+            # cannot run in the CPU emulation; it is checked against the same oracle in the GPU tests)
+            from oracle import oracle
+            HW = self.W * self.H
+            tabs = [oracle.distances(rows) for rows in lays]
+            nmax = (max(len(nodes) for nodes, _ in tabs) + 7) & ~7
+            self.dist = np.full((len(lays), nmax, nmax), 0xFFFF, np.uint16)
+            self.node_of = np.full((len(lays), HW), -1, np.int16)
+            for l, (nodes, d) in enumerate(tabs):
+                n = len(nodes)
+                self.dist[l, :n, :n] = np.where(d < 0, 0xFFFF, d).astype(np.uint16)
+                self.node_of[l, nodes[:, 1].astype(int) * self.W + nodes[:, 0].astype(int)] = np.arange(n)
+            self.desc.dist, self.desc.node_of_cell, self.desc.dist_nmax = self.dist.ctypes.data, self.node_of.ctypes.data, nmax
+        if bot_kind is not None:
+            self.desc.bot_kind = sum(int(k) << (4 * i) for i, k in enumerate(bot_kind))
+            self.desc.bot_first_best = int(bot_first_best)
         self.obs_shape = (8, self.H, self.W)
 
     def reset(self, mask=None):
@@ -81,9 +98,10 @@ class EmuEnv:
                  score_change=np.zeros(self.N, np.int32), shaping=np.zeros((4, self.N)),
                  shaped=np.zeros((4, self.N), np.float32))
         self.last_packed = np.zeros((self.N, 48), np.uint8)           # struct pm_host_record per env
+        o["actions_used"] = np.zeros((self.N, 4), np.uint8)
         so = pmlib.PmStepOut(o["obs"].ctypes.data, o["obs"][0].size, o["reward"].ctypes.data, o["done"].ctypes.data,
                              o["legal"].ctypes.data, o["score_change"].ctypes.data, o["shaping"].ctypes.data,
-                             o["shaped"].ctypes.data, self.last_packed.ctypes.data)
+                             o["shaped"].ctypes.data, self.last_packed.ctypes.data, o["actions_used"].ctypes.data)
         rc = lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
         assert rc == 0, rc
         return o
@@ -114,7 +132,8 @@ class SingleEnvDriver:
         n = self.n
         return dict(obs=np.asarray(o["obs"])[:, n], reward=np.asarray(o["reward"])[:, n], done=o["done"][n],
                     legal=np.asarray(o["legal"])[n], score_change=o["score_change"][n],
-                    shaping=np.asarray(o["shaping"])[:, n], shaped=np.asarray(o["shaped"])[:, n])
+                    shaping=np.asarray(o["shaping"])[:, n], shaped=np.asarray(o["shaped"])[:, n],
+                    actions_used=None if o.get("actions_used") is None else np.asarray(o["actions_used"])[n])
 
     def state(self):
         s = self.env.get_state()

@@ -157,16 +157,59 @@ def layout_text(name):
         return [ln.strip() for ln in f]
 
 
-def make_env(rows, **kw):
+def make_env(rows, enemie=None, **kw):
+    """enemie=None: self-play (all four agents driven by the recorded actions).  enemie='baselineTeam': the red
+    side (agents 0, 2) is played by the reference's bots (`gymPacMan.py:33-40, 157`)."""
     fd, path = tempfile.mkstemp(suffix=".lay")
     with os.fdopen(fd, "w") as f:
         f.write("\n".join(rows))
     try:
         with _quiet:
-            env = gymPacMan_parallel_env(layout_file=path, enemieName="randomTeam", self_play=True, **kw)
+            cwd = os.getcwd()
+            os.chdir(REF)                 # loadAgents resolves agents/<name>.py next to gymPacMan.py
+            try:
+                env = gymPacMan_parallel_env(layout_file=path, enemieName=enemie or "randomTeam",
+                                             self_play=enemie is None, **kw)
+            finally:
+                os.chdir(cwd)
     finally:
         os.unlink(path)
     return env
+
+
+class BotSpy:
+    """Records what the reference's bots decide.  `random.choice` (the tie-break of
+    `baselineTeam.py:92`) is pinned to the FIRST best action while recording, and the set of best
+    actions it was offered is kept, so a replay can either follow the same trajectory (tie-break =
+    first) or check that a randomly tie-broken choice lies inside the recorded set."""
+
+    def __init__(self, env):
+        self.env = env
+        self.choice_sets = []
+        self.taken = {}
+        self._orig_choice = random.choice
+        random.choice = self._choice
+        for i, ag in enumerate(env.agents):
+            if not isinstance(ag, int):
+                ag.getAction = self._wrap(i, ag.getAction)
+
+    def _choice(self, seq):
+        self.choice_sets.append(list(seq))
+        return seq[0]
+
+    def _wrap(self, i, fn):
+        def inner(state):
+            self.choice_sets = []
+            a = fn(state)
+            m = 0
+            for name in (self.choice_sets[-1] if self.choice_sets else [a]):
+                m |= 1 << DIR_ID[name]
+            self.taken[i] = (DIR_ID[a], m)
+            return a
+        return inner
+
+    def close(self):
+        random.choice = self._orig_choice
 
 
 # ---------------------------------------------------------------------------
@@ -301,18 +344,21 @@ class RandomPolicy:
 # ---------------------------------------------------------------------------
 # trajectory recorder
 # ---------------------------------------------------------------------------
-def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48, max_steps=None, **envkw):
+def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48, max_steps=None, enemie=None,
+           **envkw):
     rows = layout_text(lay_name)
     kw = dict(length=300, reward_forLegalAction=True, defenceReward=True)
     kw.update(envkw)
-    env = make_env(rows, **kw)
+    env = make_env(rows, enemie=enemie, **kw)
+    spy = BotSpy(env) if enemie else None
+    byidx = lambda d: {i: d[env.agents[i]] for i in range(4)}      # bot objects key the dicts of the red side
     rng = np.random.default_rng(seed)
     pol = SmartPolicy(env, rng) if policy == "smart" else RandomPolicy(env, rng)
     W, H = env.layout.width, env.layout.height
 
     R = dict(actions=[], pos=[], misc=[], food=[], caps=[], score=[], score_change=[], reward=[],
              done=[], legal=[], obs_dig=[], shaping=[], ep_start=[], reset_legal=[], reset_obs_dig=[],
-             full_obs=[])
+             full_obs=[], bot_best=[])
     cover = dict(steps=0, eats=0, returns=0, kills=0, dumps=0, scared_kills=0, caps=0, food_end=0,
                  rebinding=0, nonzero_final=0)
     _REBIND["n"] = _REBIND["ate"] = 0
@@ -320,6 +366,7 @@ def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48
         pol.new_episode()
         with _quiet:
             obs, info = env.reset()
+        obs, info["legal_actions"] = byidx(obs), byidx(info["legal_actions"])
         R["ep_start"].append(len(R["actions"]))
         R["reset_legal"].append([legal_mask(info["legal_actions"][i]) for i in range(4)])
         R["reset_obs_dig"].append([obs_digest(obs[i]) for i in range(4)])
@@ -329,6 +376,13 @@ def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48
             pre = snapshot(env)
             with _quiet:
                 nobs, rew, term, info = env.step({i: acts[i] for i in range(4)})
+            nobs, rew, info["legal_actions"] = byidx(nobs), byidx(rew), byidx(info["legal_actions"])
+            best = [0, 0, 0, 0]
+            if spy:                                   # what the bots really played replaces the ignored red entries
+                acts = list(acts)
+                for i, (a, m) in spy.taken.items():
+                    acts[i], best[i] = a, m
+            R["bot_best"].append(best)
             done = any(term.values())
             pos, misc, food, caps, score = snapshot(env)
             R["actions"].append(acts)
@@ -378,6 +432,11 @@ def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48
     out["reward_forLegalAction"] = np.uint8(kw["reward_forLegalAction"])
     out["defenceReward"] = np.uint8(kw["defenceReward"])
     out["WH"] = np.array([W, H], np.int32)
+    out["bot_best"] = out["bot_best"].astype(np.uint8)
+    # 0 = driven by `actions`, 2 / 3 = baselineTeam Offensive / Defensive reflex agent (createTeam order, baselineTeam.py:34-51)
+    out["bot_kind"] = np.array([2, 0, 3, 0] if enemie == "baselineTeam" else [0, 0, 0, 0], np.uint8)
+    if spy:
+        spy.close()
     np.savez_compressed(os.path.join(HERE, f"traj_{name}.npz"), **out)
     print(f"traj_{name}: {cover}", file=sys.stderr)
     return cover
@@ -500,6 +559,13 @@ def main():
             cov[f"maze{s}"] = record(f"maze{s}", f"maze{s}", "smart", episodes=3, seed=18 + s)
         cov["small_noflags"] = record("small_noflags", "smallCapture", "smart", episodes=3, seed=19, length=80,
                                       reward_forLegalAction=False, defenceReward=False)
+        digests["coverage"] = cov
+
+    if want("bots"):
+        cov = digests.get("coverage", {})
+        for lay, eps in (("tinyCapture", 3), ("smallCapture", 3), ("bloxCapture", 2), ("capsSmall", 2), ("maze7", 1)):
+            cov[f"bots_{lay}"] = record(f"bots_{lay}", lay, "smart", episodes=eps, seed=31, enemie="baselineTeam",
+                                        full_obs_steps=8)
         digests["coverage"] = cov
 
     if want("survey"):

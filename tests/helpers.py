@@ -82,3 +82,27 @@ def replay(fx, drv, where=""):
         for t in range(ep_starts[ep], ep_starts[ep + 1]):
             out = drv.step(fx["actions"][t])
             check_step(fx, t, out, drv.state(), where)
+
+
+class BotReplayDriver:
+    """Wraps a single-env driver for fixtures recorded with the reference's baselineTeam on the red side: the
+    env under test runs its OWN bots (tie-break = first best, as pinned while recording); the recorded red
+    actions are withheld (garbage is fed in their place) and must come back in `actions_used`."""
+
+    def __init__(self, inner, fx):
+        self.inner, self.fx, self.t = inner, fx, 0
+
+    def reset(self):
+        return self.inner.reset()
+
+    def step(self, a):
+        fed = np.where(self.fx["bot_kind"] >= 2, 9, np.asarray(a)).astype(np.uint8)
+        out = self.inner.step(fed)
+        bots = self.fx["bot_kind"] >= 2             # (non-bot columns report the EFFECTIVE action: illegal -> Stop)
+        np.testing.assert_array_equal(np.asarray(out["actions_used"])[bots], np.asarray(a)[bots],
+                                      err_msg=f"step {self.t}: bot actions")
+        self.t += 1
+        return out
+
+    def state(self):
+        return self.inner.state()

@@ -85,3 +85,12 @@ def test_emulated_packed_host_record_matches_separate_outputs():
         np.testing.assert_array_equal(p[:, 36:40], o["legal"])
         np.testing.assert_array_equal(p[:, 40], o["done"])
         assert not p[:, 41:].any()
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.traj_names() if n.startswith("bots_")])
+def test_emulated_baseline_team_matches_reference(name):
+    """On-device baselineTeam (Offensive + Defensive reflex agents): the kernel logic picks exactly the actions
+    the reference's bots picked, and the whole trajectory follows."""
+    fx = helpers.load_traj(name)
+    env = EmuEnv(fx["layout"], 2, length=int(fx["length"]), E=2, KB=1, bot_kind=list(fx["bot_kind"]), bot_first_best=True)
+    helpers.replay(fx, helpers.BotReplayDriver(SingleEnvDriver(env, n=1), fx), where=name)

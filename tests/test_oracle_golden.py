@@ -93,3 +93,30 @@ def test_adv_norm_matches_reference():
     z = np.load(helpers.GOLDEN + "/gae.npz")
     out = oracle.adv_norm(z["norm_adv"], z["norm_inds"], int(z["norm_mb"]))
     np.testing.assert_allclose(out, z["norm_out"], rtol=1e-5, atol=1e-6)
+
+
+class OracleBotDriver(OracleDriver):
+    """Replays a fixture recorded with the reference's baselineTeam on the red side: the oracle's own bots
+    must pick the recorded actions (ties -> first best, as pinned while recording) from the recorded best sets."""
+
+    def __init__(self, fx):
+        super().__init__(fx)
+        self.fx, self.t = fx, 0
+        self.env.set_bots(fx["bot_kind"])
+
+    def step(self, a):
+        kind = self.fx["bot_kind"]
+        fed = np.where(kind >= 2, 7, np.asarray(a, np.int32))          # bot columns get garbage: must be ignored
+        o = self.env.step_bots(fed)
+        np.testing.assert_array_equal(o["actions_used"][0], a, err_msg=f"step {self.t}: bot actions")
+        np.testing.assert_array_equal(o["best_masks"][0], self.fx["bot_best"][self.t], err_msg=f"step {self.t}: best sets")
+        self.t += 1
+        return {k: (v[0] if v is not None else None) for k, v in o.items()}
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.traj_names() if n.startswith("bots_")])
+def test_baseline_team_bots_match_reference(name):
+    """agents/baselineTeam.py (Offensive + Defensive reflex agents on the red side, gymPacMan.py:157)."""
+    fx = helpers.load_traj(name)
+    assert list(fx["bot_kind"]) == [2, 0, 3, 0]
+    helpers.replay(fx, OracleBotDriver(fx), where=name)
