@@ -38,6 +38,9 @@ file_path = os.path.dirname(os.path.abspath(__file__)) + "/"
 ACTION_NAMES = ["North", "East", "South", "West", "Stop"]
 # Actions.getPossibleActions iterates N, S, E, W, Stop (game.py:295-299,344-348)
 LEGAL_LIST_ORDER = [0, 2, 1, 3, 4]
+# opponents that run inside the step kernel -> pm_env_desc.bot_kind of the red agents (0, 2), in the order
+# createTeam returns them (randomTeam.py: two random agents; baselineTeam.py:34-51: Offensive, Defensive)
+ON_DEVICE_TEAMS = {"randomTeam": (1, 1), "baselineTeam": (2, 3)}
 
 
 def legal_mask_to_list(mask: int) -> List[int]:
@@ -223,7 +226,7 @@ class gymPacMan_parallel_env:
                  reward_forLegalAction=True, defenceReward=True, random_layout=False, enemieName="randomTeam",
                  self_play=False, *, num_envs: int = 1, device=None, layouts: Optional[Sequence] = None,
                  shaping_scale: float = 0.1, opponent_seed: int = 0, auto_reset: bool = False,
-                 env_index_base: int = 0):
+                 env_index_base: int = 0, opponent_tiebreak: str = "random"):
         if display:
             raise NotImplementedError("display=True (tkinter viewer) is outside the batched GPU path")
         if not torch.cuda.is_available():
@@ -252,10 +255,13 @@ class gymPacMan_parallel_env:
         # agent keys: ints in self-play (gymPacMan.py:33-40).  Without self-play the red side is driven by an
         # on-device opponent and still addressed by its index.
         self.agents = [0, 1, 2, 3]
-        if not self_play and enemieName not in ("randomTeam",):
+        if not self_play and enemieName not in ON_DEVICE_TEAMS:
             raise NotImplementedError(
-                f"enemieName={enemieName!r}: only the on-device randomTeam opponent exists; CPU bot teams "
-                "(agents/*.py) are outside the GPU path (SURVEY §8 row f1)")
+                f"enemieName={enemieName!r}: the on-device opponents are {sorted(ON_DEVICE_TEAMS)}; the other CPU "
+                "bot teams (agents/*.py search agents) are outside the GPU path (SURVEY §8 row f1)")
+        if opponent_tiebreak not in ("random", "first"):
+            raise ValueError("opponent_tiebreak must be 'random' (random.choice, baselineTeam.py:92) or 'first'")
+        self._opponent_tiebreak = opponent_tiebreak
         self._opponent_seed = int(opponent_seed)
         # batched extensions: restart finished envs inside the step launch; global index of env 0 when
         # this batch is one shard of a larger one (keys the on-device opponent's random draws)
@@ -290,9 +296,10 @@ class gymPacMan_parallel_env:
         self._state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self._desc = _lib.PmEnvDesc(W, H, len(lays), int(has_caps), N, self._geom.data_ptr(), self._table.data_ptr(),
                                     None, self._state.data_ptr(), int(self.length), int(bool(self.reward_forLegalAction)),
-                                    int(bool(self.defenceReward)), 0 if self.self_play else 0b0101,
+                                    int(bool(self.defenceReward)), 0,
                                     self.shaping_scale, int(self._opponent_seed), int(self.auto_reset), 0,
                                     self.env_index_base, 0, 0)
+        self._set_opponent(self.enemieName)
         self.obs_shape = (8, H, W)
         self._obs = torch.empty((4, N, 8, H, W), dtype=torch.float32, device=dev)
         self._reward = torch.zeros((2, N), dtype=torch.float64, device=dev)
@@ -301,9 +308,30 @@ class gymPacMan_parallel_env:
         self._score_change = torch.zeros(N, dtype=torch.int32, device=dev)
         self._shaping = torch.zeros((4, N), dtype=torch.float64, device=dev)
         self._shaped = torch.zeros((4, N), dtype=torch.float32, device=dev)
+        self._actions_used = torch.zeros((N, 4), dtype=torch.uint8, device=dev)
         self._step_out = _lib.PmStepOut(self._obs.data_ptr(), self._obs[0].numel(), self._reward.data_ptr(),
                                         self._done.data_ptr(), self._legal.data_ptr(), self._score_change.data_ptr(),
-                                        self._shaping.data_ptr(), self._shaped.data_ptr())
+                                        self._shaping.data_ptr(), self._shaped.data_ptr(), None,
+                                        self._actions_used.data_ptr())
+
+    def _set_opponent(self, name):
+        """Red side = the named on-device team (loadAgents(True, ...) puts bots on agents 0 and 2,
+        gymPacMan.py:33-40).  baselineTeam needs the maze-distance tables: every reset of the reference
+        rebuilds them per bot (captureAgents.py:91-109); here one BFS launch per layout set."""
+        d = self._desc
+        if self.self_play:
+            d.bot_kind = 0
+            return
+        k0, k2 = ON_DEVICE_TEAMS[name]
+        d.bot_kind = k0 | (k2 << 8)
+        d.bot_first_best = int(self._opponent_tiebreak == "first")
+        if max(k0, k2) >= 2 and getattr(self, "_dist_for", None) is not self._layouts:
+            from .distanceCalculator import compute_distances
+            self._dist_tables = compute_distances(self._layouts, device=self.device)
+            self._dist_for = self._layouts
+        if max(k0, k2) >= 2:
+            t = self._dist_tables
+            d.dist, d.node_of_cell, d.dist_nmax = t.dist.data_ptr(), t.node_of_cell.data_ptr(), int(t.dist.shape[1])
 
     def _layout_of(self, n):
         return self._layouts[n % len(self._layouts)]
@@ -342,7 +370,8 @@ class gymPacMan_parallel_env:
         self._version += 1
         self.steps += 1
         return dict(obs=self._obs, reward=self._reward, done=self._done, legal=self._legal,
-                    score_change=self._score_change, shaping=self._shaping, shaped_reward=self._shaped)
+                    score_change=self._score_change, shaping=self._shaping, shaped_reward=self._shaped,
+                    actions_used=self._actions_used)
 
     def step_host(self, actions_host: torch.Tensor, want_obs: bool = False):
         """One step with HOST buffers through the C ABI's ``pm_step_host``: ``actions_host``
@@ -510,9 +539,10 @@ class gymPacMan_parallel_env:
         if new_lays is not None:
             self._install_layouts(new_lays)
         if enemieName != "None":
-            if not self.self_play and enemieName != "randomTeam":
+            if not self.self_play and enemieName not in ON_DEVICE_TEAMS:
                 raise NotImplementedError(f"enemieName={enemieName!r} is outside the GPU path")
             self.enemieName = enemieName
+            self._set_opponent(enemieName)
         self.reset_batched(mask)
         return self._obs_dict(), {"legal_actions": self._legal_dict()}
 

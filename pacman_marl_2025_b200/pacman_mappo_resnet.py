@@ -57,7 +57,10 @@ SHAPING_SCALE = 0.1
 EVAL_FREQ = 50
 EVAL_EPISODES = 10
 EMA_DECAY = 0.995
-ON_DEVICE_TEAMS = ["randomTeam"]
+# the reference's curriculum pools (`:40-42`) restricted to the opponents that exist on the device
+EASY_TEAMS = ["randomTeam"]
+MEDIUM_TEAMS: List[str] = []          # MCTSTeam / heuristicTeam: CPU search bots, outside the GPU path
+HARD_TEAMS = ["baselineTeam"]         # (AstarTeam / approxQTeam: likewise CPU-only)
 
 # canonical (blue-perspective) view of a red agent: mirror x, swap the capsule and food plane pairs
 _CANON_PLANES = [0, 1, 3, 2, 4, 5, 7, 6]
@@ -215,7 +218,8 @@ class TrainConfig:
     seed: int = 0
     amp_bf16: bool = False            # networks in bf16 autocast (fp32 master weights); default = reference fp32
     fast_math: bool = True            # cuDNN autotune + TF32 tensor-core matmuls for the fp32 networks
-    selfplay_after: int = 800         # update index after which self-play opponents enter the mix (`:396-438`)
+    easy_until: int = 200             # updates <= this: EASY_TEAMS only (`:396-402`)
+    selfplay_after: int = 800         # update index after which self-play opponents enter the mix (`:404-438`)
     log_every: int = 1
     checkpoint_every: int = 250
     checkpoint_dir: str = "."
@@ -285,14 +289,17 @@ class MAPPOTrainer:
 
     def schedule(self, update):
         """LR / entropy / clip annealing and the opponent curriculum (`:385-447`), restricted to opponents that
-        exist on the device: randomTeam, the current policy, a pooled EMA snapshot."""
+        exist on the device: randomTeam, baselineTeam, the current policy, a pooled EMA snapshot."""
         cfg = self.cfg
         progress = update / max(cfg.total_updates, 1)
         lr = LR_START - (LR_START - LR_END) * progress
         ent_coef = ENT_COEF_START - (ENT_COEF_START - ENT_COEF_END) * progress
         clip_eps = 0.1 if update > cfg.selfplay_after else CLIP_EPS
-        if update <= cfg.selfplay_after:
-            mode, play_as_red = "randomTeam", False
+        pick = lambda pool: str(pool[int(self.rng.integers(len(pool)))])
+        if update <= cfg.easy_until:
+            mode, play_as_red = pick(EASY_TEAMS), False
+        elif update <= cfg.selfplay_after:
+            mode, play_as_red = pick(EASY_TEAMS + MEDIUM_TEAMS + HARD_TEAMS * 5), False
         else:
             r = self.rng.random()
             if r < 0.40:
@@ -300,7 +307,7 @@ class MAPPOTrainer:
             elif r < 0.60:
                 mode, play_as_red = "Self(Old)", bool(self.rng.random() > 0.5)
             else:
-                mode, play_as_red = "randomTeam", False
+                mode, play_as_red = pick(HARD_TEAMS * 5 + MEDIUM_TEAMS + EASY_TEAMS), False
         return dict(lr=lr, ent_coef=ent_coef, clip_eps=clip_eps, mode=mode, play_as_red=play_as_red)
 
     # ------------------------------------------------------------------ rollout
@@ -309,8 +316,10 @@ class MAPPOTrainer:
         """T steps of N envs (`:457-538`).  Returns (last_value [N], stats tensor)."""
         cfg, ro = self.cfg, self.rollout
         T, N = cfg.num_steps, cfg.num_envs
-        selfplay = mode != "randomTeam"
+        selfplay = mode.startswith("Self")
         env = self.env_selfplay if selfplay else self.env_bot
+        if not selfplay and env.enemieName != mode:
+            env.reset(enemieName=mode)                                # `:399, 406, 436`: env.reset(enemieName=opp_name)
         if mode == "Self(Curr)":
             self.opponent.load_state_dict(self.agent.state_dict())
         elif mode == "Self(Old)":
@@ -449,12 +458,13 @@ class MAPPOTrainer:
         return self.log
 
     @torch.no_grad()
-    def evaluate_vs_bots(self, agent: Optional[MAPPOAgent] = None, num_envs: int = 256):
-        """`:293-337` against the on-device randomTeam: deterministic blue learners, one episode per env.
+    def evaluate_vs_bots(self, agent: Optional[MAPPOAgent] = None, num_envs: int = 256, team: str = "baselineTeam"):
+        """`:293-337` against an on-device bot team: deterministic blue learners, one episode per env.
         Returns (mean return, std, win rate)."""
         agent = (agent or self.ema_agent).eval()
         env = gymPacMan_parallel_env(layouts=[self.env_bot.layout], length=self.cfg.length, self_play=False,
-                                     num_envs=num_envs, device=self.device, opponent_seed=self.cfg.seed + 7919)
+                                     enemieName=team, num_envs=num_envs, device=self.device,
+                                     opponent_seed=self.cfg.seed + 7919)
         obs4, _ = env.reset_batched()
         ret = torch.zeros(num_envs, dtype=torch.float64, device=self.device)
         alive = torch.ones(num_envs, dtype=torch.bool, device=self.device)

@@ -11,6 +11,7 @@ import torch
 
 import helpers
 from emu_driver import SingleEnvDriver
+from oracle import oracle
 from parity_bodies import (biased_actions, body_int64_out_of_range, body_large_batch, body_observe_current_state,
                            body_per_env_mazes, lay_rows, LAYDIR)
 
@@ -20,13 +21,17 @@ class CudaEnv:
     """Thin numpy-returning adapter over the product class (same surface as tests/emu_driver.EmuEnv)."""
 
     def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True,
-                 random_agent_mask=0, random_seed=0, **kw):
+                 random_agent_mask=0, random_seed=0, bot_kind=None, bot_first_best=True, **kw):
         from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
         per_env = not isinstance(layouts[0], str)
         lays = layouts if per_env else [layouts]
         assert random_agent_mask in (0, 0b0101)
+        team, self_play = "randomTeam", random_agent_mask == 0
+        if bot_kind is not None and list(bot_kind) == [2, 0, 3, 0]:
+            team, self_play = "baselineTeam", False
+            kw["opponent_tiebreak"] = "first" if bot_first_best else "random"
         self.env = gymPacMan_parallel_env(length=length, reward_forLegalAction=reward_forLegalAction,
-                                          defenceReward=defenceReward, self_play=random_agent_mask == 0,
+                                          defenceReward=defenceReward, self_play=self_play, enemieName=team,
                                           num_envs=n_envs, layouts=lays, opponent_seed=random_seed, **kw)
         self.N = n_envs
 
@@ -40,7 +45,8 @@ class CudaEnv:
         o = self.env.step_batched(a)
         return dict(obs=o["obs"].cpu().numpy(), reward=o["reward"].cpu().numpy(), done=o["done"].cpu().numpy(),
                     legal=o["legal"].cpu().numpy(), score_change=o["score_change"].cpu().numpy(),
-                    shaping=o["shaping"].cpu().numpy(), shaped=o["shaped_reward"].cpu().numpy())
+                    shaping=o["shaping"].cpu().numpy(), shaped=o["shaped_reward"].cpu().numpy(),
+                    actions_used=o["actions_used"].cpu().numpy())
 
     def set_range(self, begin=0, count=0):
         self.env._desc.env_begin, self.env._desc.env_count = int(begin), int(count)
@@ -308,12 +314,12 @@ def test_mappo_trainer_rollout_gae_and_update():
     and PPO updates move the weights with finite losses."""
     from oracle import oracle
     from pacman_marl_2025_b200 import pacman_mappo_resnet as M
-    cfg = M.TrainConfig(num_envs=96, num_steps=24, num_minibatches=4, update_epochs=2, total_updates=4, length=12,
-                        seed=3, selfplay_after=1, checkpoint_every=0)
+    cfg = M.TrainConfig(num_envs=96, num_steps=24, num_minibatches=4, update_epochs=2, total_updates=6, length=12,
+                        seed=3, easy_until=0, selfplay_after=2, checkpoint_every=0)
     tr = M.MAPPOTrainer(cfg, device="cuda:0")
     before = torch.cat([p.detach().reshape(-1).clone() for p in tr.agent.parameters()])
     modes = set()
-    for upd in range(4):
+    for upd in range(6):
         rec = tr.train_one(upd)
         modes.add(rec["mode"])
         assert all(np.isfinite(rec[k]) for k in ("pg_loss", "v_loss", "entropy", "clip_frac", "sps", "reward"))
@@ -335,9 +341,10 @@ def test_mappo_trainer_rollout_gae_and_update():
         np.testing.assert_array_equal(ret.cpu().numpy().view(np.uint32), oret.view(np.uint32))
     after = torch.cat([p.detach().reshape(-1) for p in tr.agent.parameters()])
     assert not torch.equal(before, after) and bool(torch.isfinite(after).all())
-    assert modes & {"Self(Curr)", "Self(Old)"} or "randomTeam" in modes
-    mean_ret, std_ret, win = tr.evaluate_vs_bots(num_envs=64)
-    assert np.isfinite(mean_ret) and 0.0 <= win <= 1.0
+    assert "randomTeam" in modes and "baselineTeam" in modes, modes       # updates 0 / 1-2 of the curriculum
+    for team in ("randomTeam", "baselineTeam"):
+        mean_ret, std_ret, win = tr.evaluate_vs_bots(num_envs=64, team=team)
+        assert np.isfinite(mean_ret) and 0.0 <= win <= 1.0
 
 
 def test_mappo_rollout_rewards_match_reference_formula():
@@ -368,3 +375,67 @@ def test_mappo_rollout_rewards_match_reference_formula():
         want = (2.0 * r["reward"][:, 1][:, None] + 0.1 * r["shaping"][:, [1, 3]]).astype(np.float32)
         np.testing.assert_array_equal(ro.reward[t].cpu().numpy().view(np.uint32), want.view(np.uint32), err_msg=f"t={t}")
         np.testing.assert_array_equal(ro.done[t, :, 0].cpu().numpy(), r["done"].astype(np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# on-device baselineTeam
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in helpers.traj_names() if n.startswith("bots_")])
+def test_cuda_baseline_team_matches_reference_fixture(name):
+    """Red side = baselineTeam inside the step kernel (distance tables from the BFS kernel): it plays exactly
+    what the reference's Offensive/Defensive reflex agents played, and every output of every step follows."""
+    fx = helpers.load_traj(name)
+    env = CudaEnv(fx["layout"], 3, length=int(fx["length"]), bot_kind=list(fx["bot_kind"]), bot_first_best=True)
+    helpers.replay(fx, helpers.BotReplayDriver(SingleEnvDriver(env, n=1), fx), where=name)
+
+
+@pytest.mark.parametrize("layname,N,T", [("tinyCapture", 1024, 120), ("bloxCapture", 256, 80)])
+def test_cuda_baseline_team_large_batch_vs_oracle(layname, N, T):
+    rows = lay_rows(layname)
+    env = CudaEnv(rows, N, length=60, auto_reset=True, bot_kind=[2, 0, 3, 0], bot_first_best=True)
+    ref = oracle.OracleBatch(rows, N, length=60)
+    ref.set_bots([2, 0, 3, 0])
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(17)
+    for t in range(T):
+        a = biased_actions(rng, N, 0.5, t)
+        o = env.step(a)
+        r = ref.step_bots(a, with_obs=(t % 10 == 0), auto_reset=True, nthreads=0)
+        np.testing.assert_array_equal(o["actions_used"][:, [0, 2]], r["actions_used"][:, [0, 2]], err_msg=f"t={t} bot actions")
+        np.testing.assert_array_equal(o["reward"].view(np.uint64), r["reward"].T.copy().view(np.uint64), err_msg=f"t={t}")
+        np.testing.assert_array_equal(o["done"], r["done"])
+        np.testing.assert_array_equal(o["score_change"], r["score_change"])
+        if t % 10 == 0:
+            keep = ~r["done"].astype(bool)               # finished envs already show the next episode on the GPU side
+            np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4)[keep], r["obs"][keep], err_msg=f"t={t} obs")
+
+
+def test_cuda_baseline_team_random_tiebreak_stays_in_best_set():
+    """opponent_tiebreak='random' (random.choice over the best actions, baselineTeam.py:92): agent 0's choice
+    is always inside the oracle's best set for the same pre-step state, and ties really get broken both ways."""
+    rows = lay_rows("smallCapture")
+    N = 512
+    env = CudaEnv(rows, N, length=80, auto_reset=True, bot_kind=[2, 0, 3, 0], bot_first_best=False, random_seed=5)
+    mirror = oracle.OracleBatch(rows, N, length=80)      # follows the GPU trajectory through explicit actions
+    probe = oracle.OracleBatch(rows, N, length=80)       # asked for agent 0's best set on a copy of that state
+    probe.set_bots([2, 0, 0, 0])
+    env.reset(); mirror.reset(); probe.reset()
+    rng = np.random.default_rng(23)
+    seen_multi, not_first = 0, 0
+    for t in range(60):
+        a = biased_actions(rng, N, 0.5, t)
+        probe.buf[:] = mirror.buf
+        for n in range(N):
+            oracle.lib().pmo_set_distances(probe._env(n), oracle._p(next(iter(probe._tables.values()))[0]))
+        best = probe.step_bots(a, with_obs=False)["best_masks"][:, 0]
+        o = env.step(a)
+        used = o["actions_used"]
+        chosen = used[:, 0].astype(int)
+        assert (((best >> chosen) & 1) == 1).all(), f"t={t}: a chosen action is outside the best set"
+        multi = np.array([bin(int(b)).count("1") > 1 for b in best])
+        seen_multi += int(multi.sum())
+        order = [0, 2, 1, 3, 4]
+        first_best = np.array([next(u for u in order if (int(b) >> u) & 1) for b in best])
+        not_first += int((multi & (chosen != first_best)).sum())
+        mirror.step(used.astype(np.int32), with_obs=False, auto_reset=True, nthreads=0)
+    assert seen_multi > 50 and not_first > 10, (seen_multi, not_first)
