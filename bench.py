@@ -160,6 +160,61 @@ def measure_layout(torch, env_cls, layout, n_envs, steps, warmup, length, device
     return env, acts, one
 
 
+def other_kernels(torch, device, N, peak):
+    """BFS distance tables, GAE / advantage normalisation and the bot variant of the step kernel (informational)."""
+    from pacman_marl_2025_b200 import mazeGenerator
+    from pacman_marl_2025_b200.distanceCalculator import compute_distances
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    from pacman_marl_2025_b200.layout import Layout, getLayout
+    from pacman_marl_2025_b200.mappo_ops import compute_gae, normalize_advantages
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(); ev0.record()
+        for _ in range(reps):
+            fn()
+        ev1.record(); torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / reps
+    # (3) all-pairs maze distances: one shipped board, and 256 distinct mazeGenerator boards in one launch (config 4)
+    blox = [getLayout(layout_path("bloxCapture"))]
+    ms = timed(lambda: compute_distances(blox, device=device), 20)
+    out["bfs_bloxCapture"] = {"ms": ms, "n_open": 190, "reference_python_ms": 100.0}
+    mazes = [Layout(mazeGenerator.generateMaze(1000 + s).split("\n")) for s in range(256)]
+    tabs = compute_distances(mazes, device=device)
+    ms = timed(lambda: compute_distances(mazes, device=device), 5)
+    out["bfs_256_random_mazes"] = {"ms": ms, "ms_per_maze": ms / 256, "table_bytes": int(tabs.dist.numel() * 2),
+                                   "reference_python_ms_per_maze": "190-335"}
+    # (4) GAE over a [T, M] rollout: 20 algorithmic bytes per element (read r, V, done; write A, ret)
+    T, M = 256, 2 * N
+    r, v = torch.randn(T, M, device=device), torch.randn(T, M, device=device)
+    d = (torch.rand(T, M, device=device) < 0.01).float()
+    lv = torch.randn(M, device=device)
+    ms = timed(lambda: compute_gae(r, v, d, lv), 20)
+    gbs = 20.0 * T * M / (ms * 1e-3) / 1e9
+    out["gae"] = {"ms": ms, "T": T, "columns": M, "achieved_GBps": gbs, "roofline_frac": gbs / peak}
+    adv = torch.randn(T * M, device=device)
+    idx = torch.randperm(T * M, device=device)
+    ms = timed(lambda: normalize_advantages(adv, idx, 8192), 10)
+    out["adv_norm"] = {"ms": ms, "samples": T * M, "minibatch": 8192}
+    del r, v, d, adv, idx
+    # (1b) step kernel with the on-device baselineTeam playing red (look-ahead over legal actions + maze distances)
+    env = gymPacMan_parallel_env(layout_file=layout_path("tinyCapture"), self_play=False, enemieName="baselineTeam",
+                                 length=300, num_envs=N, device=device, auto_reset=True)
+    acts = torch.randint(0, 5, (4, N, 4), dtype=torch.uint8, device=device)
+    env.reset_batched()
+    k = [0]
+
+    def one():
+        env.step_batched(acts[k[0] % 4]); k[0] += 1
+    ms = timed(one, 100)
+    out["step_vs_baselineTeam_tinyCapture"] = {"ms": ms, "agent_steps_per_s": 4.0 * N / (ms * 1e-3),
+                                               "roofline_frac": 4529 * 4.0 * N / (ms * 1e-3) / 1e9 / peak}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -338,6 +393,8 @@ def main():
                          "roofline_frac": ab * 4.0 * N / (km * 1e-3) / 1e9 / peak}
             del e2, a2, one2
             torch.cuda.empty_cache()
+        # the other kernels of the path, each timed alone (CUDA events, this stream)
+        also["kernels"] = other_kernels(torch, device, N, peak)
         line["also"] = also
 
     if rank == 0:

@@ -129,11 +129,6 @@ __global__ void pm_set_state_kernel(const PmParams P, const int32_t *agents, con
 // ---------------------------------------------------------------------------
 // host glue
 // ---------------------------------------------------------------------------
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-
 static int fill_params(const pm_env_desc *d, PmParams &P) { return pm_fill_params(d, P, PM_E); }
 
 template <int MODE, int BOTS>

@@ -790,6 +790,26 @@ PM_HD uint32_t pm_cat_word(const PmParams &P, const uint32_t *st, const PmSmem &
     return w;
 }
 
+#ifndef PM_ST256
+#define PM_ST256 0
+#endif
+#ifndef PM_ALU_EXPAND
+#define PM_ALU_EXPAND 0
+#endif
+// nibble -> four floats (bit i set -> 1.0f): 16-entry shared-memory table, or pure ALU (PM_ALU_EXPAND)
+PM_HD pm_f4 pm_expand4(const pm_f4 *lut, uint32_t nib) {
+#if PM_ALU_EXPAND && defined(__CUDA_ARCH__)
+    pm_f4 v;
+    v.x = __uint_as_float((nib & 1u) * 0x3f800000u);
+    v.y = __uint_as_float((nib & 2u) * 0x1fc00000u);
+    v.z = __uint_as_float((nib & 4u) * 0x0fe00000u);
+    v.w = __uint_as_float((nib & 8u) * 0x07f00000u);
+    return v;
+#else
+    return lut[nib];
+#endif
+}
+
 // One warp turns whole observations into fp32 planes.  Per group of 32 bit-string
 // words: lane L builds word 32g+L, then 8 store rounds follow in which lane L
 // writes float4 number 256g + 32r + L of the observation; its four floats are
@@ -801,6 +821,7 @@ template <int MODE>
 PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps, int lane, int64_t n0) {
     const int NCAT = P.NCAT, E = P.E;
     const int nf4 = 2 * P.HW;                          // float4s per observation (8*HW/4)
+    (void)nf4;
     const pm_f4 *lut = reinterpret_cast<const pm_f4 *>(st + M.lut);
     const int ngroups = (NCAT + 31) >> 5;
     for (int u = warp; u < 4 * E; u += nwarps) {
@@ -809,7 +830,30 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
         if (!pm_unit_load<MODE>(P, sm, M, k, el, U)) continue;
         float *dstf = P.obs + (size_t)k * P.obs_agent_stride + (size_t)(n0 + el) * 8 * P.HW;
         pm_f4 *dst = reinterpret_cast<pm_f4 *>(dstf);
+        (void)dst;
 #if defined(__CUDA_ARCH__)
+#if PM_ST256
+        // 256-bit stores (STG.E.ENL2.256, sm_100+): lane L writes float8 number 128g + 32r + L = byte (L & 3) of word
+        // 32g + 8r + (L >> 2); a warp store covers 1024 contiguous bytes, 4 rounds per 32 words.
+        const int sh8 = (lane & 3) * 8, src8 = lane >> 2;
+        const int nf8 = P.HW;
+        for (int g = 0; g < ngroups; ++g) {
+            const int j = 32 * g + lane;
+            const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
+            const int fbase = 128 * g + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t w = __shfl_sync(0xffffffffu, word, 8 * r + src8) >> sh8;
+                const int f = fbase + 32 * r;
+                if (f < nf8) {
+                    const pm_f4 lo = pm_expand4(lut, w & 15u), hi = pm_expand4(lut, (w >> 4) & 15u);
+                    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dstf + 8 * (size_t)f), "f"(lo.x),
+                                 "f"(lo.y), "f"(lo.z), "f"(lo.w), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w)
+                                 : "memory");
+                }
+            }
+        }
+#else
         const int sh = (lane & 7) * 4, src = lane >> 3;
         for (int g = 0; g < ngroups; ++g) {
             const int j = 32 * g + lane;
@@ -819,9 +863,10 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
             for (int r = 0; r < 8; ++r) {
                 const uint32_t w = __shfl_sync(0xffffffffu, word, 4 * r + src);
                 const int f = fbase + 32 * r;
-                if (f < nf4) dst[f] = lut[(w >> sh) & 15u];
+                if (f < nf4) dst[f] = pm_expand4(lut, (w >> sh) & 15u);
             }
         }
+#endif
         if (U.patch != 0xffffffffu) {
             __syncwarp();
             if (lane == 0) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);

@@ -230,3 +230,51 @@ def body_shard_invariant_random_agents(make_env, N=64):
     for t in range(20):
         differs |= not np.array_equal(other.step(a)["obs"], fresh.step(a)["obs"])
     assert differs
+
+
+def big_board(W=32, H=32, seed=0):
+    """A crafted W x H capture board (up to PM_MAX_CELLS = 1024 cells): closed border, random inner walls kept
+    sparse enough to stay connected around the agents, mirrored food, two capsules, four starts."""
+    rng = np.random.default_rng(seed)
+    g = [[" "] * W for _ in range(H)]
+    for x in range(W):
+        g[0][x] = g[H - 1][x] = "%"
+    for y in range(H):
+        g[y][0] = g[y][W - 1] = "%"
+    for y in range(2, H - 2, 2):
+        for x in range(2, W // 2, 1):
+            if rng.random() < 0.45:
+                g[y][x] = "%"
+                g[H - 1 - y][W - 1 - x] = "%"
+    for y in range(1, H - 1):
+        for x in range(1, W // 2):
+            if g[y][x] == " " and rng.random() < 0.18:
+                g[y][x] = "."
+                if g[H - 1 - y][W - 1 - x] == " ":
+                    g[H - 1 - y][W - 1 - x] = "."
+    g[1][1], g[2][1] = "1", "3"
+    g[H - 2][W - 2], g[H - 3][W - 2] = "2", "4"
+    g[1][W // 2 - 2], g[H - 2][W // 2 + 1] = "o", "o"
+    return ["".join(r) for r in g]
+
+
+def body_max_size_board(make_env, N=40, T=150):
+    """32 x 32 = PM_MAX_CELLS cells: the largest board the ABI accepts (and 33 x 32 is refused)."""
+    rows = big_board()
+    env = make_env(rows, N, length=70, auto_reset=True)
+    ref = oracle.OracleBatch(rows, N, length=70)
+    obs, legal = env.reset()
+    robs, rlegal = ref.reset()
+    np.testing.assert_array_equal(legal, rlegal)
+    np.testing.assert_array_equal(obs.transpose(1, 0, 2, 3, 4), robs)
+    rng = np.random.default_rng(6)
+    for t in range(T):
+        a = biased_actions(rng, N, 0.7, t)
+        o = env.step(a)
+        r = ref.step(a, with_obs=True, nthreads=0, auto_reset=True)
+        keep = ~r["done"].astype(bool)
+        np.testing.assert_array_equal(o["reward"].view(np.uint64), r["reward"].T.copy().view(np.uint64), err_msg=f"t={t}")
+        np.testing.assert_array_equal(o["done"], r["done"])
+        np.testing.assert_array_equal(o["score_change"], r["score_change"])
+        np.testing.assert_array_equal(o["legal"][keep], r["legal"][keep])
+        np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4)[keep], r["obs"][keep], err_msg=f"t={t} obs")

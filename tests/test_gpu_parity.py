@@ -89,6 +89,13 @@ def test_env_ranges_and_shard_invariant_random_agents():
     body_shard_invariant_random_agents(CudaEnv, N=256)
 
 
+def test_max_size_board_and_oversize_refusal():
+    from parity_bodies import big_board, body_max_size_board
+    body_max_size_board(CudaEnv, N=200, T=160)
+    with pytest.raises(RuntimeError, match="PM_ETOOBIG"):
+        CudaEnv(big_board(33, 32), 4)
+
+
 def test_int64_actions_and_out_of_range():
     body_int64_out_of_range(CudaEnv)
 

@@ -94,3 +94,8 @@ def test_emulated_baseline_team_matches_reference(name):
     fx = helpers.load_traj(name)
     env = EmuEnv(fx["layout"], 2, length=int(fx["length"]), E=2, KB=1, bot_kind=list(fx["bot_kind"]), bot_first_best=True)
     helpers.replay(fx, helpers.BotReplayDriver(SingleEnvDriver(env, n=1), fx), where=name)
+
+
+def test_emulated_max_size_board():
+    from parity_bodies import body_max_size_board
+    body_max_size_board(lambda rows, n, **kw: EmuEnv(rows, n, E=8, KB=1, **kw), N=10, T=90)

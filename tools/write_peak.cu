@@ -33,6 +33,17 @@ __global__ void k_obs(float4 *dst, size_t nobs, int obs_f4) {
     }
 }
 
+// same, with 256-bit stores (st.global.v8.f32 -> STG.E.ENL2.256, sm_100+): a warp store covers 1024 B
+__global__ void k_obs256(float *dst, size_t nobs, int obs_f8) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t o = warp; o < nobs; o += nwarps) {
+        float *p = dst + o * obs_f8 * 8;
+        for (int f = lane; f < obs_f8; f += 32)
+            asm volatile("st.global.v8.f32 [%0], {%1,%1,%2,%2,%1,%1,%2,%2};" ::"l"(p + 8 * (size_t)f), "f"(1.f), "f"(0.f) : "memory");
+    }
+}
+
 // TMA bulk store: each warp owns NBUF smem buffers of obs_bytes; lanes fill the buffer (st.shared.v4),
 // lane 0 issues cp.async.bulk.global.shared::cta; buffers recycle with wait_group.read.
 template <int NBUF, int FILL>
@@ -116,6 +127,10 @@ int main() {
             double b = time_ms([&] { k_obs<1><<<sms * cps, 128>>>(dst, nobs, f4); });
             printf("warp-per-obs %5d B  ctas/SM=%2d          plain %7.1f GB/s   .cs %7.1f GB/s\n", obs_bytes, cps,
                    nobs * obs_bytes / a / 1e6, nobs * obs_bytes / b / 1e6);
+        }
+        for (int cps : {4, 8, 16}) {
+            double a = time_ms([&] { k_obs256<<<sms * cps, 128>>>((float *)dst, nobs, obs_bytes / 32); });
+            printf("warp-per-obs %5d B  ctas/SM=%2d  256-bit stores  %7.1f GB/s\n", obs_bytes, cps, nobs * obs_bytes / a / 1e6);
         }
         for (int cps : {2, 4, 8}) {
             const size_t smem = (size_t)4 * 2 * obs_bytes;
