@@ -212,6 +212,21 @@ def other_kernels(torch, device, N, peak):
     ms = timed(one, 100)
     out["step_vs_baselineTeam_tinyCapture"] = {"ms": ms, "agent_steps_per_s": 4.0 * N / (ms * 1e-3),
                                                "roofline_frac": 4529 * 4.0 * N / (ms * 1e-3) / 1e9 / peak}
+    # (1c) trainer mode: no fp32 observations, the step writes the learner views (2 actor + 1 critic, uint8) instead:
+    #      3*8*H*W = 3 360 B per env-step on tiny (+ ~200 B of state and small outputs) instead of 4*32*H*W = 17 920 B
+    for name, kw in (("trainer_views_vs_randomTeam_tinyCapture", dict(enemieName="randomTeam")),
+                     ("trainer_views_vs_baselineTeam_tinyCapture", dict(enemieName="baselineTeam"))):
+        env = gymPacMan_parallel_env(layout_file=layout_path("tinyCapture"), self_play=False, length=300, num_envs=N,
+                                     device=device, auto_reset=True, **kw)
+        env.reset_batched()
+        env.set_view_outputs(False, raw_obs=False)
+
+        def one_v():
+            env.step_batched(acts[k[0] % 4]); k[0] += 1
+        ms = timed(one_v, 100)
+        vbytes = (3 * 8 * 140 + 200) * N
+        out[name] = {"ms": ms, "agent_steps_per_s": 4.0 * N / (ms * 1e-3), "bytes_per_launch": vbytes,
+                     "achieved_GBps": vbytes / (ms * 1e-3) / 1e9}
     return out
 
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 4
+#define PM_ABI_VERSION 5
 
 /* argument errors */
 #define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
@@ -124,6 +124,18 @@ typedef struct pm_step_out {
     /* ---- ABI 4 ---- */
     uint8_t *actions_used;         /* [dev] [N][4] the action every agent actually played (illegal requests
                                      appear as Stop, bot agents as the bot's choice)                          */
+    /* ---- ABI 5: learner views, the trainer's network inputs written by the encoder itself ----
+     * canonicalize_obs + merge_obs_for_critic (pacman_mappo_resnet.py:215-229, 267-274, 462-469) fused into the
+     * step: for the learner team `view_red` (0: agents 1,3 as they are; 1: agents 0,2 mirrored in x with the
+     * plane pairs (2,3) and (6,7) swapped) the kernel writes uint8 planes (0/1 and 1+numCarrying, exact):
+     *   view_actor  [dev] learner l of env n at view_actor + l*view_actor_stride + n*8*H*W   (u8 [8][H][W])
+     *   view_critic [dev] [N][8][H][W]: first learner's view, plane 1 = max over both learners, plane 4 = 0
+     * Both NULL = off.  Pointers and stride must be 8-byte aligned; boards up to 32 columns.  With `obs` NULL
+     * the step writes 3*8*H*W bytes per env instead of 4*32*H*W.                                              */
+    uint8_t *view_actor;
+    int64_t view_actor_stride;
+    uint8_t *view_critic;
+    int32_t view_red, reserved2;
 } pm_step_out;
 
 /* What a CPU-side caller of gymPacMan.step reads back every step (gymPacMan.py:184-193), one record per env. */
@@ -154,6 +166,10 @@ int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, cons
 /* get_Observation(agentIndex) on the CURRENT state (gymPacMan.py:195-229) for
  * all four agents of every env. */
 int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream);
+
+/* The learner views (see pm_step_out) of the CURRENT state, e.g. right after pm_reset. */
+int pm_observe_views(const pm_env_desc *d, int view_red, uint8_t *view_actor, int64_t view_actor_stride,
+                     uint8_t *view_critic, pm_stream_t stream);
 
 /* pm_step with HOST buffers (the call a CPU-side consumer of the reference API makes):
  * copies actions_host ([N][4] uint8, ideally pinned) into actions_dev, runs pm_step

@@ -19,7 +19,7 @@ EXPORTS = [
     "pm_abi_version", "pm_geom_words", "pm_layout_words", "pm_state_bytes", "pm_pack_geom", "pm_pack_layout",
     "pm_reset", "pm_step", "pm_observe", "pm_step_host", "pm_get_state",
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
-    "pm_step_host_pipelined", "pm_step_host_mapped",
+    "pm_step_host_pipelined", "pm_step_host_mapped", "pm_observe_views",
 ]
 
 
@@ -49,6 +49,9 @@ class PmStepOut(C.Structure):
         ("legal", C.c_void_p), ("score_change", C.c_void_p), ("shaping", C.c_void_p), ("shaped_reward", C.c_void_p),
         ("packed", C.c_void_p),     # ABI 3
         ("actions_used", C.c_void_p),   # ABI 4
+        # ABI 5: learner views
+        ("view_actor", C.c_void_p), ("view_actor_stride", C.c_int64), ("view_critic", C.c_void_p),
+        ("view_red", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
@@ -96,6 +99,8 @@ def load():
     L.pm_step.argtypes = [C.POINTER(PmEnvDesc), vp, i32, C.POINTER(PmStepOut), vp]
     L.pm_observe.restype = i32
     L.pm_observe.argtypes = [C.POINTER(PmEnvDesc), vp, i64, vp]
+    L.pm_observe_views.restype = i32
+    L.pm_observe_views.argtypes = [C.POINTER(PmEnvDesc), i32, vp, i64, vp, vp]
     L.pm_step_host.restype = i32
     L.pm_step_host.argtypes = [C.POINTER(PmEnvDesc), vp, vp, C.POINTER(PmStepOut), C.POINTER(PmStepOut), vp]
     L.pm_pipe_create.restype = i32
@@ -116,7 +121,7 @@ def load():
     L.pm_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, i32, i64, vp]
     L.pm_adv_norm.restype = i32
     L.pm_adv_norm.argtypes = [vp, vp, vp, i64, i32, vp]
-    if L.pm_abi_version() != 4:
+    if L.pm_abi_version() != 5:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

@@ -34,10 +34,12 @@
 
 // BOTS = 1: the variant with the baselineTeam look-ahead compiled in (one more bitset slot of shared
 // memory as scratch); the plain variant pays nothing for it.
-template <int MODE, int BOTS>
-__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
+// VIEWS = 1: also writes the trainer's learner views (uint8, canonicalised + merged); two more bitset
+// slots hold the mirrored snapshots of red learners.
+template <int MODE, int BOTS, int VIEWS>
+__global__ void __launch_bounds__(PM_THREADS, (BOTS || VIEWS) ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
-    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, BOTS ? 5 : 4);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const int tid = threadIdx.x;
     const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * PM_E;
 
@@ -46,23 +48,23 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_ker
         float4 v = make_float4((tid & 1) ? 1.f : 0.f, (tid & 2) ? 1.f : 0.f, (tid & 4) ? 1.f : 0.f, (tid & 8) ? 1.f : 0.f);
         reinterpret_cast<float4 *>(sm + M.lut)[tid] = v;
     }
-    for (int i = tid; i < 4 * P.NCAT; i += PM_THREADS) sm[M.masks + i] = __ldg(P.geom + PM_G_HDR + i);
+    for (int i = tid; i < PM_G_NMASKS * P.NCAT; i += PM_THREADS) sm[M.masks + i] = __ldg(P.geom + PM_G_HDR + i);
     if (P.L == 1)
         for (int i = tid; i < P.LS; i += PM_THREADS) sm[M.lay + i] = __ldg(P.layouts + i);
     __syncthreads();
 
     // ---- phase A: rules, one thread per env ----
     if (tid < PM_E) {
-        if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS>(P, sm, sm, M, tid, n0);
-        else pm_phaseA_static<MODE>(P, sm, sm, M, tid, n0);
+        if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS, VIEWS>(P, sm, sm, M, tid, n0);
+        else pm_phaseA_static<MODE, VIEWS>(P, sm, sm, M, tid, n0);
     }
     __syncthreads();
     if (MODE == PM_MODE_STEP && P.packed)
         for (int t = tid; t < 3 * PM_E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
-    if (P.obs == nullptr) return;
-
     // ---- phase B: observations, one warp per (env, agent) ----
-    pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
+    if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
+    // ---- phase B': learner views, one warp per (env, view) ----
+    if (VIEWS && P.view_actor != nullptr) pm_phaseB_views<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0, 4 + BOTS);
 }
 
 // ---- state export / import (GameState accessors; tests, checkpoints) ---------
@@ -131,25 +133,32 @@ __global__ void pm_set_state_kernel(const PmParams P, const int32_t *agents, con
 // ---------------------------------------------------------------------------
 static int fill_params(const pm_env_desc *d, PmParams &P) { return pm_fill_params(d, P, PM_E); }
 
-template <int MODE, int BOTS>
+template <int MODE, int BOTS, int VIEWS>
 static int launch_env(const PmParams &P, cudaStream_t st) {
-    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, BOTS ? 5 : 4);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const size_t smem = (size_t)M.total * 4;
-    static size_t configured[64][3][2];                // per device, per kernel instance
+    static size_t configured[64][3][2][2];             // per device, per kernel instance
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
-    if (smem > configured[dev & 63][MODE][BOTS]) {
-        cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > configured[dev & 63][MODE][BOTS][VIEWS]) {
+        cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         // the kernel streams its output and keeps its working set in shared memory: prefer smem over L1
-        e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        configured[dev & 63][MODE][BOTS] = smem;
+        configured[dev & 63][MODE][BOTS][VIEWS] = smem;
     }
     const unsigned grid = (unsigned)((P.n_end - P.n_begin + PM_E - 1) / PM_E);
-    pm_env_kernel<MODE, BOTS><<<grid, PM_THREADS, smem, st>>>(P);
+    pm_env_kernel<MODE, BOTS, VIEWS><<<grid, PM_THREADS, smem, st>>>(P);
     return (int)cudaGetLastError();
+}
+
+static int set_views(PmParams &P, uint8_t *actor, int64_t stride, uint8_t *critic, int red) {
+    if (!actor && !critic) return 0;
+    if (!actor || !critic || P.W > 32 || ((size_t)actor & 7) || ((size_t)critic & 7) || (stride & 7)) return PM_EINVAL;
+    P.view_actor = actor; P.view_actor_stride = stride; P.view_critic = critic; P.view_red = red != 0;
+    return 0;
 }
 
 static bool has_lookahead_bots(const PmParams &P) {
@@ -163,7 +172,7 @@ extern "C" int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, i
     if (int rc = fill_params(d, P)) return rc;
     if (obs && (obs_agent_stride & 3)) return PM_EINVAL;
     P.mask = mask; P.obs = obs; P.obs_agent_stride = obs_agent_stride; P.legal = legal;
-    return launch_env<PM_MODE_RESET, 0>(P, (cudaStream_t)stream);
+    return launch_env<PM_MODE_RESET, 0, 0>(P, (cudaStream_t)stream);
 }
 
 extern "C" int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream) {
@@ -171,7 +180,16 @@ extern "C" int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_st
     if (int rc = fill_params(d, P)) return rc;
     if (!obs || (obs_agent_stride & 3)) return PM_EINVAL;
     P.obs = obs; P.obs_agent_stride = obs_agent_stride;
-    return launch_env<PM_MODE_OBSERVE, 0>(P, (cudaStream_t)stream);
+    return launch_env<PM_MODE_OBSERVE, 0, 0>(P, (cudaStream_t)stream);
+}
+
+extern "C" int pm_observe_views(const pm_env_desc *d, int view_red, uint8_t *view_actor, int64_t view_actor_stride,
+                                uint8_t *view_critic, pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    if (!view_actor || !view_critic) return PM_EINVAL;
+    if (int rc = set_views(P, view_actor, view_actor_stride, view_critic, view_red)) return rc;
+    return launch_env<PM_MODE_OBSERVE, 0, 1>(P, (cudaStream_t)stream);
 }
 
 extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
@@ -184,8 +202,10 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
     P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
-    return has_lookahead_bots(P) ? launch_env<PM_MODE_STEP, 1>(P, (cudaStream_t)stream)
-                                 : launch_env<PM_MODE_STEP, 0>(P, (cudaStream_t)stream);
+    if (int rc = set_views(P, out->view_actor, out->view_actor_stride, out->view_critic, out->view_red)) return rc;
+    const bool bots = has_lookahead_bots(P), views = P.view_actor != nullptr;
+    if (bots) return views ? launch_env<PM_MODE_STEP, 1, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 1, 0>(P, (cudaStream_t)stream);
+    return views ? launch_env<PM_MODE_STEP, 0, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 0, 0>(P, (cudaStream_t)stream);
 }
 
 // ---- host-buffer step ------------------------------------------------------

@@ -98,6 +98,8 @@ struct PmParams {
     double *reward; uint8_t *done; uint8_t *legal; int32_t *score_change; double *shaping; float *shaped;
     void *packed;                       // [N] pm_host_record
     uint8_t *act_used;                  // [N][4] the action each agent actually played
+    // learner views (pm_step_out.view_*): canonicalised actor observations of one team + the merged critic observation
+    uint8_t *view_actor; int64_t view_actor_stride; uint8_t *view_critic; int view_red;
     const uint8_t *mask;                // reset only
 };
 
@@ -121,7 +123,7 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     int o = 0;
     // static tables (one copy per CTA)
     m.lut = o; o += 64;                 // 16 x float4
-    m.masks = o; o += 4 * NCAT;
+    m.masks = o; o += PM_G_NMASKS * NCAT;
     m.lay = o; o += (L == 1) ? LS : 0;
     o = (o + 3) & ~3;
     m.blk0 = o;
@@ -179,6 +181,33 @@ PM_HD uint32_t pm_extract32(const uint32_t *w, int st, int NW, int s) {
     const uint32_t lo = ((unsigned)k < (unsigned)NW) ? w[k * st] : 0u;
     const uint32_t hi = ((unsigned)(k + 1) < (unsigned)NW) ? w[(k + 1) * st] : 0u;
     return pm_funnel_r(lo, hi, r);
+}
+
+// ---- mirrored bitsets for the canonical red-learner view --------------------------
+PM_HD uint32_t pm_brev32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+    v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+    return (v >> 16) | (v << 16);
+#endif
+}
+// dst = src with every row reversed (cell (x, y) -> (W-1-x, y)); both c-indexed, word stride st; W <= 32.
+PM_HD void pm_mirror_bits(const uint32_t *src, uint32_t *dst, int st, int W, int H, int NW) {
+    for (int w = 0; w < NW; ++w) dst[w * st] = 0;
+    const uint32_t rowmask = W >= 32 ? 0xffffffffu : ((1u << W) - 1u);
+    for (int y = 0; y < H; ++y) {
+        const int s = y * W, k = s >> 5, r = s & 31;
+        const uint32_t lo = src[k * st], hi = (k + 1 < NW) ? src[(k + 1) * st] : 0u;
+        const uint32_t row = pm_funnel_r(lo, hi, r) & rowmask;
+        if (!row) continue;
+        const uint32_t m = pm_brev32(row) >> (32 - W);
+        dst[k * st] |= m << r;
+        if (r + W > 32) dst[(k + 1) * st] |= m >> (32 - r);
+    }
 }
 
 // Agents of one env, unpacked into registers (all loops over agents unroll).
@@ -462,7 +491,7 @@ struct PmStepAcc {
 
 // One turn of gymPacMan.step's loop for agent A (gymPacMan.py:149-167): pick the action (caller's,
 // random legal, or baselineTeam), get_reward bookkeeping, the sub-move, the observation snapshot.
-template <int A, int BOTS>
+template <int A, int BOTS, int VIEWS>
 PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const PmSmem &M, int el, int64_t n, uint32_t lid,
                          PmAgents &g, uint32_t *food, uint32_t *caps, PmStepAcc &S, uint32_t act4, int steps,
                          uint32_t episode) {
@@ -516,11 +545,16 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
 
     // ---- observation snapshot for agent A (gymPacMan.py:166) + shaping ----
     pm_store_snapshot(sm, M, P, A, el, g);
+    if (VIEWS && P.view_red && (A & 1) == 0) {         // red learner: keep a mirrored copy of this snapshot's bitsets
+        const int ms = 4 + BOTS + (A >> 1);
+        pm_mirror_bits(fk, food + (size_t)ms * NW * E1, E1, W, X.H, NW);
+        if (ck) pm_mirror_bits(ck, caps + (size_t)ms * NW * E1, E1, W, X.H, NW);
+    }
     S.shap[A] = pm_shaping((int)(S.snap[A] & 0xff), (int)((S.snap[A] >> 8) & 0xff), (int)(S.snap[A] >> 16), g.x[A], g.y[A]);
     S.snap[A] = (uint32_t)g.x[A] | (uint32_t)g.y[A] << 8 | (uint32_t)g.carry[A] << 16;
 }
 
-template <int BOTS>
+template <int BOTS, int VIEWS>
 PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
     if (n >= P.n_end) { sm[M.lid + el] = 0xffffffffu; return; }
@@ -567,10 +601,10 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         for (int i = 0; i < 4; ++i) { long long v = a8[i]; act4 |= (uint32_t)((v < 0 || v > 4) ? 255 : (int)v) << (8 * i); }
     }
 
-    pm_agent_turn<0, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    pm_agent_turn<1, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    pm_agent_turn<2, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    pm_agent_turn<3, BOTS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<0, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<1, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<2, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<3, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
 
     int score = S.score, rf = S.b.rf, bf = S.b.bf;
     const int sc_total = S.sc_total;
@@ -620,6 +654,12 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         food_dirty = true; caps_dirty = caps != nullptr;
 #pragma unroll
         for (int k = 0; k < 4; ++k) pm_store_snapshot(sm, M, P, k, el, g);
+        if (VIEWS && P.view_red) {
+            for (int l = 0; l < 2; ++l) {
+                pm_mirror_bits(food, food + (size_t)(4 + BOTS + l) * NW * E1, E1, W, P.H, NW);
+                if (caps) pm_mirror_bits(caps, caps + (size_t)(4 + BOTS + l) * NW * E1, E1, W, P.H, NW);
+            }
+        }
     }
 
     // ---- outputs ----
@@ -665,7 +705,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
 // ============================================================================
 // phase A, MODE_RESET / MODE_OBSERVE: one state, four observations of it
 // ============================================================================
-template <int MODE>
+template <int MODE, int VIEWS>
 PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
     if (n >= P.n_end || (MODE == PM_MODE_RESET && P.mask && !P.mask[n])) { sm[M.lid + el] = 0xffffffffu; return; }
@@ -716,6 +756,12 @@ PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm,
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) pm_store_snapshot(sm, M, P, k, el, g);
+    if (VIEWS && P.view_red) {
+        for (int l = 0; l < 2; ++l) {
+            pm_mirror_bits(food, food + (size_t)(4 + l) * NW * E1, E1, W, P.H, NW);
+            if (caps) pm_mirror_bits(caps, caps + (size_t)(4 + l) * NW * E1, E1, W, P.H, NW);
+        }
+    }
     if (P.legal) {
         const uint32_t *walls = lay + pm_l_walls(P.HW);
         uint32_t lm = 0;
@@ -743,8 +789,10 @@ PM_HD void pm_records_out(const PmParams &P, const uint32_t *sm, const PmSmem &M
 struct PmUnit {
     const uint32_t *food, *caps;                // snapshot bitsets (caps == nullptr: batch has no capsules)
     uint32_t lid;
-    uint32_t p_own, p_ally, p_e1, p_e2;         // bit positions of the four agents in the bit string
+    uint32_t p_own, p_ally, p_e1, p_e2;         // bit positions of the four agents in the bit string (0xffffffff: none)
     uint32_t patch;                             // own-cell element | (1+carrying) << 16, or 0xffffffff
+    uint32_t p_own2, patch2;                    // critic view: the second learner's own cell (plane 1) and its patch
+    int mirror;                                 // canonical red-learner view: mirrored tables and bitsets
 };
 
 template <int MODE>
@@ -757,6 +805,50 @@ PM_HD bool pm_unit_load(const PmParams &P, const uint32_t *sm, const PmSmem &M, 
     const uint32_t pa = sm[M.posA + k * M.E1 + el], pb = sm[M.posB + k * M.E1 + el];
     U.p_own = pa & 0xffff; U.p_ally = pa >> 16; U.p_e1 = pb & 0xffff; U.p_e2 = pb >> 16;
     U.patch = sm[M.patch + k * M.E1 + el];
+    U.p_own2 = 0xffffffffu; U.patch2 = 0xffffffffu; U.mirror = 0;
+    return true;
+}
+
+// x -> W-1-x inside one plane of the bit string
+PM_HD uint32_t pm_mirror_pos(uint32_t pos, int plane, int HW, int W) {
+    if (pos == 0xffffffffu) return pos;
+    const int c = (int)pos - plane * HW, x = c % W;
+    return (uint32_t)(plane * HW + c + (W - 1 - 2 * x));
+}
+PM_HD uint32_t pm_mirror_patch(uint32_t patch, int HW, int W) {
+    if (patch == 0xffffffffu) return patch;
+    return (patch & 0xffff0000u) | pm_mirror_pos(patch & 0xffff, 1, HW, W);
+}
+
+// Units of the learner views (pacman_mappo_resnet.py:462-469): v = 0, 1: the two learner agents of team
+// P.view_red as the actor sees them (canonicalize_obs); v = 2: merge_obs_for_critic of the two.
+// mslot0: first of the two bitset slots that hold the mirrored snapshots (red learners only).
+template <int MODE>
+PM_HD bool pm_view_unit_load(const PmParams &P, const uint32_t *sm, const PmSmem &M, int v, int el, int mslot0, PmUnit &U) {
+    U.lid = sm[M.lid + el];
+    if (U.lid == 0xffffffffu) return false;
+    const int red = P.view_red != 0;
+    const int l = v == 2 ? 0 : v;                                // whose snapshot the board comes from
+    const int k = red ? 2 * l : 2 * l + 1;                       // agent index of that learner
+    const int slot = red ? mslot0 + l : ((MODE == PM_MODE_STEP) ? k : 0);
+    U.food = sm + M.food + (size_t)slot * P.NW * M.E1 + el;
+    U.caps = P.has_caps ? sm + M.caps + (size_t)slot * P.NW * M.E1 + el : nullptr;
+    const uint32_t pa = sm[M.posA + k * M.E1 + el], pb = sm[M.posB + k * M.E1 + el];
+    U.p_own = pa & 0xffff; U.p_ally = pa >> 16; U.p_e1 = pb & 0xffff; U.p_e2 = pb >> 16;
+    U.patch = sm[M.patch + k * M.E1 + el];
+    U.p_own2 = 0xffffffffu; U.patch2 = 0xffffffffu; U.mirror = red;
+    if (v == 2) {                                                // merged: both learners on plane 1, plane 4 cleared
+        const int k2 = k + 2;
+        U.p_ally = 0xffffffffu;
+        U.p_own2 = sm[M.posA + k2 * M.E1 + el] & 0xffff;
+        U.patch2 = sm[M.patch + k2 * M.E1 + el];
+    }
+    if (red) {
+        U.p_own = pm_mirror_pos(U.p_own, 1, P.HW, P.W); U.p_own2 = pm_mirror_pos(U.p_own2, 1, P.HW, P.W);
+        U.p_ally = pm_mirror_pos(U.p_ally, 4, P.HW, P.W);
+        U.p_e1 = pm_mirror_pos(U.p_e1, 5, P.HW, P.W); U.p_e2 = pm_mirror_pos(U.p_e2, 5, P.HW, P.W);
+        U.patch = pm_mirror_patch(U.patch, P.HW, P.W); U.patch2 = pm_mirror_patch(U.patch2, P.HW, P.W);
+    }
     return true;
 }
 
@@ -764,8 +856,8 @@ PM_HD bool pm_unit_load(const PmParams &P, const uint32_t *sm, const PmSmem &M, 
 // static wall plane | food planes 6,7 | capsule planes 2,3 | the four agent bits.
 PM_HD uint32_t pm_cat_word(const PmParams &P, const uint32_t *st, const PmSmem &M, const PmUnit &U, int j) {
     const int NCAT = P.NCAT, NW = P.NW, HW = P.HW, E1 = M.E1;
-    const uint32_t *m2 = st + M.masks, *m3 = m2 + NCAT, *m6 = m3 + NCAT, *m7 = m6 + NCAT;
-    const int woff = pm_l_wallcat(HW) + j;
+    const uint32_t *m2 = st + M.masks + (U.mirror ? 4 * NCAT : 0), *m3 = m2 + NCAT, *m6 = m3 + NCAT, *m7 = m6 + NCAT;
+    const int woff = (U.mirror ? pm_l_wallcatm(HW) : pm_l_wallcat(HW)) + j;
     uint32_t w;
     if (P.L == 1) w = st[M.lay + woff];
     else {
@@ -787,6 +879,7 @@ PM_HD uint32_t pm_cat_word(const PmParams &P, const uint32_t *st, const PmSmem &
     d = U.p_ally - (unsigned)b0; if (d < 32u) w |= 1u << d;
     d = U.p_e1 - (unsigned)b0;   if (d < 32u) w |= 1u << d;
     d = U.p_e2 - (unsigned)b0;   if (d < 32u) w |= 1u << d;
+    d = U.p_own2 - (unsigned)b0; if (d < 32u) w |= 1u << d;
     return w;
 }
 
@@ -884,6 +977,69 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
         }
         if (U.patch != 0xffffffffu) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
 #endif
+    }
+}
+
+// ============================================================================
+// phase B': learner views as uint8 planes (f2: canonicalize_obs + merge_obs_for_critic
+// fused into the encoder, pacman_mappo_resnet.py:215-229, 267-274)
+// ============================================================================
+// Three units per env: the two learners' actor observations and the merged critic observation, each
+// 8*H*W bytes (0/1 planes, own cell = 1 + numCarrying: exact in uint8).  Lane L builds word 32g+L of the
+// (possibly mirrored) bit string; four store rounds follow in which lane L writes bytes 8*(32r+L) ..+7 of
+// the group = byte (L & 3) of word 32g + 8r + (L >> 2), spread to one bit per byte by a multiply-and-mask.
+PM_HD uint32_t pm_spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
+
+template <int MODE>
+PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps,
+                           int lane, int64_t n0, int mslot0) {
+    const int NCAT = P.NCAT, E = P.E;
+    const int n8 = P.HW;                               // 8-byte chunks per view (8*HW / 8)
+    const int ngroups = (NCAT + 31) >> 5;
+    for (int u = warp; u < 3 * E; u += nwarps) {
+        const int v = u >> P.lgE, el = u & (E - 1);
+        PmUnit U;
+        if (!pm_view_unit_load<MODE>(P, sm, M, v, el, mslot0, U)) continue;
+        uint8_t *dstb = (v == 2 ? P.view_critic : P.view_actor + (size_t)v * P.view_actor_stride) + (size_t)(n0 + el) * 8 * P.HW;
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(dstb);
+#if defined(__CUDA_ARCH__)
+        const int sh = (lane & 3) * 8, src = lane >> 2;
+        for (int g = 0; g < ngroups; ++g) {
+            const int j = 32 * g + lane;
+            const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
+            const int fbase = 128 * g + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t w = __shfl_sync(0xffffffffu, word, 8 * r + src) >> sh;
+                const int f = fbase + 32 * r;
+                if (f < n8) dst[f] = (unsigned long long)pm_spread4(w & 15u) | (unsigned long long)pm_spread4((w >> 4) & 15u) << 32;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+#else
+        if (lane != 0) continue;
+        for (int j = 0; j < NCAT; ++j) {
+            const uint32_t word = pm_cat_word(P, st, M, U, j);
+            for (int b = 0; b < 4; ++b) {
+                const int f = 4 * j + b;
+                if (f < n8) {
+                    const uint32_t w = word >> (8 * b);
+                    dst[f] = (unsigned long long)pm_spread4(w & 15u) | (unsigned long long)pm_spread4((w >> 4) & 15u) << 32;
+                }
+            }
+        }
+        {
+#endif
+            // own-cell values 1 + numCarrying; merged view: elementwise max of the two learners' planes
+            if (U.patch != 0xffffffffu) dstb[U.patch & 0xffff] = (uint8_t)(U.patch >> 16 > 255 ? 255 : U.patch >> 16);
+            if (U.patch2 != 0xffffffffu) {
+                const uint32_t v2 = U.patch2 >> 16 > 255 ? 255 : U.patch2 >> 16;
+                uint8_t *q = dstb + (U.patch2 & 0xffff);
+                const bool same = U.patch != 0xffffffffu && (U.patch & 0xffff) == (U.patch2 & 0xffff);
+                if (!same || v2 > *q) *q = (uint8_t)v2;
+            }
+        }
     }
 }
 

@@ -28,6 +28,8 @@
 // [.. +NCAT)               M3: plane-3 bits, "red capsule" cells               (2x <= W)
 // [.. +NCAT)               M6: plane-6 bits, blue food half (x >= W/2 int)     capture.py:332-342
 // [.. +NCAT)               M7: plane-7 bits, red food half  (x <  W/2 int)
+// [.. +4*NCAT)             M2m M3m M6m M7m: the same four masks for the MIRRORED (canonical red-learner) view of
+//                          pacman_mappo_resnet.py:215-229: x -> W-1-x with the plane pairs (2,3) and (6,7) swapped
 // [.. +ND)                 dump visit order: (dx & 0xff) | (dy & 0xff) << 8    capture.py:635-661
 enum { PM_G_W = 0, PM_G_H, PM_G_HW, PM_G_NW, PM_G_NCAT, PM_G_ND, PM_G_LS, PM_G_R, PM_G_HDR = 8 };
 
@@ -35,15 +37,17 @@ PM_HD int pm_nw(int HW) { return (HW + 31) >> 5; }
 PM_HD int pm_ncat(int HW) { return (8 * HW + 31) >> 5; }
 PM_HD int pm_dump_radius(int W, int H) { return (W > H ? W : H) - 1; }
 PM_HD int pm_nd(int W, int H) { int r = pm_dump_radius(W, H); return (2 * r + 1) * (2 * r + 1); }
-PM_HD int pm_geom_words_(int W, int H) { return PM_G_HDR + 4 * pm_ncat(W * H) + pm_nd(W, H); }
-PM_HD int pm_g_mask_off(int HW, int which /*0:M2 1:M3 2:M6 3:M7*/) { return PM_G_HDR + which * pm_ncat(HW); }
-PM_HD int pm_g_dump_off(int HW) { return PM_G_HDR + 4 * pm_ncat(HW); }
+#define PM_G_NMASKS 8
+PM_HD int pm_geom_words_(int W, int H) { return PM_G_HDR + PM_G_NMASKS * pm_ncat(W * H) + pm_nd(W, H); }
+PM_HD int pm_g_mask_off(int HW, int which /*0:M2 1:M3 2:M6 3:M7, 4-7: mirrored*/) { return PM_G_HDR + which * pm_ncat(HW); }
+PM_HD int pm_g_dump_off(int HW) { return PM_G_HDR + PM_G_NMASKS * pm_ncat(HW); }
 
 // ---- layout record (per board) ---------------------------------------------
 // [0 .. NW)        walls      (c-indexed)
 // [NW .. 2NW)      initial food
 // [2NW .. 3NW)     initial capsules
 // [3NW .. +NCAT)   wallcat: the plane-0 part of the observation bit string
+// [.. +NCAT)       wallcat of the mirrored board (canonical red-learner view)
 // then 8 words:    start[4] = x | y<<8 | startIsPacman<<16 ; teams (bit i = agent i red,
 //                  capture.py:316-319) ; totalFood ; redFood0 | blueFood0<<16 ; hasCaps
 enum { PM_L_START = 0, PM_L_TEAMS = 4, PM_L_TOTALFOOD = 5, PM_L_FOODCNT = 6, PM_L_HASCAPS = 7, PM_L_TAILWORDS = 8 };
@@ -51,7 +55,8 @@ PM_HD int pm_l_walls(int HW) { (void)HW; return 0; }
 PM_HD int pm_l_food(int HW) { return pm_nw(HW); }
 PM_HD int pm_l_caps(int HW) { return 2 * pm_nw(HW); }
 PM_HD int pm_l_wallcat(int HW) { return 3 * pm_nw(HW); }
-PM_HD int pm_l_tail(int HW) { return 3 * pm_nw(HW) + pm_ncat(HW); }
+PM_HD int pm_l_wallcatm(int HW) { return 3 * pm_nw(HW) + pm_ncat(HW); }
+PM_HD int pm_l_tail(int HW) { return 3 * pm_nw(HW) + 2 * pm_ncat(HW); }
 PM_HD int pm_layout_words_(int HW) { return (pm_l_tail(HW) + PM_L_TAILWORDS + 3) & ~3; }
 
 // ---- per-env state (device blob, SoA over envs) -----------------------------

@@ -70,6 +70,12 @@ extern "C" int pm_pack_geom(int W, int H, uint32_t *out) {
         auto setbit = [&](uint32_t *m, int plane) { int b = plane * HW + c; m[b >> 5] |= 1u << (b & 31); };
         if (2 * x > W) setbit(M2, 2); else setbit(M3, 3);     // halfList: x <= W/2 is red, capture.py:344-350
         if (x >= halfway) setbit(M6, 6); else setbit(M7, 7);
+        // mirrored view (canonicalize_obs, pacman_mappo_resnet.py:215-229): canonical cell c holds source column
+        // xs = W-1-x; canonical plane 2 <- source plane 3, 3 <- 2, 6 <- 7, 7 <- 6
+        const int xs = W - 1 - x;
+        uint32_t *Mm = out + pm_g_mask_off(HW, 4);
+        if (2 * xs <= W) setbit(Mm + 0 * NCAT, 2); else setbit(Mm + 1 * NCAT, 3);
+        if (xs < halfway) setbit(Mm + 2 * NCAT, 6); else setbit(Mm + 3 * NCAT, 7);
     }
     std::vector<uint32_t> order;
     dump_visit_order(pm_dump_radius(W, H), order);
@@ -93,7 +99,11 @@ extern "C" int pm_pack_layout(const char *text, int W, int H, uint32_t *out, int
         for (int x = 0; x < W; ++x) {
             const char ch = text[(H - 1 - y) * W + x];          // text row 0 is the top row
             const int c = y * W + x;
-            if (ch == '%') { walls[c >> 5] |= 1u << (c & 31); wallcat[c >> 5] |= 1u << (c & 31); }
+            if (ch == '%') {
+                walls[c >> 5] |= 1u << (c & 31); wallcat[c >> 5] |= 1u << (c & 31);
+                const int cm = y * W + (W - 1 - x);
+                (out + pm_l_wallcatm(HW))[cm >> 5] |= 1u << (cm & 31);
+            }
             else if (ch == '.') {
                 food[c >> 5] |= 1u << (c & 31);
                 ++total;

@@ -369,9 +369,56 @@ class gymPacMan_parallel_env:
                                        C.byref(self._step_out), self._stream()), "pm_step")
         self._version += 1
         self.steps += 1
-        return dict(obs=self._obs, reward=self._reward, done=self._done, legal=self._legal,
-                    score_change=self._score_change, shaping=self._shaping, shaped_reward=self._shaped,
-                    actions_used=self._actions_used)
+        out = dict(obs=self._obs, reward=self._reward, done=self._done, legal=self._legal,
+                   score_change=self._score_change, shaping=self._shaping, shaped_reward=self._shaped,
+                   actions_used=self._actions_used)
+        if getattr(self, "_views", None):
+            out["view_actor"], out["view_critic"] = self._views[0], self._views[1]
+        return out
+
+    # ---- learner views: the trainer's network inputs written by the encoder (pm_step_out.view_*) ----
+    def set_view_outputs(self, red: Optional[bool], actor: Optional[torch.Tensor] = None,
+                         critic: Optional[torch.Tensor] = None, raw_obs: bool = True):
+        """Make every following ``step_batched`` also write the learner views of team ``red`` (False: agents
+        1, 3 as they are; True: agents 0, 2 mirrored — ``canonicalize_obs``) into ``actor`` (uint8
+        [2, N, 8, H, W], or any tensor whose two leading blocks are contiguous [N, 8, H, W]) and ``critic`` (uint8
+        [N, 8, H, W], ``merge_obs_for_critic``).  ``red=None`` switches the views off.  ``raw_obs=False`` skips
+        the four fp32 observations altogether (the step then writes 3*8*H*W bytes per env instead of
+        4*32*H*W).  Returns (actor, critic)."""
+        so = self._step_out
+        so.obs = self._obs.data_ptr() if raw_obs else None
+        if red is None:
+            so.view_actor, so.view_critic = None, None
+            self._views = None
+            return None, None
+        N, shp = self.num_envs, self.obs_shape
+        if actor is None:
+            actor = torch.empty((2, N) + shp, dtype=torch.uint8, device=self.device)
+        if critic is None:
+            critic = torch.empty((N,) + shp, dtype=torch.uint8, device=self.device)
+        for t_, lead in ((actor, 2), (critic, 1)):
+            if t_.dtype != torch.uint8 or t_.device != self.device:
+                raise ValueError("view buffers must be uint8 tensors on the env's device")
+        if tuple(actor.shape) != (2, N) + shp or not actor[0].is_contiguous() or not actor[1].is_contiguous():
+            raise ValueError(f"actor view buffer must be [2, {N}, {shp}] with contiguous [N,8,H,W] blocks")
+        if tuple(critic.shape) != (N,) + shp or not critic.is_contiguous():
+            raise ValueError(f"critic view buffer must be a contiguous [{N}, {shp}] tensor")
+        so.view_actor, so.view_actor_stride = actor.data_ptr(), actor.stride(0)
+        so.view_critic, so.view_red = critic.data_ptr(), int(bool(red))
+        self._views = (actor, critic, bool(red))
+        return actor, critic
+
+    def observe_views(self, red: bool, actor: Optional[torch.Tensor] = None, critic: Optional[torch.Tensor] = None):
+        """The learner views of the CURRENT state (e.g. right after a reset)."""
+        N, shp = self.num_envs, self.obs_shape
+        if actor is None:
+            actor = torch.empty((2, N) + shp, dtype=torch.uint8, device=self.device)
+        if critic is None:
+            critic = torch.empty((N,) + shp, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_observe_views(C.byref(self._desc), int(bool(red)), actor.data_ptr(), actor.stride(0),
+                                                critic.data_ptr(), self._stream()), "pm_observe_views")
+        return actor, critic
 
     def step_host(self, actions_host: torch.Tensor, want_obs: bool = False):
         """One step with HOST buffers through the C ABI's ``pm_step_host``: ``actions_host``

@@ -218,6 +218,7 @@ class TrainConfig:
     seed: int = 0
     amp_bf16: bool = False            # networks in bf16 autocast (fp32 master weights); default = reference fp32
     fast_math: bool = True            # cuDNN autotune + TF32 tensor-core matmuls for the fp32 networks
+    use_views: bool = True            # learner views written by the step kernel (False: torch flip / merge per step)
     easy_until: int = 200             # updates <= this: EASY_TEAMS only (`:396-402`)
     selfplay_after: int = 800         # update index after which self-play opponents enter the mix (`:404-438`)
     log_every: int = 1
@@ -226,17 +227,19 @@ class TrainConfig:
 
 
 class Rollout:
-    """On-device [T, N, ...] buffers.  Observations are stored as uint8 (they hold small non-negative
-    integers: 0/1 planes and 1+numCarrying), a quarter of the fp32 footprint; converted at minibatch time."""
+    """On-device rollout buffers, agent-major ([T, 2, N, ...]) so that the step kernel can write each step's learner
+    views straight into slot t+1 (slot T holds the bootstrap observation).  Observations are stored as uint8 (they
+    hold small non-negative integers: 0/1 planes and 1+numCarrying), a quarter of the fp32 footprint; converted at
+    minibatch time."""
 
     def __init__(self, T, N, obs_shape, device):
-        self.obs = torch.zeros((T, N, 2) + tuple(obs_shape), dtype=torch.uint8, device=device)
-        self.merged = torch.zeros((T, N) + tuple(obs_shape), dtype=torch.uint8, device=device)
-        self.action = torch.zeros((T, N, 2), dtype=torch.int64, device=device)
-        self.logp = torch.zeros((T, N, 2), dtype=torch.float32, device=device)
-        self.reward = torch.zeros((T, N, 2), dtype=torch.float32, device=device)
-        self.done = torch.zeros((T, N, 2), dtype=torch.float32, device=device)
-        self.value = torch.zeros((T, N, 2), dtype=torch.float32, device=device)
+        self.obs = torch.zeros((T + 1, 2, N) + tuple(obs_shape), dtype=torch.uint8, device=device)
+        self.merged = torch.zeros((T + 1, N) + tuple(obs_shape), dtype=torch.uint8, device=device)
+        self.action = torch.zeros((T, 2, N), dtype=torch.int64, device=device)
+        self.logp = torch.zeros((T, 2, N), dtype=torch.float32, device=device)
+        self.reward = torch.zeros((T, 2, N), dtype=torch.float32, device=device)
+        self.done = torch.zeros((T, 2, N), dtype=torch.float32, device=device)
+        self.value = torch.zeros((T, 2, N), dtype=torch.float32, device=device)
 
 
 class MAPPOTrainer:
@@ -331,50 +334,62 @@ class MAPPOTrainer:
         stats = torch.zeros(4, dtype=torch.float64, device=self.device)      # episodes, return sum, wins, reward sum
         actions = torch.zeros((N, 4), dtype=torch.int64, device=self.device)
         team_row = 0 if play_as_red else 1
-        for t in range(T):
-            actor_in, merged = self._views(obs4, learner_ids, play_as_red)
-            ro.obs[t, :, 0] = actor_in[:N]
-            ro.obs[t, :, 1] = actor_in[N:]
-            ro.merged[t] = merged
-            with self._autocast():
-                act, logp, value, _ = self.agent.get_action_and_value(actor_in, merged)
-            act = act.view(2, N)
-            ro.action[t] = act.t()
-            ro.logp[t] = logp.float().view(2, N).t()
-            ro.value[t] = value.float().unsqueeze(1).expand(N, 2)
-            env_act = canonicalize_action(act, play_as_red)
-            actions[:, learner_ids[0]] = env_act[0]
-            actions[:, learner_ids[1]] = env_act[1]
-            if selfplay:
-                o_in, o_merged = self._views(obs4, opp_ids, not play_as_red)
+        shp = self.obs_shape
+
+        def store_views(slot, o4):                                    # torch path (`:462-469`) when the kernel views are off
+            a_in, m = self._views(o4, learner_ids, play_as_red)
+            ro.obs[slot] = a_in.view(2, N, *shp)
+            ro.merged[slot] = m
+        if cfg.use_views:
+            env.observe_views(play_as_red, ro.obs[0], ro.merged[0])
+        else:
+            store_views(0, obs4)
+        try:
+            for t in range(T):
+                actor_in, merged = ro.obs[t].view(2 * N, *shp).float(), ro.merged[t].float()
                 with self._autocast():
-                    o_act, _, _, _ = self.opponent.get_action_and_value(o_in, o_merged)
-                o_act = canonicalize_action(o_act.view(2, N), not play_as_red)
-                actions[:, opp_ids[0]] = o_act[0]
-                actions[:, opp_ids[1]] = o_act[1]
-            out = env.step_batched(actions)
-            obs4 = out["obs"]                                         # finished envs already show the new episode
-            ro.reward[t, :, 0] = out["shaped_reward"][learner_ids[0]]
-            ro.reward[t, :, 1] = out["shaped_reward"][learner_ids[1]]
-            d = out["done"].to(torch.float32)
-            ro.done[t] = d.unsqueeze(1).expand(N, 2)
-            # episode bookkeeping (`:516-538`): team_reward = sum over both learners = 2 x team reward
-            team_reward = 2.0 * out["reward"][team_row]
-            self._ep_return += team_reward
-            db = out["done"].bool()
-            # final score of a finished episode (`:525-531`): the env restarted in-kernel, so the score is
-            # tracked here from the per-step score_change output
-            self._score += out["score_change"]
-            won = (self._score > 0) if play_as_red else (self._score < 0)
-            stats[0] += db.sum()
-            stats[1] += (self._ep_return * db).sum()
-            stats[2] += (db & won).sum()
-            stats[3] += team_reward.sum()
-            self._ep_return.masked_fill_(db, 0.0)
-            self._score.masked_fill_(db, 0)
-        _, merged = self._views(obs4, learner_ids, play_as_red)
+                    act, logp, value, _ = self.agent.get_action_and_value(actor_in, merged)
+                act = act.view(2, N)
+                ro.action[t] = act
+                ro.logp[t] = logp.float().view(2, N)
+                ro.value[t] = value.float().unsqueeze(0).expand(2, N)
+                env_act = canonicalize_action(act, play_as_red)
+                actions[:, learner_ids[0]] = env_act[0]
+                actions[:, learner_ids[1]] = env_act[1]
+                if selfplay:
+                    o_in, o_merged = self._views(obs4, opp_ids, not play_as_red)
+                    with self._autocast():
+                        o_act, _, _, _ = self.opponent.get_action_and_value(o_in, o_merged)
+                    o_act = canonicalize_action(o_act.view(2, N), not play_as_red)
+                    actions[:, opp_ids[0]] = o_act[0]
+                    actions[:, opp_ids[1]] = o_act[1]
+                if cfg.use_views:                                     # next step's network inputs land in slot t+1;
+                    env.set_view_outputs(play_as_red, ro.obs[t + 1], ro.merged[t + 1], raw_obs=selfplay)   # raw obs only for the opponent net
+                out = env.step_batched(actions)
+                obs4 = out["obs"]                                     # finished envs already show the new episode
+                if not cfg.use_views:
+                    store_views(t + 1, obs4)
+                ro.reward[t, 0] = out["shaped_reward"][learner_ids[0]]
+                ro.reward[t, 1] = out["shaped_reward"][learner_ids[1]]
+                ro.done[t] = out["done"].to(torch.float32).unsqueeze(0).expand(2, N)
+                # episode bookkeeping (`:516-538`): team_reward = sum over both learners = 2 x team reward
+                team_reward = 2.0 * out["reward"][team_row]
+                self._ep_return += team_reward
+                db = out["done"].bool()
+                # final score of a finished episode (`:525-531`): the env restarted in-kernel, so the score is
+                # tracked here from the per-step score_change output
+                self._score += out["score_change"]
+                won = (self._score > 0) if play_as_red else (self._score < 0)
+                stats[0] += db.sum()
+                stats[1] += (self._ep_return * db).sum()
+                stats[2] += (db & won).sum()
+                stats[3] += team_reward.sum()
+                self._ep_return.masked_fill_(db, 0.0)
+                self._score.masked_fill_(db, 0)
+        finally:
+            env.set_view_outputs(None)
         with self._autocast():
-            last_value = self.agent.get_value(merged).float()
+            last_value = self.agent.get_value(ro.merged[T].float()).float()
         return last_value, stats
 
     # ------------------------------------------------------------------ update
@@ -383,9 +398,9 @@ class MAPPOTrainer:
         cfg, ro = self.cfg, self.rollout
         T, N = cfg.num_steps, cfg.num_envs
         adv, ret = compute_gae(ro.reward.view(T, 2 * N), ro.value.view(T, 2 * N), ro.done.view(T, 2 * N),
-                               last_value.unsqueeze(1).expand(N, 2).reshape(-1), GAMMA)
-        b_obs = ro.obs.view(T * N * 2, *self.obs_shape)
-        b_merged = ro.merged.view(T * N, *self.obs_shape)
+                               last_value.repeat(2), GAMMA)          # columns are (agent, env): one critic value per env
+        b_obs = ro.obs[:T].view(T * 2 * N, *self.obs_shape)            # sample s = (t, agent, env)
+        b_merged = ro.merged[:T].view(T * N, *self.obs_shape)
         b_act, b_logp = ro.action.view(-1), ro.logp.view(-1)
         b_adv, b_ret = adv.reshape(-1), ret.reshape(-1)
         S = T * N * 2
@@ -402,7 +417,8 @@ class MAPPOTrainer:
                 idx = perm[k * mb:(k + 1) * mb]
                 norm_adv = norm_adv_all[k * mb:(k + 1) * mb]
                 with self._autocast():
-                    vals, lps, ent = self.agent.evaluate(b_obs[idx].float(), b_merged[idx >> 1].float(), b_act[idx])
+                    midx = torch.div(idx, 2 * N, rounding_mode="floor") * N + idx % N       # (t, env) of sample (t, agent, env)
+                    vals, lps, ent = self.agent.evaluate(b_obs[idx].float(), b_merged[midx].float(), b_act[idx])
                 vals, lps, ent = vals.float(), lps.float(), ent.float()
                 ratio = (lps - b_logp[idx]).exp()
                 pg = -torch.min(norm_adv * ratio, norm_adv * torch.clamp(ratio, 1 - clip_eps, 1 + clip_eps)).mean()

@@ -20,8 +20,9 @@ static int fill(const pm_env_desc *d, PmParams &P, int E, int /*KB*/) { return p
 template <int MODE>
 static void run(const PmParams &P) {
     bool bots = false;
-    for (int i = 0; i < 4; ++i) bots |= ((P.bot_kind >> (4 * i)) & 15) >= 2;
-    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L, bots ? 5 : 4);
+    for (int i = 0; i < 4; ++i) bots |= MODE == PM_MODE_STEP && ((P.bot_kind >> (4 * i)) & 15) >= 2;   // like the C ABI glue
+    const bool views = P.view_actor != nullptr;
+    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L, 4 + (bots ? 1 : 0) + (views ? 2 : 0));
     std::vector<uint32_t> smv((size_t)M.total + 4);
     uint32_t *sm = smv.data();
     const int64_t nblk = (P.n_end - P.n_begin + P.E - 1) / P.E;
@@ -32,17 +33,26 @@ static void run(const PmParams &P) {
             float *v = reinterpret_cast<float *>(sm + M.lut) + 4 * t;
             v[0] = (t & 1) ? 1.f : 0.f; v[1] = (t & 2) ? 1.f : 0.f; v[2] = (t & 4) ? 1.f : 0.f; v[3] = (t & 8) ? 1.f : 0.f;
         }
-        for (int i = 0; i < 4 * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
+        for (int i = 0; i < PM_G_NMASKS * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
         if (P.L == 1) for (int i = 0; i < P.LS; ++i) sm[M.lay + i] = P.layouts[i];
         for (int el = 0; el < P.E; ++el) {
-            if (MODE == PM_MODE_STEP) { if (bots) pm_phaseA_step<1>(P, sm, sm, M, el, n0); else pm_phaseA_step<0>(P, sm, sm, M, el, n0); }
-            else pm_phaseA_static<MODE>(P, sm, sm, M, el, n0);
+            if (MODE == PM_MODE_STEP) {
+                if (bots && views) pm_phaseA_step<1, 1>(P, sm, sm, M, el, n0);
+                else if (bots) pm_phaseA_step<1, 0>(P, sm, sm, M, el, n0);
+                else if (views) pm_phaseA_step<0, 1>(P, sm, sm, M, el, n0);
+                else pm_phaseA_step<0, 0>(P, sm, sm, M, el, n0);
+            } else if (views) pm_phaseA_static<MODE, 1>(P, sm, sm, M, el, n0);
+            else pm_phaseA_static<MODE, 0>(P, sm, sm, M, el, n0);
         }
         if (MODE == PM_MODE_STEP && P.packed)
             for (int t = 0; t < 3 * P.E; ++t) pm_records_out(P, sm, M, t, n0);
-        if (!P.obs) continue;
-        for (int w = 0; w < EMU_THREADS / 32; ++w)
-            for (int lane = 0; lane < 32; ++lane) pm_phaseB<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0);
+        if (P.obs)
+            for (int w = 0; w < EMU_THREADS / 32; ++w)
+                for (int lane = 0; lane < 32; ++lane) pm_phaseB<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0);
+        if (views)
+            for (int w = 0; w < EMU_THREADS / 32; ++w)
+                for (int lane = 0; lane < 32; ++lane)
+                    pm_phaseB_views<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0, 4 + (bots ? 1 : 0));
     }
 }
 
@@ -58,12 +68,20 @@ extern "C" int emu_observe(const pm_env_desc *d, float *obs, int64_t stride, int
     run<PM_MODE_OBSERVE>(P);
     return 0;
 }
+extern "C" int emu_observe_views(const pm_env_desc *d, int red, uint8_t *actor, int64_t stride, uint8_t *critic, int E, int KB) {
+    PmParams P; if (int rc = fill(d, P, E, KB)) return rc;
+    P.view_actor = actor; P.view_actor_stride = stride; P.view_critic = critic; P.view_red = red;
+    run<PM_MODE_OBSERVE>(P);
+    return 0;
+}
 extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize, const pm_step_out *out, int E, int KB) {
     PmParams P; if (int rc = fill(d, P, E, KB)) return rc;
     P.actions = actions; P.act_size = itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
     P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
+    P.view_actor = out->view_actor; P.view_actor_stride = out->view_actor_stride; P.view_critic = out->view_critic;
+    P.view_red = out->view_red;
     run<PM_MODE_STEP>(P);
     return 0;
 }

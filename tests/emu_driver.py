@@ -88,6 +88,17 @@ class EmuEnv:
         lib().emu_observe(C.byref(self.desc), _p(obs), C.c_int64(obs[0].size), self.E, self.KB)
         return obs
 
+    def set_views(self, red=None):
+        """red=None: views off; False / True: learner team blue (agents 1,3) / red (agents 0,2, mirrored)."""
+        self.view_red = red
+
+    def observe_views(self, red):
+        va = np.full((2, self.N) + self.obs_shape, 0xEE, np.uint8)
+        vc = np.full((self.N,) + self.obs_shape, 0xEE, np.uint8)
+        rc = lib().emu_observe_views(C.byref(self.desc), int(red), _p(va), C.c_int64(va[0].size), _p(vc), self.E, self.KB)
+        assert rc == 0, rc
+        return va, vc
+
     def set_range(self, begin=0, count=0):
         self.desc.env_begin, self.desc.env_count = int(begin), int(count)
 
@@ -102,6 +113,11 @@ class EmuEnv:
         so = pmlib.PmStepOut(o["obs"].ctypes.data, o["obs"][0].size, o["reward"].ctypes.data, o["done"].ctypes.data,
                              o["legal"].ctypes.data, o["score_change"].ctypes.data, o["shaping"].ctypes.data,
                              o["shaped"].ctypes.data, self.last_packed.ctypes.data, o["actions_used"].ctypes.data)
+        if getattr(self, "view_red", None) is not None:
+            o["view_actor"] = np.full((2, self.N) + self.obs_shape, 0xEE, np.uint8)
+            o["view_critic"] = np.full((self.N,) + self.obs_shape, 0xEE, np.uint8)
+            so.view_actor, so.view_actor_stride = o["view_actor"].ctypes.data, o["view_actor"][0].size
+            so.view_critic, so.view_red = o["view_critic"].ctypes.data, int(self.view_red)
         rc = lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
         assert rc == 0, rc
         return o

@@ -278,3 +278,43 @@ def body_max_size_board(make_env, N=40, T=150):
         np.testing.assert_array_equal(o["score_change"], r["score_change"])
         np.testing.assert_array_equal(o["legal"][keep], r["legal"][keep])
         np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4)[keep], r["obs"][keep], err_msg=f"t={t} obs")
+
+
+# ---- learner views (f2): numpy restatement of the trainer's view functions, themselves pinned to the reference
+# by tests/test_mappo_host.py (canonicalize_obs / merge_obs_for_critic, pacman_mappo_resnet.py:215-229, 267-274) ----
+def np_canonicalize(obs, red):
+    if not red:
+        return obs
+    return obs[..., ::-1][..., [0, 1, 3, 2, 4, 5, 7, 6], :, :]
+
+
+def np_views(obs4, red):
+    """obs4 [4,N,8,H,W] f32 -> (actor [2,N,8,H,W], critic [N,8,H,W]) as uint8."""
+    ids = (0, 2) if red else (1, 3)
+    a, b = np_canonicalize(obs4[ids[0]], red), np_canonicalize(obs4[ids[1]], red)
+    merged = a.copy()
+    merged[:, 1] = np.maximum(a[:, 1], b[:, 1])
+    merged[:, 4] = 0
+    return np.stack([a, b]).astype(np.uint8), merged.astype(np.uint8)
+
+
+def body_learner_views(make_env, rows, N=48, T=120, length=90, **kw):
+    """view_actor / view_critic written by the encoder == canonicalize + merge applied to the raw observations of
+    the same step, for both learner teams, across auto-resets, kills, carrying and capsules."""
+    rng = np.random.default_rng(33)
+    carried = 0
+    for red in (False, True):
+        env = make_env(rows, N, length=length, auto_reset=True, **kw)
+        env.set_views(red)
+        obs, _ = env.reset()
+        va, vc = env.observe_views(red)
+        wa, wc = np_views(obs, red)
+        np.testing.assert_array_equal(va, wa, err_msg=f"reset views red={red}")
+        np.testing.assert_array_equal(vc, wc)
+        for t in range(T):
+            o = env.step(biased_actions(rng, N, 0.6, t))
+            wa, wc = np_views(o["obs"], red)
+            np.testing.assert_array_equal(o["view_actor"], wa, err_msg=f"t={t} actor views red={red}")
+            np.testing.assert_array_equal(o["view_critic"], wc, err_msg=f"t={t} critic view red={red}")
+            carried += int((wc[:, 1] > 1).sum())
+    assert carried > 0                # own-cell values above 1 (carrying) were exercised

@@ -46,7 +46,15 @@ class CudaEnv:
         return dict(obs=o["obs"].cpu().numpy(), reward=o["reward"].cpu().numpy(), done=o["done"].cpu().numpy(),
                     legal=o["legal"].cpu().numpy(), score_change=o["score_change"].cpu().numpy(),
                     shaping=o["shaping"].cpu().numpy(), shaped=o["shaped_reward"].cpu().numpy(),
-                    actions_used=o["actions_used"].cpu().numpy())
+                    actions_used=o["actions_used"].cpu().numpy(),
+                    **({k: o[k].cpu().numpy() for k in ("view_actor", "view_critic")} if "view_actor" in o else {}))
+
+    def set_views(self, red=None):
+        self.env.set_view_outputs(red)
+
+    def observe_views(self, red):
+        a, c = self.env.observe_views(red)
+        return a.cpu().numpy(), c.cpu().numpy()
 
     def set_range(self, begin=0, count=0):
         self.env._desc.env_begin, self.env._desc.env_count = int(begin), int(count)
@@ -333,15 +341,14 @@ def test_mappo_trainer_rollout_gae_and_update():
         assert rec["episodes"] >= 96                        # length 12 -> every env finishes at least once in 24 steps
         ro = tr.rollout
         # dones: identical for both learners; obs buffers hold exactly one own cell per learner
-        assert torch.equal(ro.done[:, :, 0], ro.done[:, :, 1])
+        assert torch.equal(ro.done[:, 0], ro.done[:, 1])
         assert bool(((ro.obs[:, :, :, 1] > 0).sum((-1, -2)) == 1).all())
         assert bool((ro.merged[:, :, 4] == 0).all()) and bool(((ro.merged[:, :, 1] > 0).sum((-1, -2)) <= 2).all())
         # GAE over the stored buffers == oracle restatement of compute_gae, per column, bit for bit
         T, N = cfg.num_steps, cfg.num_envs
         with torch.no_grad():
-            lv = tr.agent.get_value(ro.merged[-1].float()) * 0 + 0.25          # any [N] vector
-        adv, ret = M.compute_gae(ro.reward.view(T, 2 * N), ro.value.view(T, 2 * N), ro.done.view(T, 2 * N),
-                                 lv.unsqueeze(1).expand(N, 2).reshape(-1))
+                lv = tr.agent.get_value(ro.merged[-1].float()) * 0 + 0.25          # any [N] vector
+        adv, ret = M.compute_gae(ro.reward.view(T, 2 * N), ro.value.view(T, 2 * N), ro.done.view(T, 2 * N), lv.repeat(2))
         oadv, oret = oracle.gae(ro.reward.view(T, 2 * N).cpu().numpy(), ro.value.view(T, 2 * N).cpu().numpy(),
                                 ro.done.view(T, 2 * N).cpu().numpy(), np.full(2 * N, 0.25, np.float32))
         np.testing.assert_array_equal(adv.cpu().numpy().view(np.uint32), oadv.view(np.uint32))
@@ -379,9 +386,9 @@ def test_mappo_rollout_rewards_match_reference_formula():
     ro = tr.rollout
     for t, a in enumerate(recorded):
         r = ref.step(a.cpu().numpy(), with_obs=False, auto_reset=True, nthreads=0)
-        want = (2.0 * r["reward"][:, 1][:, None] + 0.1 * r["shaping"][:, [1, 3]]).astype(np.float32)
+        want = (2.0 * r["reward"][:, 1][:, None] + 0.1 * r["shaping"][:, [1, 3]]).astype(np.float32).T.copy()
         np.testing.assert_array_equal(ro.reward[t].cpu().numpy().view(np.uint32), want.view(np.uint32), err_msg=f"t={t}")
-        np.testing.assert_array_equal(ro.done[t, :, 0].cpu().numpy(), r["done"].astype(np.float32))
+        np.testing.assert_array_equal(ro.done[t, 0].cpu().numpy(), r["done"].astype(np.float32))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -446,3 +453,61 @@ def test_cuda_baseline_team_random_tiebreak_stays_in_best_set():
         not_first += int((multi & (chosen != first_best)).sum())
         mirror.step(used.astype(np.int32), with_obs=False, auto_reset=True, nthreads=0)
     assert seen_multi > 50 and not_first > 10, (seen_multi, not_first)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# learner views fused into the encoder
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lay", ["tinyCapture", "smallCapture", "bloxCapture", "capsSmall", "odd15"])
+def test_cuda_learner_views_match_canonicalize_and_merge(lay):
+    from parity_bodies import body_learner_views
+    rows = lay_rows(lay) if lay.endswith("Capture") else helpers.load_traj(lay)["layout"]
+    body_learner_views(CudaEnv, rows, N=300, T=140)
+
+
+def test_cuda_learner_views_with_bots_and_without_raw_obs():
+    """Views with the baselineTeam kernel variant; and with raw_obs=False the views are unchanged while the fp32
+    observation buffer is left untouched."""
+    from parity_bodies import body_learner_views, np_views
+    body_learner_views(CudaEnv, lay_rows("smallCapture"), N=200, T=100, bot_kind=[2, 0, 3, 0])
+    rows = lay_rows("tinyCapture")
+    N = 130
+    a_env, b_env = CudaEnv(rows, N, length=50, auto_reset=True), CudaEnv(rows, N, length=50, auto_reset=True)
+    a_env.reset(); b_env.reset()
+    a_env.env.set_view_outputs(True)
+    b_env.env.set_view_outputs(True, raw_obs=False)
+    b_env.env._obs.fill_(-7.0)
+    rng = np.random.default_rng(2)
+    for t in range(80):
+        act = biased_actions(rng, N, 0.6, t)
+        oa, ob = a_env.step(act), b_env.step(act)
+        np.testing.assert_array_equal(oa["view_actor"], ob["view_actor"])
+        np.testing.assert_array_equal(oa["view_critic"], ob["view_critic"])
+        np.testing.assert_array_equal(oa["reward"], ob["reward"])
+        assert (ob["obs"] == -7.0).all()
+    # torch-side functions the trainer would otherwise run give the same tensors
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    o = a_env.env.step_batched(torch.as_tensor(biased_actions(rng, N)).cuda())
+    ca, cb = M.canonicalize_obs(o["obs"][0], True), M.canonicalize_obs(o["obs"][2], True)
+    assert torch.equal(o["view_actor"][0].float(), ca) and torch.equal(o["view_actor"][1].float(), cb)
+    assert torch.equal(o["view_critic"].float(), M.merge_obs_for_critic(ca, cb))
+
+
+def test_mappo_rollout_identical_with_kernel_views_and_torch_views():
+    """use_views=True (network inputs written by the step kernel into the rollout buffer) and use_views=False
+    (torch flip / plane swap / merge on the fp32 observations, as the reference does) give the same rollout,
+    for blue and red learners, against bots and in self-play."""
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    for mode, red in (("randomTeam", False), ("baselineTeam", False), ("Self(Curr)", True), ("Self(Curr)", False)):
+        ros = []
+        for use_views in (True, False):
+            cfg = M.TrainConfig(num_envs=64, num_steps=30, num_minibatches=2, update_epochs=1, total_updates=1,
+                                length=20, seed=11, checkpoint_every=0, use_views=use_views)
+            tr = M.MAPPOTrainer(cfg, device="cuda:0")
+            torch.manual_seed(1234)
+            lv, stats = tr.collect(mode, play_as_red=red)
+            ros.append((tr.rollout, lv, stats))
+        (a, lva, sa), (b, lvb, sb) = ros
+        for name in ("obs", "merged", "action", "logp", "reward", "done", "value"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), f"{mode} red={red}: {name} differs"
+        assert torch.equal(lva, lvb) and torch.equal(sa, sb)

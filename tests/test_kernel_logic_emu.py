@@ -99,3 +99,16 @@ def test_emulated_baseline_team_matches_reference(name):
 def test_emulated_max_size_board():
     from parity_bodies import body_max_size_board
     body_max_size_board(lambda rows, n, **kw: EmuEnv(rows, n, E=8, KB=1, **kw), N=10, T=90)
+
+
+@pytest.mark.parametrize("lay", ["tinyCapture", "capsSmall", "odd15"])
+def test_emulated_learner_views(lay):
+    from parity_bodies import body_learner_views
+    rows = lay_rows(lay) if lay.endswith("Capture") else helpers.load_traj(lay)["layout"]
+    body_learner_views(lambda r, n, **kw: EmuEnv(r, n, E=8, KB=1, **kw), rows, N=20, T=110)
+
+
+def test_emulated_learner_views_with_baseline_bots():
+    from parity_bodies import body_learner_views
+    body_learner_views(lambda r, n, **kw: EmuEnv(r, n, E=4, KB=1, **kw), lay_rows("smallCapture"), N=12, T=80,
+                       bot_kind=[2, 0, 3, 0])
