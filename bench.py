@@ -227,6 +227,26 @@ def other_kernels(torch, device, N, peak):
         vbytes = (3 * 8 * 140 + 200) * N
         out[name] = {"ms": ms, "agent_steps_per_s": 4.0 * N / (ms * 1e-3), "bytes_per_launch": vbytes,
                      "achieved_GBps": vbytes / (ms * 1e-3) / 1e9}
+    # (0) BASELINE config 1 through the reference-shaped API: ONE env, dict actions, Python scalars back, red side =
+    #     baselineTeam (on-device), blue = uniform over the returned legal-action lists; wall clock incl. resets
+    import random
+    env1 = gymPacMan_parallel_env(layout_file=layout_path("tinyCapture"), self_play=False, enemieName="baselineTeam",
+                                  length=299, num_envs=1, device=device)
+    rnd = random.Random(1)
+    obs, info = env1.reset()
+    n_steps, t0 = 0, None
+    for it in range(2300):
+        if it == 300:
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        acts = {i: rnd.choice(info["legal_actions"][i]) for i in (1, 3)}
+        obs, rew, term, info = env1.step(acts)
+        n_steps += it >= 300
+        if term[1]:
+            obs, info = env1.reset()
+    dt = time.perf_counter() - t0
+    out["single_env_reference_api_tinyCapture_vs_baselineTeam"] = {
+        "env_steps_per_s": n_steps / dt, "agent_steps_per_s": 4.0 * n_steps / dt,
+        "reference_python_agent_steps_per_s_1core": 1414, "note": "one env, env.step({agent: action}) per step"}
     return out
 
 

@@ -37,7 +37,7 @@
 // VIEWS = 1: also writes the trainer's learner views (uint8, canonicalised + merged); two more bitset
 // slots hold the mirrored snapshots of red learners.
 template <int MODE, int BOTS, int VIEWS>
-__global__ void __launch_bounds__(PM_THREADS, (BOTS || VIEWS) ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
+__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const int tid = threadIdx.x;

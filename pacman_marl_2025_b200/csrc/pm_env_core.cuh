@@ -1008,8 +1008,8 @@ PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t
             const int j = 32 * g + lane;
             const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
             const int fbase = 128 * g + lane;
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            const int left = n8 - 128 * g, nr = left >= 128 ? 4 : (left + 31) >> 5;     // only the rounds that hold data
+            for (int r = 0; r < nr; ++r) {
                 const uint32_t w = __shfl_sync(0xffffffffu, word, 8 * r + src) >> sh;
                 const int f = fbase + 32 * r;
                 if (f < n8) dst[f] = (unsigned long long)pm_spread4(w & 15u) | (unsigned long long)pm_spread4((w >> 4) & 15u) << 32;

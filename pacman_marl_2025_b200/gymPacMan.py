@@ -508,7 +508,8 @@ class gymPacMan_parallel_env:
             self._rec_mapped = torch.zeros((self.num_envs, 48), dtype=torch.uint8).pin_memory()
             self._rec_mapped_views = self._record_views(self._rec_mapped)
             so = self._step_out
-            self._mapped_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None, None)
+            self._mapped_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None, None,
+                                              self._actions_used.data_ptr())
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host_mapped(C.byref(self._desc), actions_host.data_ptr(),
                                                    C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
@@ -614,8 +615,40 @@ class gymPacMan_parallel_env:
             a = torch.stack([c if c is not None else zero for c in cols], dim=1)   # bot columns are ignored in-kernel
         return a
 
+    def _step_single(self, actions):
+        """num_envs == 1 with scalar actions (the reference's own calling convention): the actions go into a pinned
+        host word the kernel reads itself, the scalars come back in one pinned ``pm_host_record``
+        (``pm_step_host_mapped``) - one launch, one clone of the observation block and one stream synchronise per
+        step instead of a handful of small copies."""
+        if not hasattr(self, "_single_act"):
+            self._single_act = torch.zeros((1, 4), dtype=torch.uint8).pin_memory()
+            self._single_np = self._single_act.numpy()
+        for i in range(4):
+            if not self.self_play and i in (0, 2):
+                continue
+            v = actions[self.agents[i]]
+            if isinstance(v, str):
+                v = self._name_to_int.get(v, 255)
+            v = int(v)
+            self._single_np[0, i] = v if 0 <= v <= 4 else 255          # out of range = illegal -> Stop, like the kernel
+        rec = self.step_host_mapped(self._single_act)
+        o = self._obs.clone()
+        obs = {self.agents[i]: o[i, 0] for i in range(4)}
+        red, blue = (float(x) for x in rec["reward"][0].tolist())
+        rewards = {self.agents[i]: (blue if i & 1 else red) for i in range(4)}
+        done = bool(rec["done"][0])
+        terms = {self.agents[i]: done for i in range(4)}
+        legal = rec["legal"][0].tolist()
+        info = {"legal_actions": {self.agents[i]: legal_mask_to_list(legal[i]) for i in range(4)},
+                "score_change": int(rec["score_change"][0])}
+        return obs, rewards, terms, info
+
     def step(self, actions):
         """gymPacMan.step (gymPacMan.py:143-193)."""
+        if self.num_envs == 1 and not isinstance(actions, torch.Tensor) and not any(
+                isinstance(actions[self.agents[i]], torch.Tensor) for i in range(4)
+                if self.self_play or i in (1, 3)):
+            return self._step_single(actions)
         out = self.step_batched(self._gather_actions(actions))
         obs = self._obs_dict()
         if self.num_envs == 1:

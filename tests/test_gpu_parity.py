@@ -511,3 +511,94 @@ def test_mappo_rollout_identical_with_kernel_views_and_torch_views():
         for name in ("obs", "merged", "action", "logp", "reward", "done", "value"):
             assert torch.equal(getattr(a, name), getattr(b, name)), f"{mode} red={red}: {name} differs"
         assert torch.equal(lva, lvb) and torch.equal(sa, sb)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference-shaped API itself (1 env, dicts, Python scalars, lists of legal actions)
+# ---------------------------------------------------------------------------------------------------------
+class RefApiDriver:
+    """Drives gymPacMan_parallel_env exactly like the reference's callers do (pacman_mappo_resnet.py:457-538,
+    pacman.py:342-358): reset() / step({agent: action}) on ONE env, reading dicts of tensors, floats, bools and
+    legal-action lists, and the GameState accessors (env.game.state...)."""
+
+    def __init__(self, fx, bots=False):
+        import tempfile
+        from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+        with tempfile.NamedTemporaryFile("w", suffix=".lay", delete=False) as f:
+            f.write("\n".join(fx["layout"]))
+        kw = dict(enemieName="baselineTeam", self_play=False, opponent_tiebreak="first") if bots else dict(self_play=True)
+        self.env = gymPacMan_parallel_env(layout_file=f.name, length=int(fx["length"]),
+                                          reward_forLegalAction=bool(fx["reward_forLegalAction"]),
+                                          defenceReward=bool(fx["defenceReward"]), **kw)
+        os.unlink(f.name)
+        self.bots, self.prev = bots, None
+
+    @staticmethod
+    def _mask(lst):
+        m = 0
+        for a in lst:
+            m |= 1 << a
+        return m
+
+    def reset(self):
+        obs, info = self.env.reset()
+        self.prev = obs
+        ag = self.env.agents
+        assert all(isinstance(a, int) for a in info["legal_actions"][ag[0]])
+        return np.stack([obs[ag[i]].cpu().numpy() for i in range(4)]), [self._mask(info["legal_actions"][ag[i]]) for i in range(4)]
+
+    def step(self, a):
+        ag = self.env.agents
+        acts = {ag[i]: int(a[i]) for i in range(4) if not (self.bots and i in (0, 2))}
+        if not self.bots:
+            acts[ag[1]] = self.env.action_mapping[int(a[1])]          # direction names are accepted too (gymPacMan.py:66-77)
+        obs, rew, term, info = self.env.step(acts)
+        assert isinstance(rew[ag[0]], float) and isinstance(term[ag[0]], bool) and isinstance(info["score_change"], int)
+        assert rew[ag[0]] == rew[ag[2]] and rew[ag[1]] == rew[ag[3]] and len(set(term.values())) == 1
+        from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+        shaping = [0.0] * 4
+        for i in range(4):                                            # the trainer's own shaping on the returned tensors
+            red = i in (0, 2)
+            pa = M.canonicalize_obs(self.prev[ag[i]], red)[1].nonzero()[0]
+            pb_t = M.canonicalize_obs(obs[ag[i]], red)[1]
+            pb = pb_t.nonzero()[0]
+            carry = float(M.canonicalize_obs(self.prev[ag[i]], red)[1][pa[0], pa[1]]) - 1
+            d = abs(int(pa[0]) - int(pb[0])) + abs(int(pa[1]) - int(pb[1]))
+            shaping[i] = (-0.15 - 0.4 - 0.15 * carry) if d > 1.5 else ((-0.15 - 0.05) if d < 0.1 else -0.15)
+        self.prev = obs
+        used = self.env._actions_used[0].cpu().numpy()
+        return dict(obs=np.stack([obs[ag[i]].cpu().numpy() for i in range(4)]), reward=[rew[ag[0]], rew[ag[1]]],
+                    done=term[ag[0]], legal=[self._mask(info["legal_actions"][ag[i]]) for i in range(4)],
+                    score_change=info["score_change"], shaping=shaping, actions_used=used)
+
+    def state(self):
+        st = self.env.game.state
+        ags = np.zeros((4, 7), np.int64)
+        names = {"North": 0, "East": 1, "South": 2, "West": 3, "Stop": 4}
+        for i in range(4):
+            s = st.getAgentState(i)
+            x, y = s.getPosition()
+            ags[i] = (x, y, names[s.configuration.direction], int(s.isPacman), s.scaredTimer, s.numCarrying, s.numReturned)
+        lay = self.env.layout
+        food = np.zeros(lay.width * lay.height, np.uint8)
+        f = st.data.food
+        for x in range(lay.width):
+            for y in range(lay.height):
+                food[y * lay.width + x] = bool(f[x][y])
+        caps = np.zeros(lay.width * lay.height, np.uint8)
+        for x, y in st.getCapsules():
+            caps[y * lay.width + x] = 1
+        return dict(agents=ags, food=food, caps=caps, score=st.data.score)
+
+
+@pytest.mark.parametrize("name", ["tinyCapture_smart", "capsSmall", "rebind", "odd15", "maze7", "small_noflags"])
+def test_reference_api_single_env_replays_reference_fixture(name):
+    fx = helpers.load_traj(name)
+    helpers.replay(fx, RefApiDriver(fx), where=name)
+
+
+@pytest.mark.parametrize("name", ["bots_tinyCapture", "bots_capsSmall"])
+def test_reference_api_single_env_with_baseline_team(name):
+    """The reference's config-1 shape: one env, red = baselineTeam bots, blue driven through the dict API."""
+    fx = helpers.load_traj(name)
+    helpers.replay(fx, helpers.BotReplayDriver(RefApiDriver(fx, bots=True), fx), where=name)
