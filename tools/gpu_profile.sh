@@ -14,5 +14,5 @@ CMD="python bench.py --steps 6 --warmup 3 --no-extras"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:pm_env_kernelILi0 -s 6 -c 1 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:pm_env_kernelILi0ELi0ELi0E -s 6 -c 1 -f -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
