@@ -224,6 +224,8 @@ class TrainConfig:
     log_every: int = 1
     checkpoint_every: int = 250
     checkpoint_dir: str = "."
+    load_checkpoint: str = ""         # LOAD_CHECKPOINT (`:44, 368-372`): a state_dict saved by this trainer or the reference's
+    start_update: int = 0             # START_UPDATES (`:45`)
 
 
 class Rollout:
@@ -262,6 +264,8 @@ class MAPPOTrainer:
         self.obs_shape = self.env_selfplay.obs_shape
         torch.manual_seed(cfg.seed)                                   # same initial weights on every rank
         self.agent = MAPPOAgent(self.obs_shape, 5, 2).to(self.device)
+        if cfg.load_checkpoint:
+            self.agent.load_state_dict(torch.load(cfg.load_checkpoint, map_location=self.device))
         sharding.broadcast_module_(self.agent)
         self.ema_agent = copy.deepcopy(self.agent)
         self.opponent = copy.deepcopy(self.agent).eval()
@@ -459,8 +463,9 @@ class MAPPOTrainer:
         rec.update(mode=sched["mode"], side="Red " if sched["play_as_red"] else "Blue", seconds=dt, episodes=eps)
         return rec
 
-    def train(self, total_updates: Optional[int] = None, start: int = 0):
+    def train(self, total_updates: Optional[int] = None, start: Optional[int] = None):
         n = self.cfg.total_updates if total_updates is None else total_updates
+        start = self.cfg.start_update if start is None else start
         for update in range(start, n + 1):
             rec = self.train_one(update)
             if self.rank == 0 and update % self.cfg.log_every == 0:
