@@ -36,12 +36,25 @@
 // memory as scratch); the plain variant pays nothing for it.
 // VIEWS = 1: also writes the trainer's learner views (uint8, canonicalised + merged); two more bitset
 // slots hold the mirrored snapshots of red learners.
+#ifdef PM_TRACE
+// dev instrumentation (tools/trace_step.py): [grid][4] = smid, t_start, t_rules_done, t_end (globaltimer ns)
+__device__ unsigned long long *pm_trace_buf;
+__device__ __forceinline__ unsigned long long pm_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToSymbol(pm_trace_buf, &buf, sizeof(buf)); }
+#endif
+
 template <int MODE, int BOTS, int VIEWS>
 __global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const int tid = threadIdx.x;
     const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * PM_E;
+#ifdef PM_TRACE
+    if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) {
+        unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        pm_trace_buf[4 * blockIdx.x + 0] = smid; pm_trace_buf[4 * blockIdx.x + 1] = pm_gtime();
+    }
+#endif
 
     // ---- stage per-batch tables ----
     if (tid < 16) {
@@ -59,12 +72,19 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_ker
         else pm_phaseA_static<MODE, VIEWS>(P, sm, sm, M, tid, n0);
     }
     __syncthreads();
+#ifdef PM_TRACE
+    if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 2] = pm_gtime();
+#endif
     if (MODE == PM_MODE_STEP && P.packed)
         for (int t = tid; t < 3 * PM_E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
     // ---- phase B: observations, one warp per (env, agent) ----
     if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
     // ---- phase B': learner views, one warp per (env, view) ----
     if (VIEWS && P.view_actor != nullptr) pm_phaseB_views<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0, 4 + BOTS);
+#ifdef PM_TRACE
+    __syncthreads();
+    if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 3] = pm_gtime();
+#endif
 }
 
 // ---- state export / import (GameState accessors; tests, checkpoints) ---------
