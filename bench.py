@@ -250,6 +250,24 @@ def other_kernels(torch, device, N, peak):
     return out
 
 
+def mappo_sps(torch, device):
+    """BASELINE's second metric, MAPPO SPS: learner-agent samples per second of rollout + GAE + PPO update on
+    smallCapture (short run: 1 warm-up update + 1 timed; tools/bench_mappo.py is the long form)."""
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    out = {}
+    for name, amp in (("fp32_tf32", False), ("bf16_autocast", True)):
+        cfg = M.TrainConfig(layout_file=layout_path("smallCapture"), num_envs=1024, num_steps=32, amp_bf16=amp,
+                            checkpoint_every=0)
+        tr = M.MAPPOTrainer(cfg, device=device)
+        tr.train_one(0)
+        rec = tr.train_one(1)
+        out[name] = {"samples_per_s": rec["sps"], "seconds_per_update": rec["seconds"]}
+        del tr
+        torch.cuda.empty_cache()
+    out["config"] = "smallCapture, 1024 envs x 32 steps x 2 learners per update, 3 epochs x 8 minibatches, randomTeam opponent, 1 GPU"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -430,6 +448,7 @@ def main():
             torch.cuda.empty_cache()
         # the other kernels of the path, each timed alone (CUDA events, this stream)
         also["kernels"] = other_kernels(torch, device, N, peak)
+        also["mappo"] = mappo_sps(torch, device)
         line["also"] = also
 
     if rank == 0:

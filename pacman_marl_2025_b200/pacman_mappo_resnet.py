@@ -165,7 +165,7 @@ class MAPPOAgent(nn.Module):
         lg = torch.log_softmax(self.logits(obs), dim=-1)
         logp = lg.gather(1, action.unsqueeze(1)).squeeze(1)
         ent = -(lg.exp() * lg).sum(-1)
-        return self.get_value(merged_obs), logp, ent
+        return (self.get_value(merged_obs) if merged_obs is not None else None), logp, ent
 
     @torch.no_grad()
     def get_deterministic_action(self, obs):
@@ -219,6 +219,9 @@ class TrainConfig:
     amp_bf16: bool = False            # networks in bf16 autocast (fp32 master weights); default = reference fp32
     fast_math: bool = True            # cuDNN autotune + TF32 tensor-core matmuls for the fp32 networks
     use_views: bool = True            # learner views written by the step kernel (False: torch flip / merge per step)
+    pair_agents: bool = True          # minibatches are drawn over env-steps and hold BOTH learners of each, so the critic
+                                      # runs once per env-step (the reference shuffles (step, agent) samples and runs it
+                                      # once per sample on the same merged observation, `:563-575`); False = reference order
     easy_until: int = 200             # updates <= this: EASY_TEAMS only (`:396-402`)
     selfplay_after: int = 800         # update index after which self-play opponents enter the mix (`:404-438`)
     log_every: int = 1
@@ -276,6 +279,7 @@ class MAPPOTrainer:
         self.opponent_pool = deque(maxlen=OPPONENT_POOL_SIZE)
         self.opponent_pool.append(copy.deepcopy(self.ema_agent.state_dict()))
         self.rollout = Rollout(cfg.num_steps, cfg.num_envs, self.obs_shape, self.device)
+        self._pair = cfg.pair_agents and (cfg.num_steps * cfg.num_envs) % cfg.num_minibatches == 0
         self.rng = np.random.default_rng(cfg.seed)                    # curriculum draws: identical on every rank
         torch.manual_seed(cfg.seed * 1000003 + self.rank)             # action sampling: different per rank
         self.log: Dict[str, List[float]] = {k: [] for k in (
@@ -415,14 +419,26 @@ class MAPPOTrainer:
         sums = torch.zeros(4, device=self.device)
         steps = 0
         for _ in range(cfg.update_epochs):
-            perm = torch.randperm(S, device=self.device)
+            if self._pair:
+                # shuffle env-steps e = (t, env); sample indices of its two learners: (t, 0, env) and (t, 1, env)
+                pe = torch.randperm(T * N, device=self.device)
+                s0 = torch.div(pe, N, rounding_mode="floor") * (2 * N) + pe % N
+                half = mb // 2
+                perm = torch.stack([s0.view(-1, half), (s0 + N).view(-1, half)], dim=1).reshape(-1)   # [mb] blocks: agent 0 | agent 1
+            else:
+                perm = torch.randperm(S, device=self.device)
             norm_adv_all = mappo_ops.normalize_advantages(b_adv, perm[: mb * cfg.num_minibatches], mb)
             for k in range(cfg.num_minibatches):
                 idx = perm[k * mb:(k + 1) * mb]
                 norm_adv = norm_adv_all[k * mb:(k + 1) * mb]
                 with self._autocast():
-                    midx = torch.div(idx, 2 * N, rounding_mode="floor") * N + idx % N       # (t, env) of sample (t, agent, env)
-                    vals, lps, ent = self.agent.evaluate(b_obs[idx].float(), b_merged[midx].float(), b_act[idx])
+                    if self._pair:
+                        v1 = self.agent.get_value(b_merged[pe[k * half:(k + 1) * half]].float())
+                        _, lps, ent = self.agent.evaluate(b_obs[idx].float(), None, b_act[idx])
+                        vals = torch.cat([v1, v1])
+                    else:
+                        midx = torch.div(idx, 2 * N, rounding_mode="floor") * N + idx % N   # (t, env) of sample (t, agent, env)
+                        vals, lps, ent = self.agent.evaluate(b_obs[idx].float(), b_merged[midx].float(), b_act[idx])
                 vals, lps, ent = vals.float(), lps.float(), ent.float()
                 ratio = (lps - b_logp[idx]).exp()
                 pg = -torch.min(norm_adv * ratio, norm_adv * torch.clamp(ratio, 1 - clip_eps, 1 + clip_eps)).mean()
