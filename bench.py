@@ -227,6 +227,19 @@ def other_kernels(torch, device, N, peak):
         vbytes = (3 * 8 * 140 + 200) * N
         out[name] = {"ms": ms, "agent_steps_per_s": 4.0 * N / (ms * 1e-3), "bytes_per_launch": vbytes,
                      "achieved_GBps": vbytes / (ms * 1e-3) / 1e9}
+    # (1d) BASELINE config 4: per-env distinct mazeGenerator boards (4 096 different 20x20 mazes over the batch; walls,
+    #      starts and the wall plane come from the layout table in HBM instead of shared memory)
+    mz = [Layout(mazeGenerator.generateMaze(5000 + s).split("\n")) for s in range(1024)]
+    envm = gymPacMan_parallel_env(layouts=mz, self_play=True, length=300, num_envs=N, device=device, auto_reset=True)
+    envm.reset_batched()
+
+    def one_m():
+        envm.step_batched(acts[k[0] % 4]); k[0] += 1
+    ms = timed(one_m, 40)
+    out["step_1024_distinct_mazes_20x20"] = {"ms": ms, "agent_steps_per_s": 4.0 * N / (ms * 1e-3),
+                                            "roofline_frac": 12875 * 4.0 * N / (ms * 1e-3) / 1e9 / peak}
+    del envm
+    torch.cuda.empty_cache()
     # (0) BASELINE config 1 through the reference-shaped API: ONE env, dict actions, Python scalars back, red side =
     #     baselineTeam (on-device), blue = uniform over the returned legal-action lists; wall clock incl. resets
     import random

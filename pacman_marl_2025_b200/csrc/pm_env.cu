@@ -28,9 +28,6 @@
 #ifndef PM_MIN_CTAS
 #define PM_MIN_CTAS 8                             // 64 registers/thread: 8 CTAs x 4 warps per SM
 #endif
-#ifndef PM_MIN_CTAS_OBS
-#define PM_MIN_CTAS_OBS PM_MIN_CTAS                // encoder-only launches (pm_observe)
-#endif
 #ifndef PM_E
 #define PM_E 32                                   // envs per CTA (power of two <= PM_THREADS)
 #endif
@@ -46,18 +43,8 @@ __device__ __forceinline__ unsigned long long pm_gtime() { unsigned long long t;
 extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToSymbol(pm_trace_buf, &buf, sizeof(buf)); }
 #endif
 
-// named barriers 1-4: warp 0 arrives, the encoder warps wait (producer / consumer inside the CTA)
-template <int ID> __device__ __forceinline__ void pm_bar_arrive_c() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(PM_THREADS) : "memory"); }
-template <int ID> __device__ __forceinline__ void pm_bar_sync_c() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(PM_THREADS) : "memory"); }
-__device__ __forceinline__ void pm_bar_arrive(int id, int) {
-    if (id == 1) pm_bar_arrive_c<1>(); else if (id == 2) pm_bar_arrive_c<2>(); else if (id == 3) pm_bar_arrive_c<3>(); else pm_bar_arrive_c<4>();
-}
-__device__ __forceinline__ void pm_bar_sync(int id, int) {
-    if (id == 1) pm_bar_sync_c<1>(); else if (id == 2) pm_bar_sync_c<2>(); else if (id == 3) pm_bar_sync_c<3>(); else pm_bar_sync_c<4>();
-}
-
 template <int MODE, int BOTS, int VIEWS>
-__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
+__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const int tid = threadIdx.x;
@@ -77,72 +64,23 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : (MODE == PM_MODE_OBSERV
     for (int i = tid; i < PM_G_NMASKS * P.NCAT; i += PM_THREADS) sm[M.masks + i] = __ldg(P.geom + PM_G_HDR + i);
     if (P.L == 1)
         for (int i = tid; i < P.LS; i += PM_THREADS) sm[M.lay + i] = __ldg(P.layouts + i);
-    if (tid == 0) sm[M.ucount] = 0;
     __syncthreads();
 
-    const int warp = tid >> 5, lane = tid & 31;
-    if (MODE == PM_MODE_STEP && PM_E == 32 && PM_THREADS > 32) {
-        // ---- rules and encoder as a pipeline inside the CTA ----
-        // Warp 0 steps its 32 envs; after EACH of the four ordered sub-moves the snapshot the moving agent is
-        // observed from is final (gymPacMan.py:166), so warp 0 publishes it through a named barrier (ids 1-4)
-        // and the other warps start streaming that agent's 32 observations while warp 0 plays the next agent:
-        // the first store of the launch leaves after one sub-move instead of after the whole step.  Observations
-        // are handed out dynamically (shared counter, agent-major), warp 0 joins once its rules are done.
-        if (warp == 0) {
-            PmStepCtx c;
-            const bool valid = pm_stepA_begin<BOTS, VIEWS>(P, sm, sm, M, lane, n0, c);
-            if (valid) pm_stepA_turn<0, BOTS, VIEWS>(P, sm, M, lane, c);
-            __syncwarp(); __threadfence_block(); pm_bar_arrive(1, PM_THREADS);
-            if (valid) pm_stepA_turn<1, BOTS, VIEWS>(P, sm, M, lane, c);
-            __syncwarp(); __threadfence_block(); pm_bar_arrive(2, PM_THREADS);
-            if (valid) pm_stepA_turn<2, BOTS, VIEWS>(P, sm, M, lane, c);
-            __syncwarp(); __threadfence_block(); pm_bar_arrive(3, PM_THREADS);
-            if (valid) pm_stepA_turn<3, BOTS, VIEWS>(P, sm, M, lane, c);
-            __syncwarp(); __threadfence_block(); pm_bar_arrive(4, PM_THREADS);
-            const bool restarted = valid && pm_stepA_end<BOTS, VIEWS>(P, sm, M, lane, c);
-            sm[M.redo + lane] = restarted ? 1u : 0u;
-#ifdef PM_TRACE
-            if (tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 2] = pm_gtime();
-#endif
-        }
-        int passed = warp == 0 ? 4 : 0;                 // barriers this warp has been through (warp 0 produced the data)
-        if (P.obs != nullptr) {
-            for (;;) {
-                int u = 0;
-                if (lane == 0) u = (int)atomicAdd(&sm[M.ucount], 1u);
-                u = __shfl_sync(0xffffffffu, u, 0);
-                if (u >= 4 * PM_E) break;
-                const int k = u >> 5;                   // agent of this observation
-                while (passed <= k) { ++passed; pm_bar_sync(passed, PM_THREADS); }
-                pm_encode_unit<MODE>(P, sm, sm, M, u, lane, n0);
-            }
-        }
-        while (passed < 4) { ++passed; pm_bar_sync(passed, PM_THREADS); }   // every consumer warp passes every barrier once
-        __syncthreads();
-        // an env that finished and was restarted in place (auto_reset) shows the NEW episode in all four
-        // observations: encode them again from the rewritten snapshots (about one env in `length` per step)
-        if (P.obs != nullptr && P.auto_reset)
-            for (int u = warp; u < 4 * PM_E; u += PM_THREADS / 32)
-                if (sm[M.redo + (u & (PM_E - 1))]) pm_encode_unit<MODE>(P, sm, sm, M, u, lane, n0);
-        if (P.packed)
-            for (int t = tid; t < 3 * PM_E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
-    } else {
-        // ---- phase A: rules, one thread per env ----
-        if (tid < PM_E) {
-            if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS, VIEWS>(P, sm, sm, M, tid, n0);
-            else pm_phaseA_static<MODE, VIEWS>(P, sm, sm, M, tid, n0);
-        }
-        __syncthreads();
-#ifdef PM_TRACE
-        if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 2] = pm_gtime();
-#endif
-        if (MODE == PM_MODE_STEP && P.packed)
-            for (int t = tid; t < 3 * PM_E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
-        // ---- phase B: observations, one warp per (env, agent) ----
-        if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, warp, PM_THREADS / 32, lane, n0);
+    // ---- phase A: rules, one thread per env ----
+    if (tid < PM_E) {
+        if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS, VIEWS>(P, sm, sm, M, tid, n0);
+        else pm_phaseA_static<MODE, VIEWS>(P, sm, sm, M, tid, n0);
     }
+    __syncthreads();
+#ifdef PM_TRACE
+    if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 2] = pm_gtime();
+#endif
+    if (MODE == PM_MODE_STEP && P.packed)
+        for (int t = tid; t < 3 * PM_E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
+    // ---- phase B: observations, one warp per (env, agent) ----
+    if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
     // ---- phase B': learner views, one warp per (env, view) ----
-    if (VIEWS && P.view_actor != nullptr) pm_phaseB_views<MODE>(P, sm, sm, M, warp, PM_THREADS / 32, lane, n0, 4 + BOTS);
+    if (VIEWS && P.view_actor != nullptr) pm_phaseB_views<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0, 4 + BOTS);
 #ifdef PM_TRACE
     __syncthreads();
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 3] = pm_gtime();

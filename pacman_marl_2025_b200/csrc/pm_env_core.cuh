@@ -113,7 +113,7 @@ struct PmParams {
 //   posA/posB/patch[k] : the four agent bit positions and the own-cell patch
 //   rec               : the CTA's pm_host_record block (E x 48 bytes), 16-byte aligned
 struct PmSmem {
-    int lut, masks, lay, blk0, blk_words, lid, redo, ucount, posA, posB, patch, rec, food, caps, total;
+    int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, total;
     int E1;                             // padded env stride
 };
 PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots = 4) {
@@ -129,8 +129,6 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     m.blk0 = o;
     // per-block buffer
     m.lid = o; o += E;
-    m.redo = o; o += E;                 // env restarted inside the step: its observations are encoded again
-    m.ucount = o; o += 4;               // next observation to encode (dynamic assignment to warps)
     m.posA = o; o += 4 * m.E1;
     m.posB = o; o += 4 * m.E1;
     m.patch = o; o += 4 * m.E1;
@@ -556,21 +554,10 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
     S.snap[A] = (uint32_t)g.x[A] | (uint32_t)g.y[A] << 8 | (uint32_t)g.carry[A] << 16;
 }
 
-// The step of one env as three pieces, so that the kernel can publish each agent's snapshot to the encoder
-// warps as soon as that agent has moved (pm_env.cu) while the emulation and the simple path just chain them.
-struct PmStepCtx {
-    int64_t n; uint32_t lid;
-    const uint32_t *lay, *tail;
-    uint32_t *food, *caps;
-    PmCtx X; PmAgents g; PmStepAcc S;
-    uint32_t act4, episode; int steps;
-};
-
-// load the env; false = no env in this slot
 template <int BOTS, int VIEWS>
-PM_HD bool pm_stepA_begin(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0, PmStepCtx &c) {
+PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
-    if (n >= P.n_end) { sm[M.lid + el] = 0xffffffffu; return false; }
+    if (n >= P.n_end) { sm[M.lid + el] = 0xffffffffu; return; }
     const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
     sm[M.lid + el] = lid;
     const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
@@ -578,7 +565,7 @@ PM_HD bool pm_stepA_begin(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     const uint32_t *tail = lay + pm_l_tail(P.HW);
     const int W = P.W, NW = P.NW, E1 = M.E1;
     const int64_t NP = pm_np(P.N);
-    PmCtx &X = c.X;
+    PmCtx X;
     X.W = W; X.H = P.H; X.NW = NW; X.E1 = E1; X.ND = P.ND; X.HW = P.HW;
     X.walls = walls; X.dumptab = P.geom + pm_g_dump_off(P.HW); X.teams = tail[PM_L_TEAMS];
 
@@ -594,11 +581,11 @@ PM_HD bool pm_stepA_begin(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     for (int w = 0; w < NW; ++w) food[w * E1] = gfood[(size_t)w * NP + n];
     if (caps) for (int w = 0; w < NW; ++w) caps[w * E1] = gcaps[(size_t)w * NP + n];
 
-    PmAgents &g = c.g;
+    PmAgents g;
     pm_unpack_agents(g, A, B, tail);
-    c.steps = (int)Mi.y;
-    c.episode = Mi.w;                                      // restarts of this env (keys the random draws)
-    PmStepAcc &S = c.S;
+    int steps = (int)Mi.y;
+    uint32_t episode = Mi.w;                                      // restarts of this env (keys the random draws)
+    PmStepAcc S;
     S.score = (int)Mi.x;
     S.b.rf = (int)(Mi.z & 0xffff); S.b.bf = (int)(Mi.z >> 16);
     S.b.food_dirty = false; S.b.caps_dirty = false;
@@ -614,32 +601,11 @@ PM_HD bool pm_stepA_begin(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         for (int i = 0; i < 4; ++i) { long long v = a8[i]; act4 |= (uint32_t)((v < 0 || v > 4) ? 255 : (int)v) << (8 * i); }
     }
 
-    c.n = n; c.lid = lid; c.lay = lay; c.tail = tail; c.food = food; c.caps = caps; c.act4 = act4;
-    return true;
-}
+    pm_agent_turn<0, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<1, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<2, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    pm_agent_turn<3, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
 
-template <int A, int BOTS, int VIEWS>
-PM_HD void pm_stepA_turn(const PmParams &P, uint32_t *sm, const PmSmem &M, int el, PmStepCtx &c) {
-    pm_agent_turn<A, BOTS, VIEWS>(P, c.X, sm, M, el, c.n, c.lid, c.g, c.food, c.caps, c.S, c.act4, c.steps, c.episode);
-}
-
-// epilogue, outputs, state write-back; true = the env was restarted in place (auto_reset), i.e. ALL FOUR snapshots
-// now show the new episode
-template <int BOTS, int VIEWS>
-PM_HD bool pm_stepA_end(const PmParams &P, uint32_t *sm, const PmSmem &M, int el, PmStepCtx &c) {
-    const int64_t n = c.n;
-    const uint32_t *lay = c.lay, *tail = c.tail;
-    const uint32_t *walls = c.X.walls;
-    const int W = P.W, NW = P.NW, E1 = M.E1;
-    const int64_t NP = pm_np(P.N);
-    PmAgents &g = c.g;
-    PmStepAcc &S = c.S;
-    uint32_t *food = c.food, *caps = c.caps;
-    uint32_t *gfood = reinterpret_cast<uint32_t *>(P.state + pm_st_food(P.N));
-    uint32_t *gcaps = reinterpret_cast<uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
-    int steps = c.steps;
-    uint32_t episode = c.episode;
-    bool restarted = false;
     int score = S.score, rf = S.b.rf, bf = S.b.bf;
     const int sc_total = S.sc_total;
     double red_r = S.red_r, blue_r = S.blue_r;
@@ -666,7 +632,6 @@ PM_HD bool pm_stepA_end(const PmParams &P, uint32_t *sm, const PmSmem &M, int el
     // belong to the terminal step; state, the four observations and the legal masks below are
     // CaptureRules.newGame's (capture.py:369-382, game.py:490-508). ----
     if (term && P.auto_reset) {
-        restarted = true;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t s0 = tail[PM_L_START + i];
@@ -726,7 +691,6 @@ PM_HD bool pm_stepA_end(const PmParams &P, uint32_t *sm, const PmSmem &M, int el
         rec[0] = r0; rec[1] = r1; rec[2] = r2;
     }
     // ---- state write-back ----
-    pm_u4 A, B, Sn, Mi;
     pm_pack_agents(g, A, B);
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
@@ -736,18 +700,6 @@ PM_HD bool pm_stepA_end(const PmParams &P, uint32_t *sm, const PmSmem &M, int el
     reinterpret_cast<pm_u4 *>(P.state + pm_st_misc(P.N))[n] = Mi;
     if (food_dirty) for (int w = 0; w < NW; ++w) gfood[(size_t)w * NP + n] = food[(3 * NW + w) * E1];
     if (caps_dirty) for (int w = 0; w < NW; ++w) gcaps[(size_t)w * NP + n] = caps[(3 * NW + w) * E1];
-    return restarted;
-}
-
-template <int BOTS, int VIEWS>
-PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
-    PmStepCtx c;
-    if (!pm_stepA_begin<BOTS, VIEWS>(P, st, sm, M, el, n0, c)) { sm[M.redo + el] = 0; return; }
-    pm_stepA_turn<0, BOTS, VIEWS>(P, sm, M, el, c);
-    pm_stepA_turn<1, BOTS, VIEWS>(P, sm, M, el, c);
-    pm_stepA_turn<2, BOTS, VIEWS>(P, sm, M, el, c);
-    pm_stepA_turn<3, BOTS, VIEWS>(P, sm, M, el, c);
-    sm[M.redo + el] = pm_stepA_end<BOTS, VIEWS>(P, sm, M, el, c) ? 1u : 0u;
 }
 
 // ============================================================================
@@ -958,18 +910,17 @@ PM_HD pm_f4 pm_expand4(const pm_f4 *lut, uint32_t nib) {
 // into a float4 by a 16-entry shared-memory table.  A warp store covers 512
 // contiguous bytes.  The own-cell value 1+numCarrying (gymPacMan.py:205) is
 // patched by one lane after the warp's stores (ordered by __syncwarp).
-// Encode observation `u` of the CTA (agent u >> lgE of env u & (E-1)); the whole warp calls it.
 template <int MODE>
-PM_HD void pm_encode_unit(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int u, int lane, int64_t n0) {
+PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps, int lane, int64_t n0) {
     const int NCAT = P.NCAT, E = P.E;
     const int nf4 = 2 * P.HW;                          // float4s per observation (8*HW/4)
     (void)nf4;
     const pm_f4 *lut = reinterpret_cast<const pm_f4 *>(st + M.lut);
     const int ngroups = (NCAT + 31) >> 5;
-    {
+    for (int u = warp; u < 4 * E; u += nwarps) {
         const int k = u >> P.lgE, el = u & (E - 1);
         PmUnit U;
-        if (!pm_unit_load<MODE>(P, sm, M, k, el, U)) return;
+        if (!pm_unit_load<MODE>(P, sm, M, k, el, U)) continue;
         float *dstf = P.obs + (size_t)k * P.obs_agent_stride + (size_t)(n0 + el) * 8 * P.HW;
         pm_f4 *dst = reinterpret_cast<pm_f4 *>(dstf);
         (void)dst;
@@ -1014,7 +965,7 @@ PM_HD void pm_encode_unit(const PmParams &P, const uint32_t *st, const uint32_t 
             if (lane == 0) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
         }
 #else
-        if (lane != 0) return;                          // host emulation: lane 0 plays the whole warp
+        if (lane != 0) continue;                        // host emulation: lane 0 plays the whole warp
         for (int g = 0; g < ngroups; ++g) {
             uint32_t words[32];
             for (int L = 0; L < 32; ++L) { const int j = 32 * g + L; words[L] = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u; }
@@ -1027,11 +978,6 @@ PM_HD void pm_encode_unit(const PmParams &P, const uint32_t *st, const uint32_t 
         if (U.patch != 0xffffffffu) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
 #endif
     }
-}
-
-template <int MODE>
-PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps, int lane, int64_t n0) {
-    for (int u = warp; u < 4 * P.E; u += nwarps) pm_encode_unit<MODE>(P, st, sm, M, u, lane, n0);
 }
 
 // ============================================================================

@@ -226,7 +226,7 @@ class gymPacMan_parallel_env:
                  reward_forLegalAction=True, defenceReward=True, random_layout=False, enemieName="randomTeam",
                  self_play=False, *, num_envs: int = 1, device=None, layouts: Optional[Sequence] = None,
                  shaping_scale: float = 0.1, opponent_seed: int = 0, auto_reset: bool = False,
-                 env_index_base: int = 0, opponent_tiebreak: str = "random"):
+                 env_index_base: int = 0, opponent_tiebreak: str = "random", layout_ids=None):
         if display:
             raise NotImplementedError("display=True (tkinter viewer) is outside the batched GPU path")
         if not torch.cuda.is_available():
@@ -267,6 +267,8 @@ class gymPacMan_parallel_env:
         # this batch is one shard of a larger one (keys the on-device opponent's random draws)
         self.auto_reset = bool(auto_reset)
         self.env_index_base = int(env_index_base)
+        # with several `layouts`: env n plays layouts[layout_ids[n]] (default: n % len(layouts))
+        self._layout_ids_arg = layout_ids
 
         if layouts is not None:
             lays = [l if isinstance(l, _layout.Layout) else _layout.Layout(list(l)) for l in layouts]
@@ -299,6 +301,15 @@ class gymPacMan_parallel_env:
                                     int(bool(self.defenceReward)), 0,
                                     self.shaping_scale, int(self._opponent_seed), int(self.auto_reset), 0,
                                     self.env_index_base, 0, 0)
+        if self._layout_ids_arg is not None and len(lays) > 1:
+            ids = torch.as_tensor(np.asarray(self._layout_ids_arg), dtype=torch.int32)
+            if ids.numel() != N or int(ids.min()) < 0 or int(ids.max()) >= len(lays):
+                raise ValueError("layout_ids must hold one index into `layouts` per env")
+            self._layout_id = ids.to(dev).contiguous()
+            self._layout_id_host = ids.numpy().copy()
+            self._desc.layout_id = self._layout_id.data_ptr()
+        else:
+            self._layout_id_host = None
         self._set_opponent(self.enemieName)
         self.obs_shape = (8, H, W)
         self._obs = torch.empty((4, N, 8, H, W), dtype=torch.float32, device=dev)
@@ -334,6 +345,8 @@ class gymPacMan_parallel_env:
             d.dist, d.node_of_cell, d.dist_nmax = t.dist.data_ptr(), t.node_of_cell.data_ptr(), int(t.dist.shape[1])
 
     def _layout_of(self, n):
+        if getattr(self, "_layout_id_host", None) is not None:
+            return self._layouts[int(self._layout_id_host[n])]
         return self._layouts[n % len(self._layouts)]
 
     def _stream(self):

@@ -33,7 +33,8 @@ def _p(a):
 class EmuEnv:
     def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True,
                  shaping_scale=0.1, E=64, KB=4, layout_id=None, random_agent_mask=0, random_seed=0,
-                 auto_reset=False, env_index_base=0, bot_kind=None, bot_first_best=True):
+                 auto_reset=False, env_index_base=0, bot_kind=None, bot_first_best=True, layout_ids=None):
+        layout_id = layout_ids if layout_ids is not None else layout_id
         L = lib()
         per_env = not isinstance(layouts[0], str)
         lays = layouts if per_env else [layouts]

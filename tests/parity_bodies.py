@@ -318,3 +318,26 @@ def body_learner_views(make_env, rows, N=48, T=120, length=90, **kw):
             np.testing.assert_array_equal(o["view_critic"], wc, err_msg=f"t={t} critic view red={red}")
             carried += int((wc[:, 1] > 1).sum())
     assert carried > 0                # own-cell values above 1 (carrying) were exercised
+
+
+def body_layout_ids(make_env, N=40, T=90):
+    """A table of L boards with an explicit per-env index (pm_env_desc.layout_id): env n plays layouts[ids[n]]."""
+    from pacman_marl_2025_b200 import mazeGenerator
+    L = 5
+    mazes = [mazeGenerator.generateMaze(2000 + s).split("\n") for s in range(L)]
+    ids = np.random.default_rng(1).integers(0, L, size=N)
+    env = make_env(mazes, N, length=60, auto_reset=True, layout_ids=ids)
+    ref = oracle.OracleBatch([mazes[i] for i in ids], N, length=60)
+    obs, legal = env.reset()
+    robs, rlegal = ref.reset()
+    np.testing.assert_array_equal(legal, rlegal)
+    np.testing.assert_array_equal(obs.transpose(1, 0, 2, 3, 4), robs)
+    rng = np.random.default_rng(12)
+    for t in range(T):
+        a = biased_actions(rng, N, 0.6, t)
+        o = env.step(a)
+        r = ref.step(a, with_obs=True, nthreads=0, auto_reset=True)
+        keep = ~r["done"].astype(bool)
+        np.testing.assert_array_equal(o["reward"].view(np.uint64), r["reward"].T.copy().view(np.uint64), err_msg=f"t={t}")
+        np.testing.assert_array_equal(o["done"], r["done"])
+        np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4)[keep], r["obs"][keep], err_msg=f"t={t} obs")

@@ -104,6 +104,11 @@ def test_max_size_board_and_oversize_refusal():
         CudaEnv(big_board(33, 32), 4)
 
 
+def test_explicit_layout_ids():
+    from parity_bodies import body_layout_ids
+    body_layout_ids(CudaEnv, N=300, T=120)
+
+
 def test_int64_actions_and_out_of_range():
     body_int64_out_of_range(CudaEnv)
 

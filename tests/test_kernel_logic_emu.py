@@ -112,3 +112,8 @@ def test_emulated_learner_views_with_baseline_bots():
     from parity_bodies import body_learner_views
     body_learner_views(lambda r, n, **kw: EmuEnv(r, n, E=4, KB=1, **kw), lay_rows("smallCapture"), N=12, T=80,
                        bot_kind=[2, 0, 3, 0])
+
+
+def test_emulated_explicit_layout_ids():
+    from parity_bodies import body_layout_ids
+    body_layout_ids(lambda lays, n, **kw: EmuEnv(lays, n, E=8, KB=1, **kw), N=20, T=70)

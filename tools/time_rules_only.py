@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from pacman_marl_2025_b200 import _lib
 from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
 lay = sys.argv[1] if len(sys.argv) > 1 else "tinyCapture"
-N = 65536
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
 env = gymPacMan_parallel_env(layout_file=os.path.join(os.path.dirname(_lib.LIB_PATH), "layouts", lay + ".lay"),
                              self_play=True, length=300, num_envs=N)
 acts = torch.randint(0, 5, (8, N, 4), dtype=torch.uint8).cuda()
@@ -20,4 +20,4 @@ for name, out in (("with obs", so), ("rules only", noobs)):
     for i in range(50):
         L.pm_step(C.byref(env._desc), acts[i % 8].data_ptr(), 1, C.byref(out), st)
     e1.record(); torch.cuda.synchronize()
-    print(lay, name, "%.1f us/launch" % (e0.elapsed_time(e1) * 1000 / 50))
+    print(lay, N, name, "%.1f us/launch" % (e0.elapsed_time(e1) * 1000 / 50))
