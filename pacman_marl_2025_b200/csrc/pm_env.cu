@@ -28,6 +28,9 @@
 #ifndef PM_MIN_CTAS
 #define PM_MIN_CTAS 8                             // 64 registers/thread: 8 CTAs x 4 warps per SM
 #endif
+#ifndef PM_MIN_CTAS_OBS
+#define PM_MIN_CTAS_OBS PM_MIN_CTAS                // encoder-only launches (pm_observe); tools/gpu_sweep_obs.sh
+#endif
 #ifndef PM_E
 #define PM_E 32                                   // envs per CTA (power of two <= PM_THREADS)
 #endif
@@ -44,7 +47,7 @@ extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToS
 #endif
 
 template <int MODE, int BOTS, int VIEWS>
-__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : PM_MIN_CTAS) pm_env_kernel(const PmParams P) {
+__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const int tid = threadIdx.x;
