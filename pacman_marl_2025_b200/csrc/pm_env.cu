@@ -30,6 +30,9 @@
 #ifndef PM_MIN_CTAS
 #define PM_MIN_CTAS 8                             // 64 registers/thread: 8 CTAs x 4 warps per SM
 #endif
+#ifndef PM_MIN_CTAS_BOTS
+#define PM_MIN_CTAS_BOTS 8                         // step with the baselineTeam look-ahead (B200 sweep: 4 -> 448 us, 6 -> 400, 8 -> 350 on tiny)
+#endif
 #ifndef PM_MIN_CTAS_OBS
 #define PM_MIN_CTAS_OBS PM_MIN_CTAS                // encoder-only launches (pm_observe); tools/gpu_sweep_obs.sh
 #endif
@@ -49,7 +52,7 @@ extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToS
 #endif
 
 template <int MODE, int BOTS, int VIEWS>
-__global__ void __launch_bounds__(PM_THREADS, BOTS ? 4 : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
+__global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const int tid = threadIdx.x;

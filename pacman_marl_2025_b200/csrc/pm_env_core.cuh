@@ -402,6 +402,7 @@ PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2,
         if (n > 0) {
             int best = 0x7fffffff;
             const int half = W >> 1;
+            const uint16_t *row = D.dist + (size_t)D.node_of[me] * D.nmax;     // distances from my cell
             for (int w = 0; w < X.NW; ++w) {
                 uint32_t bits = fs[w * X.E1];
                 while (bits) {
@@ -413,7 +414,7 @@ PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2,
                     bits &= bits - 1;
                     const int c = 32 * w + bpos, x = c % W;
                     if ((x >= half) != (is_red != 0)) continue;            // red eats x >= W//2, blue eats x < W//2
-                    const int d = pm_maze_dist(D, me, c);
+                    const int d = (int)row[D.node_of[c]];
                     best = d < best ? d : best;
                 }
             }
