@@ -198,7 +198,7 @@ extern "C" int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, i
                         pm_stream_t stream) {
     PmParams P;
     if (int rc = fill_params(d, P)) return rc;
-    if (obs && (obs_agent_stride & 3)) return PM_EINVAL;
+    if (obs && ((obs_agent_stride & 3) || ((size_t)obs & 15))) return PM_EINVAL;      // 128-bit stores
     P.mask = mask; P.obs = obs; P.obs_agent_stride = obs_agent_stride; P.legal = legal;
     return launch_env<PM_MODE_RESET, 0, 0>(P, (cudaStream_t)stream);
 }
@@ -206,7 +206,7 @@ extern "C" int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, i
 extern "C" int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream) {
     PmParams P;
     if (int rc = fill_params(d, P)) return rc;
-    if (!obs || (obs_agent_stride & 3)) return PM_EINVAL;
+    if (!obs || (obs_agent_stride & 3) || ((size_t)obs & 15)) return PM_EINVAL;
     P.obs = obs; P.obs_agent_stride = obs_agent_stride;
     return launch_env<PM_MODE_OBSERVE, 0, 0>(P, (cudaStream_t)stream);
 }
@@ -225,7 +225,7 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     PmParams P;
     if (int rc = fill_params(d, P)) return rc;
     if (!actions || !out || (action_itemsize != 1 && action_itemsize != 8)) return PM_EINVAL;
-    if (out->obs && (out->obs_agent_stride & 3)) return PM_EINVAL;
+    if (out->obs && ((out->obs_agent_stride & 3) || ((size_t)out->obs & 15))) return PM_EINVAL;
     P.actions = actions; P.act_size = action_itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
@@ -304,6 +304,8 @@ extern "C" int pm_step_host_pipelined(const pm_env_desc *d, pm_pipe *p, const ui
                                       const pm_step_out *od, pm_host_record *records_host, pm_stream_t stream) {
     if (!d || !p || !actions_host || !actions_dev || !od || !od->packed || !records_host) return PM_EINVAL;
     if (d->env_begin != 0 || d->env_count != 0) return PM_EINVAL;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != p->device) return PM_EINVAL;      // a pipe belongs to one device
     cudaStream_t caller = (cudaStream_t)stream;
     const int64_t N = d->n_envs;
     const int C = p->n_chunks;

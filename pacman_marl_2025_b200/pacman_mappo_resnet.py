@@ -274,7 +274,7 @@ class MAPPOTrainer:
         self.opponent = copy.deepcopy(self.agent).eval()
         self._params = list(self.agent.parameters())
         self._ema_params = list(self.ema_agent.parameters())
-        self.optimizer = torch.optim.Adam(self.agent.parameters(), lr=LR_START, eps=1e-5)
+        self.optimizer = torch.optim.Adam(self.agent.parameters(), lr=LR_START, eps=1e-5, fused=cfg.fast_math)   # `:366`; one fused multi-tensor kernel per step
         self.bucket = sharding.FlatGradBucket(self.agent.parameters())
         self.opponent_pool = deque(maxlen=OPPONENT_POOL_SIZE)
         self.opponent_pool.append(copy.deepcopy(self.ema_agent.state_dict()))
