@@ -103,6 +103,13 @@ struct PmParams {
     const uint8_t *mask;                // reset only
 };
 
+#ifndef PM_TMA_STORE
+#define PM_TMA_STORE 0                  // 1: the encoder stages 4 KB of fp32 in shared memory and lets the TMA engine
+#endif                                  //    (cp.async.bulk shared -> global) write it instead of issuing STG.128 itself
+#ifndef PM_TMA_WARPS
+#define PM_TMA_WARPS 4
+#endif
+
 // ---- shared-memory map (u32 word offsets) ----------------------------------
 // Per-env arrays are [..][E1] with E1 odd, so both the per-env phase (consecutive
 // threads = consecutive envs) and the per-observation phase (consecutive lanes =
@@ -113,7 +120,7 @@ struct PmParams {
 //   posA/posB/patch[k] : the four agent bit positions and the own-cell patch
 //   rec               : the CTA's pm_host_record block (E x 48 bytes), 16-byte aligned
 struct PmSmem {
-    int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, total;
+    int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, stage, total;
     int E1;                             // padded env stride
 };
 PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots = 4) {
@@ -138,6 +145,11 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     m.caps = o; o += has_caps ? nslots * NW * m.E1 : 0;
     o = (o + 3) & ~3;
     m.blk_words = o - m.blk0;
+    m.stage = 0;
+#if PM_TMA_STORE
+    o = (o + 31) & ~31;                 // 128-byte aligned: one 4 KB fp32 staging buffer per warp for the bulk stores
+    m.stage = o; o += PM_TMA_WARPS * 1024;
+#endif
     m.total = o;
     return m;
 }
@@ -947,8 +959,41 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
                 }
             }
         }
+        if (U.patch != 0xffffffffu) {
+            __syncwarp();
+            if (lane == 0) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
+        }
 #else
         const int sh = (lane & 7) * 4, src = lane >> 3;
+#if PM_TMA_STORE
+        // stage one group (32 words = 1024 floats = 4 KB) in this warp's shared-memory buffer, patch the own-cell
+        // value there, and hand the buffer to the TMA engine: the LSU only sees shared-memory stores
+        pm_f4 *buf = reinterpret_cast<pm_f4 *>(const_cast<uint32_t *>(sm) + M.stage + warp * 1024);
+        const uint32_t buf_s = (uint32_t)__cvta_generic_to_shared(buf);
+        const int pf = (U.patch != 0xffffffffu) ? (int)(U.patch & 0xffff) : -1;
+        for (int g = 0; g < ngroups; ++g) {
+            const int j = 32 * g + lane;
+            const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // buffer free again?
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const uint32_t w = __shfl_sync(0xffffffffu, word, 4 * r + src);
+                buf[32 * r + lane] = pm_expand4(lut, (w >> sh) & 15u);
+            }
+            __syncwarp();
+            if (lane == 0 && (pf >> 10) == g) reinterpret_cast<float *>(buf)[pf & 1023] = (float)(U.patch >> 16);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const int left = nf4 - 256 * g;
+                const uint32_t bytes = (uint32_t)(left >= 256 ? 256 : left) * 16u;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + 256 * g), "r"(buf_s), "r"(bytes)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+#else
         for (int g = 0; g < ngroups; ++g) {
             const int j = 32 * g + lane;
             const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
@@ -960,11 +1005,12 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
                 if (f < nf4) dst[f] = pm_expand4(lut, (w >> sh) & 15u);
             }
         }
-#endif
         if (U.patch != 0xffffffffu) {
             __syncwarp();
             if (lane == 0) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
         }
+#endif
+#endif
 #else
         if (lane != 0) continue;                        // host emulation: lane 0 plays the whole warp
         for (int g = 0; g < ngroups; ++g) {
@@ -979,6 +1025,9 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
         if (U.patch != 0xffffffffu) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);
 #endif
     }
+#if PM_TMA_STORE && defined(__CUDA_ARCH__)
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all bulk stores of this warp have landed
+#endif
 }
 
 // ============================================================================
