@@ -39,6 +39,9 @@
 #ifndef PM_E
 #define PM_E 32                                   // envs per CTA (power of two <= PM_THREADS)
 #endif
+#ifndef PM_E_SMALL
+#define PM_E_SMALL 8                              // envs per CTA for batches too small to give every SM work at PM_E
+#endif
 
 // BOTS = 1: the variant with the baselineTeam look-ahead compiled in (one more bitset slot of shared
 // memory as scratch); the plain variant pays nothing for it.
@@ -51,12 +54,14 @@ __device__ __forceinline__ unsigned long long pm_gtime() { unsigned long long t;
 extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToSymbol(pm_trace_buf, &buf, sizeof(buf)); }
 #endif
 
-template <int MODE, int BOTS, int VIEWS>
+// E = envs per CTA: PM_E (32) for big batches; PM_E_SMALL (8) when the batch would otherwise leave most SMs
+// without a CTA (a trainer-sized batch of 1 024 envs is 32 CTAs of 32 envs but 128 CTAs of 8).
+template <int MODE, int BOTS, int VIEWS, int E>
 __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
-    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const int tid = threadIdx.x;
-    const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * PM_E;
+    const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * E;
 #ifdef PM_TRACE
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) {
         unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
     __syncthreads();
 
     // ---- phase A: rules, one thread per env ----
-    if (tid < PM_E) {
+    if (tid < E) {
         if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS, VIEWS>(P, sm, sm, M, tid, n0);
         else pm_phaseA_static<MODE, VIEWS>(P, sm, sm, M, tid, n0);
     }
@@ -84,7 +89,7 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 2] = pm_gtime();
 #endif
     if (MODE == PM_MODE_STEP && P.packed)
-        for (int t = tid; t < 3 * PM_E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
+        for (int t = tid; t < 3 * E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
     // ---- phase B: observations, one warp per (env, agent) ----
     if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
     // ---- phase B': learner views, one warp per (env, view) ----
@@ -161,25 +166,48 @@ __global__ void pm_set_state_kernel(const PmParams P, const int32_t *agents, con
 // ---------------------------------------------------------------------------
 static int fill_params(const pm_env_desc *d, PmParams &P) { return pm_fill_params(d, P, PM_E); }
 
-template <int MODE, int BOTS, int VIEWS>
-static int launch_env(const PmParams &P, cudaStream_t st) {
-    const PmSmem M = pm_smem_map(P.HW, P.LS, PM_E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
+static void set_envs_per_cta(PmParams &P, int E) {
+    P.E = E; P.lgE = 0;
+    while ((1 << P.lgE) < E) ++P.lgE;
+}
+
+template <int MODE, int BOTS, int VIEWS, int E>
+static int launch_env_e(const PmParams &P0, cudaStream_t st) {
+    PmParams P = P0;
+    set_envs_per_cta(P, E);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const size_t smem = (size_t)M.total * 4;
-    static size_t configured[64][3][2][2];             // per device, per kernel instance
+    static size_t configured[64];                      // per device (this function is one kernel instance)
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
-    if (smem > configured[dev & 63][MODE][BOTS][VIEWS]) {
-        cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         // the kernel streams its output and keeps its working set in shared memory: prefer smem over L1
-        e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS, E>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        configured[dev & 63][MODE][BOTS][VIEWS] = smem;
+        configured[dev & 63] = smem;
     }
-    const unsigned grid = (unsigned)((P.n_end - P.n_begin + PM_E - 1) / PM_E);
-    pm_env_kernel<MODE, BOTS, VIEWS><<<grid, PM_THREADS, smem, st>>>(P);
+    const unsigned grid = (unsigned)((P.n_end - P.n_begin + E - 1) / E);
+    pm_env_kernel<MODE, BOTS, VIEWS, E><<<grid, PM_THREADS, smem, st>>>(P);
     return (int)cudaGetLastError();
+}
+
+template <int MODE, int BOTS, int VIEWS>
+static int launch_env(const PmParams &P, cudaStream_t st) {
+    // fewer than ~2 CTAs of PM_E envs per SM: use small CTAs so that the whole GPU takes part
+    static int sm_count[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
+    if (!sm_count[dev & 63]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sm_count[dev & 63] = v;
+    }
+    int small = (P.n_end - P.n_begin) < (int64_t)2 * PM_E * sm_count[dev & 63];
+    if (const char *e = getenv("PM_ENVS_PER_CTA")) small = atoi(e) == PM_E_SMALL;      // tests / sweeps
+    return small ? launch_env_e<MODE, BOTS, VIEWS, PM_E_SMALL>(P, st) : launch_env_e<MODE, BOTS, VIEWS, PM_E>(P, st);
 }
 
 static int set_views(PmParams &P, uint8_t *actor, int64_t stride, uint8_t *critic, int red) {

@@ -607,3 +607,28 @@ def test_reference_api_single_env_with_baseline_team(name):
     """The reference's config-1 shape: one env, red = baselineTeam bots, blue driven through the dict API."""
     fx = helpers.load_traj(name)
     helpers.replay(fx, helpers.BotReplayDriver(RefApiDriver(fx, bots=True), fx), where=name)
+
+
+def test_envs_per_cta_choice_does_not_change_results(monkeypatch):
+    """Launch geometry only: small batches run 8 envs per CTA, large ones 32 (pm_env.cu); forcing either through
+    PM_ENVS_PER_CTA must give identical outputs, states and learner views."""
+    rows = lay_rows("smallCapture")
+    N = 1000
+    res = {}
+    for epc in ("8", "32"):
+        monkeypatch.setenv("PM_ENVS_PER_CTA", epc)
+        env = CudaEnv(rows, N, length=35, auto_reset=True, bot_kind=[2, 0, 3, 0])
+        env.reset()
+        env.set_views(True)
+        rng = np.random.default_rng(8)
+        outs = []
+        for t in range(45):
+            o = env.step(biased_actions(rng, N, 0.6, t))
+            outs.append({k: o[k].copy() for k in ("obs", "reward", "done", "legal", "score_change", "shaped", "actions_used",
+                                                  "view_actor", "view_critic")})
+        res[epc] = (outs, env.get_state())
+    for a, b in zip(res["8"][0], res["32"][0]):
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    for k in res["8"][1]:
+        np.testing.assert_array_equal(res["8"][1][k], res["32"][1][k])
