@@ -202,6 +202,10 @@ int pm_step_host_pipelined(const pm_env_desc *d, pm_pipe *pipe, const uint8_t *a
  * PM_EINVAL if a buffer is not page-locked.                                                       */
 int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *out_dev,
                         struct pm_host_record *records_pinned, pm_stream_t stream);
+/* Same launch without the final synchronise: the records are valid once the caller has synchronised
+ * `stream` (lets a caller queue more work, e.g. a copy of the observations, under the same wait). */
+int pm_step_host_mapped_async(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *out_dev,
+                              struct pm_host_record *records_pinned, pm_stream_t stream);
 
 /* Unpack the device state into plain arrays (GameState accessors,
  * capture.py:125-234): agents [N][4][7] int32 = x,y,dir,isPacman,scaredTimer,

@@ -19,7 +19,7 @@ EXPORTS = [
     "pm_abi_version", "pm_geom_words", "pm_layout_words", "pm_state_bytes", "pm_pack_geom", "pm_pack_layout",
     "pm_reset", "pm_step", "pm_observe", "pm_step_host", "pm_get_state",
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
-    "pm_step_host_pipelined", "pm_step_host_mapped", "pm_observe_views",
+    "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
 ]
 
 
@@ -111,6 +111,8 @@ def load():
     L.pm_step_host_pipelined.argtypes = [C.POINTER(PmEnvDesc), vp, vp, vp, C.POINTER(PmStepOut), vp, vp]
     L.pm_step_host_mapped.restype = i32
     L.pm_step_host_mapped.argtypes = [C.POINTER(PmEnvDesc), vp, C.POINTER(PmStepOut), vp, vp]
+    L.pm_step_host_mapped_async.restype = i32
+    L.pm_step_host_mapped_async.argtypes = [C.POINTER(PmEnvDesc), vp, C.POINTER(PmStepOut), vp, vp]
     L.pm_get_state.restype = i32
     L.pm_get_state.argtypes = [C.POINTER(PmEnvDesc), vp, vp, vp, vp, vp]
     L.pm_set_state.restype = i32

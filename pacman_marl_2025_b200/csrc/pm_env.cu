@@ -364,8 +364,8 @@ extern "C" int pm_step_host_pipelined(const pm_env_desc *d, pm_pipe *p, const ui
 }
 
 // ---- zero-copy host step ----------------------------------------------------------
-extern "C" int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *od,
-                                   pm_host_record *records_pinned, pm_stream_t stream) {
+extern "C" int pm_step_host_mapped_async(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *od,
+                                         pm_host_record *records_pinned, pm_stream_t stream) {
     if (!d || !actions_pinned || !od || !records_pinned) return PM_EINVAL;
     void *a_dev = nullptr, *r_dev = nullptr;
     cudaError_t e = cudaHostGetDevicePointer(&a_dev, (void *)actions_pinned, 0);
@@ -374,7 +374,12 @@ extern "C" int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_
     if (e != cudaSuccess) { cudaGetLastError(); return PM_EINVAL; }
     pm_step_out o = *od;
     o.packed = (pm_host_record *)r_dev;
-    if (int rc = pm_step(d, a_dev, 1, &o, stream)) return rc;
+    return pm_step(d, a_dev, 1, &o, stream);
+}
+
+extern "C" int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *od,
+                                   pm_host_record *records_pinned, pm_stream_t stream) {
+    if (int rc = pm_step_host_mapped_async(d, actions_pinned, od, records_pinned, stream)) return rc;
     return (int)cudaStreamSynchronize((cudaStream_t)stream);
 }
 

@@ -644,16 +644,32 @@ class gymPacMan_parallel_env:
                 v = self._name_to_int.get(v, 255)
             v = int(v)
             self._single_np[0, i] = v if 0 <= v <= 4 else 255          # out of range = illegal -> Stop, like the kernel
-        rec = self.step_host_mapped(self._single_act)
-        o = self._obs.clone()
+        # launch (the kernel reads the pinned action word and writes the pinned record), clone the observation block
+        # on the same stream, and only then synchronise: one wait covers both
+        if not hasattr(self, "_rec_mapped"):
+            self.step_host_mapped(self._single_act)          # first call: allocates the record buffer (and steps)
+            o = self._obs.clone()
+            dt = np.dtype([("reward", "<f8", 2), ("shaped", "<f4", 4), ("score_change", "<i4"), ("legal", "u1", 4),
+                           ("done", "u1"), ("pad", "u1", 7)])
+            self._rec_np = self._rec_mapped.numpy().view(dt)[:, 0]
+        else:
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pm_step_host_mapped_async(C.byref(self._desc), self._single_act.data_ptr(),
+                                                             C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
+                                                             self._stream()), "pm_step_host_mapped_async")
+                o = self._obs.clone()
+                torch.cuda.current_stream(self.device).synchronize()
+            self._version += 1
+            self.steps += 1
+        r = self._rec_np[0]
         obs = {self.agents[i]: o[i, 0] for i in range(4)}
-        red, blue = (float(x) for x in rec["reward"][0].tolist())
-        rewards = {self.agents[i]: (blue if i & 1 else red) for i in range(4)}
-        done = bool(rec["done"][0])
-        terms = {self.agents[i]: done for i in range(4)}
-        legal = rec["legal"][0].tolist()
+        red, blue = float(r["reward"][0]), float(r["reward"][1])
+        rewards = {self.agents[0]: red, self.agents[1]: blue, self.agents[2]: red, self.agents[3]: blue}
+        done = bool(r["done"])
+        terms = {a: done for a in self.agents}
+        legal = r["legal"]
         info = {"legal_actions": {self.agents[i]: legal_mask_to_list(legal[i]) for i in range(4)},
-                "score_change": int(rec["score_change"][0])}
+                "score_change": int(r["score_change"])}
         return obs, rewards, terms, info
 
     def step(self, actions):

@@ -6,6 +6,6 @@ python bench.py --steps 200 --warmup 10 > gpurun_out/bench_quick.json 2>gpurun_o
 import json
 d=json.loads(open('gpurun_out/bench_quick.json').read().strip().splitlines()[-1])
 print('value',d['value'],'frac',d['roofline']['frac'],'kernel_ms',d['roofline']['kernel_ms'],'e2e',d['e2e']['value'])
-print({k:(v['value'],v['roofline_frac']) for k,v in d['also'].items() if k!='kernels'})
+print({k:(v['value'],v['roofline_frac']) for k,v in d['also'].items() if k not in ('kernels','mappo')})
 print({k:v.get('ms') for k,v in d['also']['kernels'].items()})
 PY
