@@ -341,3 +341,27 @@ def body_layout_ids(make_env, N=40, T=90):
         np.testing.assert_array_equal(o["reward"].view(np.uint64), r["reward"].T.copy().view(np.uint64), err_msg=f"t={t}")
         np.testing.assert_array_equal(o["done"], r["done"])
         np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4)[keep], r["obs"][keep], err_msg=f"t={t} obs")
+
+
+def body_bots_and_views_on_distinct_mazes(make_env, N=12, T=70):
+    """Per-env boards (L = N) together with the baselineTeam look-ahead (one distance table per board) and the
+    mirrored learner views (mirrored wall plane per board)."""
+    from pacman_marl_2025_b200 import mazeGenerator
+    mazes = [mazeGenerator.generateMaze(3000 + s).split("\n") for s in range(N)]
+    env = make_env(mazes, N, length=50, auto_reset=True, bot_kind=[2, 0, 3, 0], bot_first_best=True)
+    ref = oracle.OracleBatch(mazes, N, length=50)
+    ref.set_bots([2, 0, 3, 0])
+    env.set_views(True)
+    env.reset(); ref.reset()
+    rng = np.random.default_rng(41)
+    for t in range(T):
+        a = biased_actions(rng, N, 0.5, t)
+        o = env.step(a)
+        r = ref.step_bots(a, with_obs=True, auto_reset=True, nthreads=0)
+        np.testing.assert_array_equal(o["actions_used"][:, [0, 2]], r["actions_used"][:, [0, 2]], err_msg=f"t={t} bot actions")
+        np.testing.assert_array_equal(o["reward"].view(np.uint64), r["reward"].T.copy().view(np.uint64), err_msg=f"t={t}")
+        keep = ~r["done"].astype(bool)
+        np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4)[keep], r["obs"][keep], err_msg=f"t={t} obs")
+        wa, wc = np_views(o["obs"], True)
+        np.testing.assert_array_equal(o["view_actor"], wa, err_msg=f"t={t} mirrored actor views")
+        np.testing.assert_array_equal(o["view_critic"], wc, err_msg=f"t={t} mirrored critic view")

@@ -109,6 +109,11 @@ def test_explicit_layout_ids():
     body_layout_ids(CudaEnv, N=300, T=120)
 
 
+def test_bots_and_views_on_distinct_mazes():
+    from parity_bodies import body_bots_and_views_on_distinct_mazes
+    body_bots_and_views_on_distinct_mazes(CudaEnv, N=70, T=90)
+
+
 def test_int64_actions_and_out_of_range():
     body_int64_out_of_range(CudaEnv)
 

@@ -117,3 +117,8 @@ def test_emulated_learner_views_with_baseline_bots():
 def test_emulated_explicit_layout_ids():
     from parity_bodies import body_layout_ids
     body_layout_ids(lambda lays, n, **kw: EmuEnv(lays, n, E=8, KB=1, **kw), N=20, T=70)
+
+
+def test_emulated_bots_and_views_on_distinct_mazes():
+    from parity_bodies import body_bots_and_views_on_distinct_mazes
+    body_bots_and_views_on_distinct_mazes(lambda lays, n, **kw: EmuEnv(lays, n, E=4, KB=1, **kw), N=6, T=50)
