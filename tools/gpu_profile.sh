@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 TAG=${1:-r01}
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?"
 tail -3 gpurun_out/pytest_gpu_$TAG.log
-python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"
+T0=$SECONDS; python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$? wall $((SECONDS-T0)) s"
 cat gpurun_out/bench_$TAG.json
 [ -x tools/write_peak ] && ./tools/write_peak > gpurun_out/write_peak_$TAG.log 2>&1; cat gpurun_out/write_peak_$TAG.log
 for l in tinyCapture bloxCapture; do python tools/time_rules_only.py $l; done 2>&1 | tee gpurun_out/rules_only_$TAG.log
