@@ -145,7 +145,7 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def measure_layout(torch, env_cls, layout, n_envs, steps, warmup, length, device, pool=8):
+def measure_layout(torch, env_cls, layout, n_envs, steps, warmup, length, device, pool=8):  # noqa: ARG001 (steps)
     """-> dict(step_ms total loop, kernel_ms step kernel alone) for one layout on this rank."""
     env = env_cls(layout_file=layout_path(layout), self_play=True, length=length, num_envs=n_envs, device=device,
                   auto_reset=True)
@@ -459,6 +459,18 @@ def main():
                          "roofline_frac": ab * 4.0 * N / (km * 1e-3) / 1e9 / peak}
             del e2, a2, one2
             torch.cuda.empty_cache()
+        # the same layout at 4x the batch: the fixed cost of a launch (the store-free rules phase at its start) weighs less
+        e4, a4, one4 = measure_layout(torch, gymPacMan_parallel_env, args.layout, 4 * N, 0, 5, args.length, device, pool=2)
+        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+        torch.cuda.synchronize()
+        for i in range(30):
+            ee[i][0].record(); e4.step_batched(a4[i % 2]); ee[i][1].record()
+        torch.cuda.synchronize()
+        km = sum(a.elapsed_time(b) for a, b in ee) / 30
+        also[f"{args.layout}_x4_envs"] = {"envs": 4 * N, "value": 16.0 * N / (km * 1e-3), "kernel_ms": km,
+                                          "roofline_frac": algo * 16.0 * N / (km * 1e-3) / 1e9 / peak}
+        del e4, a4, one4
+        torch.cuda.empty_cache()
         # the other kernels of the path, each timed alone (CUDA events, this stream)
         also["kernels"] = other_kernels(torch, device, N, peak)
         also["mappo"] = mappo_sps(torch, device)
