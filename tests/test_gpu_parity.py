@@ -331,6 +331,10 @@ def test_reference_shaped_single_env_api():
     assert env.game.state.getAgentPosition(1) == (13, 1)
     assert env.game.state.data.score == 0 and env.max_score == 11
     assert env.get_Observation(0).shape == (8, 7, 20)
+    # pacman.py:352-356 passes the actions as a LIST indexed by agent and reads info["legal_actions"][agent]
+    obs2, rew2, term2, info2 = env.step([4, 4, 4, 4])
+    assert all(isinstance(info2["legal_actions"][i], list) for i in range(4)) and rew2[0] == 0.02 and rew2[1] == 0.02
+    assert torch.equal(env.get_Observation(3), obs2[3])              # last mover's snapshot == current state
 
 
 def test_mappo_trainer_rollout_gae_and_update():
