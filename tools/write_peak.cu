@@ -21,6 +21,22 @@ __global__ void k_stream(float4 *dst, size_t n4) {
     }
 }
 
+// data dependence: the same grid-stride float4 store with different VALUES (the observations are ~90 % zeros)
+template <int PAT>
+__global__ void k_pattern(float4 *dst, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v;
+        if (PAT == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
+        else if (PAT == 1) v = make_float4(1.f, 1.f, 1.f, 1.f);
+        else if (PAT == 2) v = make_float4(1.f, 0.f, 1.f, 0.f);
+        else {
+            unsigned h = (unsigned)i * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            v = make_float4(__uint_as_float(h | 0x3f000000u), __uint_as_float(h * 3u), __uint_as_float(h * 7u), __uint_as_float(h * 11u));
+        }
+        dst[i] = v;
+    }
+}
+
 // one warp writes whole "observations" of obs_f4 float4s, observation index strided by total warps
 template <int CS>
 __global__ void k_obs(float4 *dst, size_t nobs, int obs_f4) {
@@ -119,6 +135,14 @@ int main() {
             printf("grid-stride float4  tpb=%3d ctas/SM=%2d  plain %7.1f GB/s   .cs %7.1f GB/s\n", tpb, cps, bytes / a / 1e6,
                    bytes / b / 1e6);
         }
+    {
+        double z = time_ms([&] { k_pattern<0><<<sms * 8, 256>>>(dst, n4); });
+        double o = time_ms([&] { k_pattern<1><<<sms * 8, 256>>>(dst, n4); });
+        double m = time_ms([&] { k_pattern<2><<<sms * 8, 256>>>(dst, n4); });
+        double r = time_ms([&] { k_pattern<3><<<sms * 8, 256>>>(dst, n4); });
+        printf("value patterns (grid-stride float4, 256x8/SM): zeros %7.1f  ones %7.1f  1,0,1,0 %7.1f  hashed %7.1f GB/s\n",
+               bytes / z / 1e6, bytes / o / 1e6, bytes / m / 1e6, bytes / r / 1e6);
+    }
     for (int obs_bytes : {4480, 4928, 12800}) {
         const int f4 = obs_bytes / 16;
         const size_t nobs = bytes / obs_bytes;
