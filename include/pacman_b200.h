@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 5
+#define PM_ABI_VERSION 6
 
 /* argument errors */
 #define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
@@ -102,6 +102,14 @@ typedef struct pm_env_desc {
     const uint16_t *dist;          /* [dev] pm_distances output [L][nmax][nmax]; required for kinds 2, 3        */
     const int16_t *node_of_cell;   /* [dev] pm_distances output [L][H*W]                                        */
     int32_t dist_nmax, reserved1;
+    /* ---- ABI 6: a step played in several launches ----
+     * pm_step plays only the sub-moves of agents [agent_begin, agent_end) (0, 0 = the whole step).  The launches
+     * of one step must cover 0..4 in order; the state keeps the step's accumulators in between.  A launch writes
+     * the observations of the agents it moved (and actions_used so far); rewards, done, legal masks, shaping and
+     * the restart of finished envs come with the launch that ends at 4.  This is the hook for opponents that
+     * decide on the host at their own sub-move from the live state (gymPacMan.py:157): step agent 0, hand the
+     * state to the bot of agent 1, step agent 1, ...  Learner views need the whole step in one launch.        */
+    int32_t agent_begin, agent_end;
 } pm_env_desc;
 
 enum { PM_BOT_NONE = 0, PM_BOT_RANDOM = 1, PM_BOT_BASELINE_OFFENSE = 2, PM_BOT_BASELINE_DEFENSE = 3 };

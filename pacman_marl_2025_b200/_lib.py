@@ -39,6 +39,8 @@ class PmEnvDesc(C.Structure):
         # ABI 4
         ("bot_kind", C.c_int32), ("bot_first_best", C.c_int32), ("dist", C.c_void_p), ("node_of_cell", C.c_void_p),
         ("dist_nmax", C.c_int32), ("reserved1", C.c_int32),
+        # ABI 6
+        ("agent_begin", C.c_int32), ("agent_end", C.c_int32),
     ]
 
 
@@ -123,7 +125,7 @@ def load():
     L.pm_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, i32, i64, vp]
     L.pm_adv_norm.restype = i32
     L.pm_adv_norm.argtypes = [vp, vp, vp, i64, i32, vp]
-    if L.pm_abi_version() != 5:
+    if L.pm_abi_version() != 6:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

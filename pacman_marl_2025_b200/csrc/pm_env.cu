@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
 #ifdef PM_TRACE
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 2] = pm_gtime();
 #endif
-    if (MODE == PM_MODE_STEP && P.packed)
+    if (MODE == PM_MODE_STEP && P.packed && P.a1 == 4)
         for (int t = tid; t < 3 * E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
     // ---- phase B: observations, one warp per (env, agent) ----
     if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
@@ -259,6 +259,7 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
     P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
     if (int rc = set_views(P, out->view_actor, out->view_actor_stride, out->view_critic, out->view_red)) return rc;
+    if (P.view_actor && (P.a0 != 0 || P.a1 != 4)) return PM_EINVAL;                    // views need both learners' snapshots
     const bool bots = has_lookahead_bots(P), views = P.view_actor != nullptr;
     if (bots) return views ? launch_env<PM_MODE_STEP, 1, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 1, 0>(P, (cudaStream_t)stream);
     return views ? launch_env<PM_MODE_STEP, 0, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 0, 0>(P, (cudaStream_t)stream);

@@ -62,6 +62,14 @@ PM_HD uint64_t pm_dbits(double d) {
     uint64_t u; memcpy(&u, &d, 8); return u;
 #endif
 }
+PM_HD double pm_dfrom(uint32_t lo, uint32_t hi) {
+    const uint64_t u = (uint64_t)lo | (uint64_t)hi << 32;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d; memcpy(&d, &u, 8); return d;
+#endif
+}
 PM_HD uint32_t pm_fbits(float f) {
 #if defined(__CUDA_ARCH__)
     return __float_as_uint(f);
@@ -92,6 +100,7 @@ struct PmParams {
     int auto_reset;                     // step: terminal envs restart inside the launch
     int64_t n_base;                     // global index of env 0 (keys the random draws)
     int64_t n_begin, n_end;             // env range of this launch
+    int a0, a1;                         // sub-moves [a0, a1) of the step played by this launch (0, 4 = the whole step)
     // step inputs / outputs (see pm_step_out in pacman_b200.h)
     const void *actions; int act_size;
     float *obs; int64_t obs_agent_stride;
@@ -591,8 +600,10 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     uint32_t *gcaps = reinterpret_cast<uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
     uint32_t *food = sm + M.food + el;                 // slot k, word w at food[(k*NW + w)*E1]
     uint32_t *caps = P.has_caps ? sm + M.caps + el : nullptr;
-    for (int w = 0; w < NW; ++w) food[w * E1] = gfood[(size_t)w * NP + n];
-    if (caps) for (int w = 0; w < NW; ++w) caps[w * E1] = gcaps[(size_t)w * NP + n];
+    // the board goes into the slot the first sub-move of this launch copies from (slot 0 for a whole step)
+    const int s0 = P.a0 > 0 ? P.a0 - 1 : 0;
+    for (int w = 0; w < NW; ++w) food[(s0 * NW + w) * E1] = gfood[(size_t)w * NP + n];
+    if (caps) for (int w = 0; w < NW; ++w) caps[(s0 * NW + w) * E1] = gcaps[(size_t)w * NP + n];
 
     PmAgents g;
     pm_unpack_agents(g, A, B, tail);
@@ -604,6 +615,16 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     S.b.food_dirty = false; S.b.caps_dirty = false;
     S.sc_total = 0; S.red_sc = 0; S.blue_sc = 0; S.red_r = 0.0; S.blue_r = 0.0; S.act_used = 0;
     S.snap[0] = Sn.x; S.snap[1] = Sn.y; S.snap[2] = Sn.z; S.snap[3] = Sn.w;
+    pm_u4 *gacc = reinterpret_cast<pm_u4 *>(P.state + pm_st_acc(P.N, P.HW));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) S.shap[i] = 0.0;
+    if (P.a0 > 0) {                                    // continue a step that earlier launches started
+        const pm_u4 c0 = gacc[n], c1 = gacc[NP + n], c2 = gacc[2 * NP + n], c3 = gacc[3 * NP + n];
+        S.red_r = pm_dfrom(c0.x, c0.y); S.blue_r = pm_dfrom(c0.z, c0.w);
+        S.sc_total = (int)c1.x; S.red_sc = (int)c1.y; S.blue_sc = (int)c1.z; S.act_used = c1.w;
+        S.shap[0] = pm_dfrom(c2.x, c2.y); S.shap[1] = pm_dfrom(c2.z, c2.w);
+        S.shap[2] = pm_dfrom(c3.x, c3.y); S.shap[3] = pm_dfrom(c3.z, c3.w);
+    }
 
     uint32_t act4;
     if (P.act_size == 1) act4 = reinterpret_cast<const uint32_t *>(P.actions)[n];
@@ -614,10 +635,37 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         for (int i = 0; i < 4; ++i) { long long v = a8[i]; act4 |= (uint32_t)((v < 0 || v > 4) ? 255 : (int)v) << (8 * i); }
     }
 
-    pm_agent_turn<0, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    pm_agent_turn<1, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    pm_agent_turn<2, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    pm_agent_turn<3, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    if (P.a0 <= 0 && 0 < P.a1) pm_agent_turn<0, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    if (P.a0 <= 1 && 1 < P.a1) pm_agent_turn<1, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    if (P.a0 <= 2 && 2 < P.a1) pm_agent_turn<2, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    if (P.a0 <= 3 && 3 < P.a1) pm_agent_turn<3, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+
+    if (P.a1 < 4) {
+        // ---- the step continues in a later launch (a CPU bot decides the next sub-move from the state as it is
+        // now, gymPacMan.py:157): park the accumulators and the state; no epilogue, no step outputs ----
+        pm_u4 c0, c1, c2, c3;
+        uint64_t u;
+        u = pm_dbits(S.red_r); c0.x = (uint32_t)u; c0.y = (uint32_t)(u >> 32);
+        u = pm_dbits(S.blue_r); c0.z = (uint32_t)u; c0.w = (uint32_t)(u >> 32);
+        c1.x = (uint32_t)S.sc_total; c1.y = (uint32_t)S.red_sc; c1.z = (uint32_t)S.blue_sc; c1.w = S.act_used;
+        u = pm_dbits(S.shap[0]); c2.x = (uint32_t)u; c2.y = (uint32_t)(u >> 32);
+        u = pm_dbits(S.shap[1]); c2.z = (uint32_t)u; c2.w = (uint32_t)(u >> 32);
+        u = pm_dbits(S.shap[2]); c3.x = (uint32_t)u; c3.y = (uint32_t)(u >> 32);
+        u = pm_dbits(S.shap[3]); c3.z = (uint32_t)u; c3.w = (uint32_t)(u >> 32);
+        gacc[n] = c0; gacc[NP + n] = c1; gacc[2 * NP + n] = c2; gacc[3 * NP + n] = c3;
+        pm_pack_agents(g, A, B);
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
+        Sn.x = S.snap[0]; Sn.y = S.snap[1]; Sn.z = S.snap[2]; Sn.w = S.snap[3];
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = Sn;
+        Mi.x = (uint32_t)S.score; Mi.z = (uint32_t)S.b.rf | (uint32_t)S.b.bf << 16;
+        reinterpret_cast<pm_u4 *>(P.state + pm_st_misc(P.N))[n] = Mi;
+        const int sl = P.a1 - 1;
+        if (S.b.food_dirty) for (int w = 0; w < NW; ++w) gfood[(size_t)w * NP + n] = food[(sl * NW + w) * E1];
+        if (S.b.caps_dirty) for (int w = 0; w < NW; ++w) gcaps[(size_t)w * NP + n] = caps[(sl * NW + w) * E1];
+        if (P.act_used) reinterpret_cast<uint32_t *>(P.act_used)[n] = S.act_used;
+        return;
+    }
 
     int score = S.score, rf = S.b.rf, bf = S.b.bf;
     const int sc_total = S.sc_total;
@@ -812,6 +860,7 @@ template <int MODE>
 PM_HD bool pm_unit_load(const PmParams &P, const uint32_t *sm, const PmSmem &M, int k, int el, PmUnit &U) {
     U.lid = sm[M.lid + el];
     if (U.lid == 0xffffffffu) return false;
+    if (MODE == PM_MODE_STEP && (k < P.a0 || k >= P.a1)) return false;     // only the agents that moved in this launch
     const int slot = (MODE == PM_MODE_STEP) ? k : 0;
     U.food = sm + M.food + (size_t)slot * P.NW * M.E1 + el;
     U.caps = P.has_caps ? sm + M.caps + (size_t)slot * P.NW * M.E1 + el : nullptr;
@@ -1122,6 +1171,11 @@ static inline int pm_fill_params(const pm_env_desc *d, PmParams &P, int E) {
     P.auto_reset = d->auto_reset != 0;
     P.n_base = d->env_index_base;
     P.n_begin = d->env_begin; P.n_end = d->env_count ? d->env_begin + d->env_count : d->n_envs;
+    P.a0 = 0; P.a1 = 4;
+    if (d->agent_begin || d->agent_end) {
+        if (d->agent_begin < 0 || d->agent_end > 4 || d->agent_begin >= d->agent_end) return PM_EINVAL;
+        P.a0 = d->agent_begin; P.a1 = d->agent_end;
+    }
     P.E = E; P.lgE = 0;
     while ((1 << P.lgE) < E) ++P.lgE;
     return 0;

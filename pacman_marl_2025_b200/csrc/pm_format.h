@@ -64,7 +64,7 @@ PM_HD int pm_layout_words_(int HW) { return (pm_l_tail(HW) + PM_L_TAILWORDS + 3)
 // agB  uint4[N]  per agent: numCarrying | numReturned<<16
 // snap uint4[N]  per agent: own cell of the last observation handed out: x | y<<8 | carrying<<16
 // misc uint4[N]  score (i32) ; steps ; redFood | blueFood<<16 (board counts) ; reserved
-// food u32[NW][NP] ; caps u32[NW][NP]      NP = N rounded up to 32
+// food u32[NW][NP] ; caps u32[NW][NP] ; acc uint4[4][NP]      NP = N rounded up to 32
 PM_HD int64_t pm_np(int64_t N) { return (N + 31) & ~(int64_t)31; }
 PM_HD size_t pm_st_agA(int64_t N) { (void)N; return 0; }
 PM_HD size_t pm_st_agB(int64_t N) { return (size_t)pm_np(N) * 16; }
@@ -72,7 +72,10 @@ PM_HD size_t pm_st_snap(int64_t N) { return (size_t)pm_np(N) * 32; }
 PM_HD size_t pm_st_misc(int64_t N) { return (size_t)pm_np(N) * 48; }
 PM_HD size_t pm_st_food(int64_t N) { return (size_t)pm_np(N) * 64; }
 PM_HD size_t pm_st_caps(int64_t N, int HW) { return pm_st_food(N) + (size_t)pm_np(N) * 4 * pm_nw(HW); }
-PM_HD size_t pm_state_bytes_(int64_t N, int HW) { return pm_st_caps(N, HW) + (size_t)pm_np(N) * 4 * pm_nw(HW); }
+// acc uint4[4][N]: the accumulators of a step that is played in several launches (pm_env_desc.agent_begin/agent_end):
+//   [0] red reward, blue reward (fp64 bits)   [1] score change, red / blue score delta, actions used   [2],[3] shaping[4] (fp64)
+PM_HD size_t pm_st_acc(int64_t N, int HW) { return pm_st_caps(N, HW) + (size_t)pm_np(N) * 4 * pm_nw(HW); }
+PM_HD size_t pm_state_bytes_(int64_t N, int HW) { return pm_st_acc(N, HW) + (size_t)pm_np(N) * 64; }
 
 PM_HD uint32_t pm_agA_pack(int x, int y, int dir, int pac, int scared) {
     return (uint32_t)x | (uint32_t)y << 8 | (uint32_t)dir << 16 | (uint32_t)(pac & 1) << 19 | (uint32_t)scared << 20;

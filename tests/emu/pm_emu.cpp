@@ -44,7 +44,7 @@ static void run(const PmParams &P) {
             } else if (views) pm_phaseA_static<MODE, 1>(P, sm, sm, M, el, n0);
             else pm_phaseA_static<MODE, 0>(P, sm, sm, M, el, n0);
         }
-        if (MODE == PM_MODE_STEP && P.packed)
+        if (MODE == PM_MODE_STEP && P.packed && P.a1 == 4)
             for (int t = 0; t < 3 * P.E; ++t) pm_records_out(P, sm, M, t, n0);
         if (P.obs)
             for (int w = 0; w < EMU_THREADS / 32; ++w)

@@ -100,6 +100,10 @@ class EmuEnv:
         assert rc == 0, rc
         return va, vc
 
+    def set_agents(self, begin=0, end=0):
+        """Play only the sub-moves of agents [begin, end) in the following step launches (0, 0 = whole step)."""
+        self.desc.agent_begin, self.desc.agent_end = int(begin), int(end)
+
     def set_range(self, begin=0, count=0):
         self.desc.env_begin, self.desc.env_count = int(begin), int(count)
 

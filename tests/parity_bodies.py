@@ -365,3 +365,29 @@ def body_bots_and_views_on_distinct_mazes(make_env, N=12, T=70):
         wa, wc = np_views(o["obs"], True)
         np.testing.assert_array_equal(o["view_actor"], wa, err_msg=f"t={t} mirrored actor views")
         np.testing.assert_array_equal(o["view_critic"], wc, err_msg=f"t={t} mirrored critic view")
+
+
+def body_step_in_several_launches(make_env, set_agents, rows, N=40, T=120, splits=((0, 1), (1, 2), (2, 3), (3, 4)), **kw):
+    """pm_env_desc.agent_begin/agent_end: a step played as several launches (the hook for host-side opponents that
+    decide at their own sub-move) gives exactly the outputs, observations and state of the one-launch step."""
+    rng = np.random.default_rng(5)
+    whole, parts = make_env(rows, N, length=50, auto_reset=True, **kw), make_env(rows, N, length=50, auto_reset=True, **kw)
+    whole.reset(); parts.reset()
+    for t in range(T):
+        a = biased_actions(rng, N, 0.6, t)
+        o = whole.step(a)
+        obs = np.zeros_like(o["obs"])
+        for b, e in splits:
+            set_agents(parts, b, e)
+            p = parts.step(a)
+            obs[b:e] = p["obs"][b:e]
+        set_agents(parts, 0, 0)
+        for k in ("reward", "done", "legal", "score_change", "shaping", "shaped", "actions_used"):
+            if k in o:
+                np.testing.assert_array_equal(p[k], o[k], err_msg=f"t={t} {k}")
+        keep = ~o["done"].astype(bool)     # a restarted env shows the new episode in all four observations only in the last launch
+        np.testing.assert_array_equal(obs[:, keep], o["obs"][:, keep], err_msg=f"t={t} obs")
+        np.testing.assert_array_equal(p["obs"][3:, ~keep], o["obs"][3:, ~keep])
+    s1, s2 = whole.get_state(), parts.get_state()
+    for k in s1:
+        np.testing.assert_array_equal(s1[k], s2[k])

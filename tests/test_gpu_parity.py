@@ -56,6 +56,9 @@ class CudaEnv:
         a, c = self.env.observe_views(red)
         return a.cpu().numpy(), c.cpu().numpy()
 
+    def set_agents(self, begin=0, end=0):
+        self.env._desc.agent_begin, self.env._desc.agent_end = int(begin), int(end)
+
     def set_range(self, begin=0, count=0):
         self.env._desc.env_begin, self.env._desc.env_count = int(begin), int(count)
 
@@ -112,6 +115,14 @@ def test_explicit_layout_ids():
 def test_bots_and_views_on_distinct_mazes():
     from parity_bodies import body_bots_and_views_on_distinct_mazes
     body_bots_and_views_on_distinct_mazes(CudaEnv, N=70, T=90)
+
+
+def test_step_in_several_launches():
+    from parity_bodies import body_step_in_several_launches
+    sa = lambda e, b, c: e.set_agents(b, c)
+    body_step_in_several_launches(CudaEnv, sa, lay_rows("tinyCapture"), N=700, T=130)
+    body_step_in_several_launches(CudaEnv, sa, helpers.load_traj("capsSmall")["layout"], N=200, T=100, splits=((0, 2), (2, 3), (3, 4)))
+    body_step_in_several_launches(CudaEnv, sa, lay_rows("smallCapture"), N=100, T=70, splits=((0, 1), (1, 4)), bot_kind=[2, 0, 3, 0])
 
 
 def test_int64_actions_and_out_of_range():

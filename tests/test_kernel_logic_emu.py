@@ -122,3 +122,12 @@ def test_emulated_explicit_layout_ids():
 def test_emulated_bots_and_views_on_distinct_mazes():
     from parity_bodies import body_bots_and_views_on_distinct_mazes
     body_bots_and_views_on_distinct_mazes(lambda lays, n, **kw: EmuEnv(lays, n, E=4, KB=1, **kw), N=6, T=50)
+
+
+def test_emulated_step_in_several_launches():
+    from parity_bodies import body_step_in_several_launches
+    mk = lambda rows, n, **kw: EmuEnv(rows, n, E=8, KB=1, **kw)
+    sa = lambda e, b, c: e.set_agents(b, c)
+    body_step_in_several_launches(mk, sa, lay_rows("tinyCapture"), N=16, T=110)
+    body_step_in_several_launches(mk, sa, helpers.load_traj("capsSmall")["layout"], N=12, T=90, splits=((0, 2), (2, 3), (3, 4)))
+    body_step_in_several_launches(mk, sa, lay_rows("smallCapture"), N=10, T=60, splits=((0, 1), (1, 4)), bot_kind=[0, 0, 3, 0])
