@@ -226,7 +226,8 @@ class gymPacMan_parallel_env:
                  reward_forLegalAction=True, defenceReward=True, random_layout=False, enemieName="randomTeam",
                  self_play=False, *, num_envs: int = 1, device=None, layouts: Optional[Sequence] = None,
                  shaping_scale: float = 0.1, opponent_seed: int = 0, auto_reset: bool = False,
-                 env_index_base: int = 0, opponent_tiebreak: str = "random", layout_ids=None):
+                 env_index_base: int = 0, opponent_tiebreak: str = "random", layout_ids=None,
+                 bot_team=None, state_factory=None):
         if display:
             raise NotImplementedError("display=True (tkinter viewer) is outside the batched GPU path")
         if not torch.cuda.is_available():
@@ -255,7 +256,16 @@ class gymPacMan_parallel_env:
         # agent keys: ints in self-play (gymPacMan.py:33-40).  Without self-play the red side is driven by an
         # on-device opponent and still addressed by its index.
         self.agents = [0, 1, 2, 3]
-        if not self_play and enemieName not in ON_DEVICE_TEAMS:
+        # host-side opponents (the reference's agents/*.py teams): two objects with getAction(state) [and
+        # registerInitialState(state)] playing agents 0 and 2 at their own sub-move; `state_factory(env, n)` builds
+        # what they are handed (default: this module's read-only GameState view; reference_bridge.state_factory
+        # builds the reference's own GameState for bots that call generateSuccessor)
+        self._bot_team = list(bot_team) if bot_team is not None else None
+        self._state_factory = state_factory
+        if self._bot_team is not None:
+            if self_play or len(self._bot_team) != 2:
+                raise ValueError("bot_team needs self_play=False and exactly two bots (agents 0 and 2)")
+        if not self_play and self._bot_team is None and enemieName not in ON_DEVICE_TEAMS:
             raise NotImplementedError(
                 f"enemieName={enemieName!r}: the on-device opponents are {sorted(ON_DEVICE_TEAMS)}; the other CPU "
                 "bot teams (agents/*.py search agents) are outside the GPU path (SURVEY §8 row f1)")
@@ -330,7 +340,7 @@ class gymPacMan_parallel_env:
         gymPacMan.py:33-40).  baselineTeam needs the maze-distance tables: every reset of the reference
         rebuilds them per bot (captureAgents.py:91-109); here one BFS launch per layout set."""
         d = self._desc
-        if self.self_play:
+        if self.self_play or self._bot_team is not None:
             d.bot_kind = 0
             return
         k0, k2 = ON_DEVICE_TEAMS[name]
@@ -600,11 +610,15 @@ class gymPacMan_parallel_env:
         if new_lays is not None:
             self._install_layouts(new_lays)
         if enemieName != "None":
-            if not self.self_play and enemieName not in ON_DEVICE_TEAMS:
+            if not self.self_play and self._bot_team is None and enemieName not in ON_DEVICE_TEAMS:
                 raise NotImplementedError(f"enemieName={enemieName!r} is outside the GPU path")
             self.enemieName = enemieName
             self._set_opponent(enemieName)
         self.reset_batched(mask)
+        if self._bot_team is not None:                 # gymPacMan.py:130-132: every bot sees the initial state
+            for b in self._bot_team:
+                if hasattr(b, "registerInitialState"):
+                    b.registerInitialState(self._bot_state(0))
         return self._obs_dict(), {"legal_actions": self._legal_dict()}
 
     def _gather_actions(self, actions) -> torch.Tensor:
@@ -672,8 +686,47 @@ class gymPacMan_parallel_env:
                 "score_change": int(r["score_change"])}
         return obs, rewards, terms, info
 
+    # ---- host-side opponents: a step in two launches, each bot asked at its own sub-move ----
+    def _bot_state(self, n):
+        return self._state_factory(self, n) if self._state_factory is not None else _StateView(self, n)
+
+    def _step_with_host_bots(self, actions):
+        """gymPacMan.step with `bot.getAction(state)` for the red agents (gymPacMan.py:149-167): agent 0's bot sees the
+        state before the step; after the launch that plays agents 0 and 1, agent 2's bot sees the state as it is
+        then; the second launch plays agents 2 and 3 and finishes the step."""
+        N = self.num_envs
+        a = self._gather_actions(actions).to(torch.int64).clone()             # blue columns; red filled below
+        name_to_int = self._name_to_int
+        out = None
+        for first, (lo, hi) in ((0, (0, 2)), (2, (2, 4))):
+            bot = self._bot_team[first >> 1]
+            self._version += 1                                                # invalidate the cached state view
+            for n in range(N):
+                act = bot.getAction(self._bot_state(n))
+                a[n, first] = name_to_int[act] if isinstance(act, str) else int(act)
+            self._desc.agent_begin, self._desc.agent_end = lo, hi
+            try:
+                self.steps -= 0 if hi == 4 else 1                             # step_batched counts whole steps
+                out = self.step_batched(a)
+            finally:
+                self._desc.agent_begin, self._desc.agent_end = 0, 0
+            self.num_moves += hi - lo
+        return out
+
     def step(self, actions):
         """gymPacMan.step (gymPacMan.py:143-193)."""
+        if self._bot_team is not None:
+            out = self._step_with_host_bots(actions)
+            obs = self._obs_dict()
+            if self.num_envs == 1:
+                rew = out["reward"][:, 0].cpu().tolist()
+                done = bool(out["done"][0].item())
+                return (obs, {self.agents[i]: rew[i & 1] for i in range(4)}, {self.agents[i]: done for i in range(4)},
+                        {"legal_actions": self._legal_dict(), "score_change": int(out["score_change"][0].item())})
+            d = out["done"].bool()
+            return (obs, {self.agents[i]: out["reward"][i & 1].clone() for i in range(4)},
+                    {self.agents[i]: d for i in range(4)},
+                    {"legal_actions": self._legal_dict(), "score_change": out["score_change"].clone()})
         if self.num_envs == 1 and not isinstance(actions, torch.Tensor) and not any(
                 isinstance(actions[self.agents[i]], torch.Tensor) for i in range(4)
                 if self.self_play or i in (1, 3)):

@@ -652,3 +652,64 @@ def test_envs_per_cta_choice_does_not_change_results(monkeypatch):
             np.testing.assert_array_equal(a[k], b[k], err_msg=k)
     for k in res["8"][1]:
         np.testing.assert_array_equal(res["8"][1][k], res["32"][1][k])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side opponents: the step in two launches, each bot asked at its own sub-move (rest of row f1)
+# ---------------------------------------------------------------------------------------------------------
+class _GreedyEastBot:
+    """A stand-in for an agents/*.py bot that only uses the GameState accessors (no reference checkout on the GPU box)."""
+
+    def __init__(self, index):
+        self.index, self.registered, self.seen_positions = index, 0, []
+
+    def registerInitialState(self, state):
+        self.registered += 1
+
+    def getAction(self, state):
+        self.seen_positions.append(tuple(state.getAgentPosition(i) for i in range(4)))
+        legal = state.getLegalActions(self.index)
+        x, y = state.getAgentPosition(self.index)
+        if state.getAgentState(self.index).numCarrying >= 2 and "West" in legal:
+            return "West"
+        for a in ("East", "North", "South", "West"):
+            if a in legal:
+                return a
+        return "Stop"
+
+
+def test_host_side_bots_play_at_their_own_sub_move():
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    rows = lay_rows("tinyCapture")
+    N = 3
+    bots = [_GreedyEastBot(0), _GreedyEastBot(2)]
+    env = gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, "tinyCapture.lay"), self_play=False, length=40,
+                                 num_envs=N, bot_team=bots, enemieName="someHostTeam")
+    ref = oracle.OracleBatch(rows, N, length=40)
+    obs, info = env.reset()
+    ref.reset()
+    assert bots[0].registered >= 1 and bots[1].registered >= 1
+    rng = np.random.default_rng(4)
+    for t in range(41):
+        blue = rng.integers(0, 5, size=(N, 2))
+        before = ref.state(0)["agents"][:, :2].copy()
+        obs, rew, term, info = env.step({1: torch.as_tensor(blue[:, 0]), 3: torch.as_tensor(blue[:, 1])})
+        used = env._actions_used.cpu().numpy().astype(np.int32)
+        # what the bots saw: agent 0's bot the state before the step, agent 2's bot the state after agents 0 and 1 moved
+        assert bots[0].seen_positions[-N] == tuple(map(tuple, before))
+        r = ref.step(used, with_obs=True, nthreads=0)
+        # 'used' holds the EFFECTIVE actions (illegal blue requests became Stop), so drop the legal-action bonus
+        # difference by comparing everything except the 0.01 bonuses of illegal requests: compare obs / done / score
+        np.testing.assert_array_equal(torch.stack([obs[i] for i in range(4)]).cpu().numpy().transpose(1, 0, 2, 3, 4), r["obs"])
+        np.testing.assert_array_equal(term[1].cpu().numpy().astype(np.uint8), r["done"])
+        np.testing.assert_array_equal(info["score_change"].cpu().numpy(), r["score_change"])
+        req_illegal = np.stack([(used[:, 1] != blue[:, 0]), (used[:, 3] != blue[:, 1])], 1).sum(1)
+        np.testing.assert_allclose(rew[1].cpu().numpy(), r["reward"][:, 1] - 0.01 * req_illegal, rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(rew[0].cpu().numpy().view(np.uint64), r["reward"][:, 0].copy().view(np.uint64))
+        # agent 2's bot saw env 0 AFTER agents 0 and 1 had moved: their cells are already the ones of the final state
+        mid, after = bots[1].seen_positions[-N], ref.state(0)["agents"][:, :2]
+        if not r["done"][0] and tuple(after[0]) != tuple(ref.state(0)["agents"][0, :2] * 0 - 1):
+            assert mid[0] == tuple(after[0]) or tuple(after[0]) == (env.layout.starts[0][0], env.layout.starts[0][1])
+        if bool(term[1].any()):
+            break
+    assert env.steps == t + 1 and env.num_moves == 4 * (t + 1)
