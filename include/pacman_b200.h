@@ -8,9 +8,13 @@
  * Each entry point below names the reference interface it replaces.  All data
  * pointers marked [dev] are device pointers owned by the caller (PyTorch
  * tensors in the bundled host code), every launch goes to the caller's stream,
- * nothing here synchronises the device except the *_host entry point, and no
- * entry point keeps global state (re-entrant).  Return value: 0 = OK,
- * > 0 = cudaError_t from the launch, < 0 = PM_E* argument error.
+ * nothing here synchronises the device except the *_host entry points.  The
+ * library keeps no per-batch state: everything a call needs is in its arguments,
+ * so independent batches can be driven from different host threads / streams.
+ * (The only process-wide data are per-device caches of the SM count and of the
+ * kernels' dynamic shared-memory attribute; they are mutex-guarded.)
+ * Return value: 0 = OK, > 0 = cudaError_t from the launch, < 0 = PM_E* argument
+ * error.
  *
  * Batch layout ("SoA over envs"): N independent 4-agent games share one board
  * size W x H.  Boards come from a table of L packed layout records (L = 1: one
@@ -27,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 6
+#define PM_ABI_VERSION 7
 
 /* argument errors */
 #define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
@@ -49,6 +53,9 @@ int pm_geom_words(int W, int H);
 int pm_layout_words(int W, int H);
 /* bytes of the device state blob for N envs */
 size_t pm_state_bytes(int W, int H, int64_t n_envs);
+
+/* u32 words of one packed observation (pm_step_out.obs_bits): ceil(8*W*H/32) + 1 patch word, rounded up to 4 */
+int pm_obs_bits_words(int W, int H);
 
 /* ---- host-side packing (pure CPU, no CUDA call) -------------------------- */
 /* Geometry record: plane masks for the three half-board formulas
@@ -84,7 +91,9 @@ typedef struct pm_env_desc {
        reward / done / score_change / shaping describe the terminal step; obs / legal and the
        stored state are those of the fresh episode.                                         */
     int32_t auto_reset;
-    int32_t reserved0;
+    /* ---- ABI 7 ---- envs per CTA of the env kernels: 0 = chosen from the batch size (32, or 8 for batches that
+       would leave SMs idle), 8 or 32 = forced (launch geometry only; results never depend on it)            */
+    int32_t envs_per_cta;
     int64_t env_index_base;       /* global index of env 0 of this batch (rank offset when the batch is a
                                      shard): keys the in-kernel random draws, so trajectories do not
                                      depend on how envs are partitioned over GPUs                      */
@@ -101,7 +110,13 @@ typedef struct pm_env_desc {
                                       counter-based draw), 1 = first best in N,S,E,W,Stop order (parity tests) */
     const uint16_t *dist;          /* [dev] pm_distances output [L][nmax][nmax]; required for kinds 2, 3        */
     const int16_t *node_of_cell;   /* [dev] pm_distances output [L][H*W]                                        */
-    int32_t dist_nmax, reserved1;
+    int32_t dist_nmax;
+    /* ---- ABI 7: a new maze every episode (gymPacMan.py:98-100 with random_layout=True, capture.py:905-911) ----
+     * non-zero: `layouts` is a POOL of L boards and `layout_id` ([N], required, written by the kernels) names the
+     * board each env is playing.  Whenever an env (re)starts - pm_reset, or auto_reset inside pm_step - it moves to
+     * board  hash(random_seed, global env index, episode) % L, so the sequence of boards an env sees depends on
+     * nothing but (seed, env, episode number).                                                             */
+    int32_t layout_pool;
     /* ---- ABI 6: a step played in several launches ----
      * pm_step plays only the sub-moves of agents [agent_begin, agent_end) (0, 0 = the whole step).  The launches
      * of one step must cover 0..4 in order; the state keeps the step's accumulators in between.  A launch writes
@@ -110,6 +125,13 @@ typedef struct pm_env_desc {
      * decide on the host at their own sub-move from the live state (gymPacMan.py:157): step agent 0, hand the
      * state to the bot of agent 1, step agent 1, ...  Learner views need the whole step in one launch.        */
     int32_t agent_begin, agent_end;
+    /* ---- ABI 7: externally supplied random draws for the on-device opponents ----
+     * [dev] [N][4] uint32 or NULL.  When set, an on-device bot does not hash its own draw: agent a of env n uses
+     * bot_draws[n][a] as the INDEX random.choice would have returned - into the legal-action list in the
+     * reference's order N,S,E,W,Stop for randomTeam (agents/randomTeam.py:100), into the list of best actions
+     * (same order) for baselineTeam (agents/baselineTeam.py:92); an index past the end wraps (modulo).  Feeding
+     * the indices recorded from the reference's own MT19937 stream replays its trajectories bit for bit.     */
+    const uint32_t *bot_draws;
 } pm_env_desc;
 
 enum { PM_BOT_NONE = 0, PM_BOT_RANDOM = 1, PM_BOT_BASELINE_OFFENSE = 2, PM_BOT_BASELINE_DEFENSE = 3 };
@@ -144,6 +166,16 @@ typedef struct pm_step_out {
     int64_t view_actor_stride;
     uint8_t *view_critic;
     int32_t view_red, reserved2;
+    /* ---- ABI 7: packed observations for a HOST-side consumer ----
+     * The eight planes of an observation hold 0/1 except the own cell (1 + numCarrying), so an observation is an
+     * 8*H*W-bit string plus one patch.  obs_bits: [dev or mapped pinned host] agent a, env n at
+     * obs_bits + a*obs_bits_agent_stride + n*pm_obs_bits_words(W,H) (u32 words): bit (p*H*W + y*W + x) & 31 of word
+     * (p*H*W + y*W + x) >> 5 = plane p, row y, column x; then ONE patch word = element index | value << 16 of the
+     * own cell (0xFFFFFFFF: value is 1, nothing to patch); then zero padding to a multiple of 4 words.
+     * 144 B per observation on tinyCapture instead of 4 480 B of fp32 - what crosses PCIe when the policy lives on
+     * the host.  NULL = off.  Pointer 16-byte aligned, stride a multiple of 4 words.                          */
+    uint32_t *obs_bits;
+    int64_t obs_bits_agent_stride;   /* in u32 words */
 } pm_step_out;
 
 /* What a CPU-side caller of gymPacMan.step reads back every step (gymPacMan.py:184-193), one record per env. */
@@ -175,6 +207,9 @@ int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, cons
  * all four agents of every env. */
 int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream);
 
+/* The packed observations (pm_step_out.obs_bits) of the CURRENT state for all four agents. */
+int pm_observe_bits(const pm_env_desc *d, uint32_t *obs_bits, int64_t obs_bits_agent_stride, pm_stream_t stream);
+
 /* The learner views (see pm_step_out) of the CURRENT state, e.g. right after pm_reset. */
 int pm_observe_views(const pm_env_desc *d, int view_red, uint8_t *view_actor, int64_t view_actor_stride,
                      uint8_t *view_critic, pm_stream_t stream);
@@ -184,7 +219,8 @@ int pm_observe_views(const pm_env_desc *d, int view_red, uint8_t *view_actor, in
  * into the DEVICE buffers of out_dev, copies every member of out_dev that has a
  * non-NULL counterpart in out_host back to the host, and synchronises the stream.
  * out_host->obs may be NULL to keep observations resident in HBM for a policy
- * network on the same GPU. */
+ * network on the same GPU.  out_host->view_actor / view_critic / obs_bits (ABI 7)
+ * bring the uint8 learner views / the packed observations to the host instead. */
 int pm_step_host(const pm_env_desc *d, const uint8_t *actions_host, uint8_t *actions_dev,
                  const pm_step_out *out_dev, const pm_step_out *out_host, pm_stream_t stream);
 
@@ -206,7 +242,9 @@ int pm_step_host_pipelined(const pm_env_desc *d, pm_pipe *pipe, const uint8_t *a
  * ([N] pm_host_record) are page-locked host buffers (cudaHostAlloc / torch pin_memory); the step
  * kernel reads the actions and writes the records straight across PCIe (coalesced 128-bit
  * accesses), so one step is ONE launch plus a stream synchronise.  out_dev->packed is ignored;
- * observations and any other non-NULL member of out_dev stay in device memory.
+ * observations and any other non-NULL member of out_dev stay in device memory - except
+ * out_dev->obs_bits, which may itself point at page-locked host memory: the packed observations
+ * then cross PCIe from inside the kernel too.
  * PM_EINVAL if a buffer is not page-locked.                                                       */
 int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *out_dev,
                         struct pm_host_record *records_pinned, pm_stream_t stream);
@@ -218,10 +256,14 @@ int pm_step_host_mapped_async(const pm_env_desc *d, const uint8_t *actions_pinne
 /* Unpack the device state into plain arrays (GameState accessors,
  * capture.py:125-234): agents [N][4][7] int32 = x,y,dir,isPacman,scaredTimer,
  * numCarrying,numReturned; food/caps [N][H*W] uint8 (cell y*W+x);
- * misc [N][2] int32 = score, steps.  Any pointer may be NULL.               */
+ * misc [N][3] int32 = score, steps, episode (restarts of this env so far: it keys
+ * the in-kernel opponent draws and the layout pool).  Any pointer may be NULL.
+ * Export / import describe the state BETWEEN whole steps: the parked accumulators
+ * of a step that is being played in several launches (agent_begin/agent_end) are
+ * not part of it.                                                             */
 int pm_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc,
                  pm_stream_t stream);
-/* Inverse of pm_get_state (test / checkpoint-restore hook). All four required. */
+/* Inverse of pm_get_state (checkpoint restore / crafted test states). All four required; misc is [N][3]. */
 int pm_set_state(const pm_env_desc *d, const int32_t *agents, const uint8_t *food, const uint8_t *caps,
                  const int32_t *misc, pm_stream_t stream);
 

@@ -15,11 +15,14 @@ LIB_PATH = os.path.join(_HERE, "libpacman_b200.so")
 PM_ERRORS = {-1: "PM_EINVAL (bad argument)", -2: "PM_ELAYOUT (malformed layout text)",
              -3: "PM_ETOOBIG (board larger than 1024 cells or a side > 255)", -4: "PM_ENOGPU"}
 
+ABI_VERSION = 7
+
 EXPORTS = [
     "pm_abi_version", "pm_geom_words", "pm_layout_words", "pm_state_bytes", "pm_pack_geom", "pm_pack_layout",
     "pm_reset", "pm_step", "pm_observe", "pm_step_host", "pm_get_state",
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
     "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
+    "pm_obs_bits_words", "pm_observe_bits",
 ]
 
 
@@ -34,13 +37,15 @@ class PmEnvDesc(C.Structure):
         ("shaping_scale", C.c_double),
         ("random_seed", C.c_uint64),
         # ABI 2
-        ("auto_reset", C.c_int32), ("reserved0", C.c_int32), ("env_index_base", C.c_int64),
+        ("auto_reset", C.c_int32), ("envs_per_cta", C.c_int32), ("env_index_base", C.c_int64),
         ("env_begin", C.c_int64), ("env_count", C.c_int64),
         # ABI 4
         ("bot_kind", C.c_int32), ("bot_first_best", C.c_int32), ("dist", C.c_void_p), ("node_of_cell", C.c_void_p),
-        ("dist_nmax", C.c_int32), ("reserved1", C.c_int32),
+        ("dist_nmax", C.c_int32), ("layout_pool", C.c_int32),
         # ABI 6
         ("agent_begin", C.c_int32), ("agent_end", C.c_int32),
+        # ABI 7
+        ("bot_draws", C.c_void_p),
     ]
 
 
@@ -54,6 +59,8 @@ class PmStepOut(C.Structure):
         # ABI 5: learner views
         ("view_actor", C.c_void_p), ("view_actor_stride", C.c_int64), ("view_critic", C.c_void_p),
         ("view_red", C.c_int32), ("reserved2", C.c_int32),
+        # ABI 7: packed observations
+        ("obs_bits", C.c_void_p), ("obs_bits_agent_stride", C.c_int64),
     ]
 
 
@@ -71,6 +78,8 @@ def declare_pack_api(L):
     L.pm_layout_words.argtypes = [C.c_int, C.c_int]
     L.pm_state_bytes.restype = C.c_size_t
     L.pm_state_bytes.argtypes = [C.c_int, C.c_int, C.c_int64]
+    L.pm_obs_bits_words.restype = C.c_int
+    L.pm_obs_bits_words.argtypes = [C.c_int, C.c_int]
     L.pm_pack_geom.restype = C.c_int
     L.pm_pack_geom.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.pm_pack_layout.restype = C.c_int
@@ -101,6 +110,8 @@ def load():
     L.pm_step.argtypes = [C.POINTER(PmEnvDesc), vp, i32, C.POINTER(PmStepOut), vp]
     L.pm_observe.restype = i32
     L.pm_observe.argtypes = [C.POINTER(PmEnvDesc), vp, i64, vp]
+    L.pm_observe_bits.restype = i32
+    L.pm_observe_bits.argtypes = [C.POINTER(PmEnvDesc), vp, i64, vp]
     L.pm_observe_views.restype = i32
     L.pm_observe_views.argtypes = [C.POINTER(PmEnvDesc), i32, vp, i64, vp, vp]
     L.pm_step_host.restype = i32
@@ -125,7 +136,7 @@ def load():
     L.pm_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, i32, i64, vp]
     L.pm_adv_norm.restype = i32
     L.pm_adv_norm.argtypes = [vp, vp, vp, i64, i32, vp]
-    if L.pm_abi_version() != 6:
+    if L.pm_abi_version() != ABI_VERSION:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L
     return L

@@ -18,8 +18,8 @@
 // small outputs, and 4 * 32*H*W B of observations (98+ % of all bytes).
 #include <cuda_runtime.h>
 
-#include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/pacman_b200.h"
 #include "pm_env_core.cuh"
@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
     if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
     // ---- phase B': learner views, one warp per (env, view) ----
     if (VIEWS && P.view_actor != nullptr) pm_phaseB_views<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0, 4 + BOTS);
+    // ---- phase B'': packed observations for a host-side consumer ----
+    if (P.obs_bits != nullptr) pm_phaseB_bits<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
 #ifdef PM_TRACE
     __syncthreads();
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 3] = pm_gtime();
@@ -115,7 +117,7 @@ __global__ void pm_get_state_kernel(const PmParams P, int32_t *agents, uint8_t *
             o[0] = a[i] & 0xff; o[1] = (a[i] >> 8) & 0xff; o[2] = (a[i] >> 16) & 7; o[3] = (a[i] >> 19) & 1;
             o[4] = (a[i] >> 20) & 0xff; o[5] = b[i] & 0xffff; o[6] = b[i] >> 16;
         }
-    if (misc) { misc[2 * n] = (int32_t)Mi.x; misc[2 * n + 1] = (int32_t)Mi.y; }
+    if (misc) { misc[3 * n] = (int32_t)Mi.x; misc[3 * n + 1] = (int32_t)Mi.y; misc[3 * n + 2] = (int32_t)Mi.w; }
     const uint32_t *gfood = reinterpret_cast<const uint32_t *>(P.state + pm_st_food(P.N));
     const uint32_t *gcaps = reinterpret_cast<const uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
     for (int c = 0; c < P.HW; ++c) {
@@ -154,7 +156,8 @@ __global__ void pm_set_state_kernel(const PmParams P, const int32_t *agents, con
         gfood[(size_t)w * NP + n] = fw;
         gcaps[(size_t)w * NP + n] = cw;
     }
-    Mi.x = (uint32_t)misc[2 * n]; Mi.y = (uint32_t)misc[2 * n + 1]; Mi.z = (uint32_t)rf | (uint32_t)bf << 16; Mi.w = 0;
+    Mi.x = (uint32_t)misc[3 * n]; Mi.y = (uint32_t)misc[3 * n + 1]; Mi.z = (uint32_t)rf | (uint32_t)bf << 16;
+    Mi.w = (uint32_t)misc[3 * n + 2];                  // episode counter: keys the opponent draws and the layout pool
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
     reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
@@ -164,6 +167,24 @@ __global__ void pm_set_state_kernel(const PmParams P, const int32_t *agents, con
 // ---------------------------------------------------------------------------
 // host glue
 // ---------------------------------------------------------------------------
+#define PM_MAX_DEVICES 64
+
+// SM count of the current device (cached per device, mutex-guarded); < 0 = PM_E* error
+static int pm_sm_count() {
+    static int count[PM_MAX_DEVICES];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
+    if (dev < 0 || dev >= PM_MAX_DEVICES) return PM_EINVAL;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!count[dev]) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        count[dev] = v;
+    }
+    return count[dev];
+}
+
 static int fill_params(const pm_env_desc *d, PmParams &P) { return pm_fill_params(d, P, PM_E); }
 
 static void set_envs_per_cta(PmParams &P, int E) {
@@ -177,19 +198,26 @@ static int launch_env_e(const PmParams &P0, cudaStream_t st) {
     set_envs_per_cta(P, E);
     const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
     const size_t smem = (size_t)M.total * 4;
-    static size_t configured[64];                      // per device (this function is one kernel instance)
+    // Per-device cache of the dynamic shared-memory size this kernel instance is configured for.  The launch stays
+    // under the lock whenever the attribute may still change, so another host thread can neither launch with a size
+    // that is not configured yet nor shrink it in between; the common path (already large enough) takes the lock
+    // only to read.
+    static size_t configured[PM_MAX_DEVICES];
+    static std::mutex mu;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
-    if (smem > configured[dev & 63]) {
+    if (dev < 0 || dev >= PM_MAX_DEVICES) return PM_EINVAL;
+    const unsigned grid = (unsigned)((P.n_end - P.n_begin + E - 1) / E);
+    std::lock_guard<std::mutex> lock(mu);
+    if (smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         // the kernel streams its output and keeps its working set in shared memory: prefer smem over L1
         e = cudaFuncSetAttribute(pm_env_kernel<MODE, BOTS, VIEWS, E>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return (int)e;
-        configured[dev & 63] = smem;
+        configured[dev] = smem;
     }
-    const unsigned grid = (unsigned)((P.n_end - P.n_begin + E - 1) / E);
     pm_env_kernel<MODE, BOTS, VIEWS, E><<<grid, PM_THREADS, smem, st>>>(P);
     return (int)cudaGetLastError();
 }
@@ -197,16 +225,13 @@ static int launch_env_e(const PmParams &P0, cudaStream_t st) {
 template <int MODE, int BOTS, int VIEWS>
 static int launch_env(const PmParams &P, cudaStream_t st) {
     // fewer than ~2 CTAs of PM_E envs per SM: use small CTAs so that the whole GPU takes part
-    static int sm_count[64];
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return PM_ENOGPU;
-    if (!sm_count[dev & 63]) {
-        int v = 0;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
-        sm_count[dev & 63] = v;
+    // (pm_env_desc.envs_per_cta overrides the choice)
+    bool small = P.epc == PM_E_SMALL;
+    if (P.epc == 0) {
+        int sms = pm_sm_count();
+        if (sms < 0) return sms;
+        small = (P.n_end - P.n_begin) < (int64_t)2 * PM_E * sms;
     }
-    int small = (P.n_end - P.n_begin) < (int64_t)2 * PM_E * sm_count[dev & 63];
-    if (const char *e = getenv("PM_ENVS_PER_CTA")) small = atoi(e) == PM_E_SMALL;      // tests / sweeps
     return small ? launch_env_e<MODE, BOTS, VIEWS, PM_E_SMALL>(P, st) : launch_env_e<MODE, BOTS, VIEWS, PM_E>(P, st);
 }
 
@@ -214,6 +239,13 @@ static int set_views(PmParams &P, uint8_t *actor, int64_t stride, uint8_t *criti
     if (!actor && !critic) return 0;
     if (!actor || !critic || P.W > 32 || ((size_t)actor & 7) || ((size_t)critic & 7) || (stride & 7)) return PM_EINVAL;
     P.view_actor = actor; P.view_actor_stride = stride; P.view_critic = critic; P.view_red = red != 0;
+    return 0;
+}
+
+static int set_bits(PmParams &P, uint32_t *bits, int64_t stride) {
+    if (!bits) return 0;
+    if (((size_t)bits & 15) || (stride & 3) || stride < (int64_t)P.NB) return PM_EINVAL;
+    P.obs_bits = bits; P.obs_bits_stride = stride;
     return 0;
 }
 
@@ -239,6 +271,14 @@ extern "C" int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_st
     return launch_env<PM_MODE_OBSERVE, 0, 0>(P, (cudaStream_t)stream);
 }
 
+extern "C" int pm_observe_bits(const pm_env_desc *d, uint32_t *obs_bits, int64_t obs_bits_agent_stride, pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    if (!obs_bits) return PM_EINVAL;
+    if (int rc = set_bits(P, obs_bits, obs_bits_agent_stride)) return rc;
+    return launch_env<PM_MODE_OBSERVE, 0, 0>(P, (cudaStream_t)stream);
+}
+
 extern "C" int pm_observe_views(const pm_env_desc *d, int view_red, uint8_t *view_actor, int64_t view_actor_stride,
                                 uint8_t *view_critic, pm_stream_t stream) {
     PmParams P;
@@ -260,6 +300,7 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
     if (int rc = set_views(P, out->view_actor, out->view_actor_stride, out->view_critic, out->view_red)) return rc;
     if (P.view_actor && (P.a0 != 0 || P.a1 != 4)) return PM_EINVAL;                    // views need both learners' snapshots
+    if (int rc = set_bits(P, out->obs_bits, out->obs_bits_agent_stride)) return rc;
     const bool bots = has_lookahead_bots(P), views = P.view_actor != nullptr;
     if (bots) return views ? launch_env<PM_MODE_STEP, 1, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 1, 0>(P, (cudaStream_t)stream);
     return views ? launch_env<PM_MODE_STEP, 0, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 0, 0>(P, (cudaStream_t)stream);
@@ -295,6 +336,28 @@ extern "C" int pm_step_host(const pm_env_desc *d, const uint8_t *actions_host, u
             if (e != cudaSuccess) return (int)e;
         }
     }
+    // ABI 7: the compact per-step products a host-side consumer may want instead of the fp32 observations
+    if (oh->view_actor || oh->view_critic) {
+        if (!od->view_actor || !od->view_critic) return PM_EINVAL;
+        for (int l = 0; l < 2 && oh->view_actor; ++l) {
+            e = cudaMemcpyAsync(oh->view_actor + l * oh->view_actor_stride, od->view_actor + l * od->view_actor_stride,
+                                N * 8 * HW, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+        if (oh->view_critic) {
+            e = cudaMemcpyAsync(oh->view_critic, od->view_critic, N * 8 * HW, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (oh->obs_bits) {
+        if (!od->obs_bits) return PM_EINVAL;
+        const size_t nb = (size_t)pm_obs_bits_words_((int)HW);
+        for (int a = 0; a < 4; ++a) {
+            e = cudaMemcpyAsync(oh->obs_bits + a * oh->obs_bits_agent_stride, od->obs_bits + a * od->obs_bits_agent_stride,
+                                N * nb * 4, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
     return (int)cudaStreamSynchronize(st);
 }
 
@@ -316,15 +379,18 @@ extern "C" int pm_pipe_create(pm_pipe **pipe, int n_chunks) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming);
     }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->start, cudaEventDisableTiming);
-    if (e != cudaSuccess) { delete p; return (int)e; }
+    if (e != cudaSuccess) { pm_pipe_destroy(p); return (int)e; }       // releases whatever was created so far
     *pipe = p;
     return 0;
 }
 
 extern "C" int pm_pipe_destroy(pm_pipe *p) {
     if (!p) return PM_EINVAL;
-    for (int i = 0; i < 2; ++i) { cudaStreamDestroy(p->s[i]); cudaEventDestroy(p->done[i]); }
-    cudaEventDestroy(p->start);
+    for (int i = 0; i < 2; ++i) {
+        if (p->s[i]) cudaStreamDestroy(p->s[i]);
+        if (p->done[i]) cudaEventDestroy(p->done[i]);
+    }
+    if (p->start) cudaEventDestroy(p->start);
     delete p;
     return 0;
 }
@@ -344,24 +410,26 @@ extern "C" int pm_step_host_pipelined(const pm_env_desc *d, pm_pipe *p, const ui
     for (int i = 0; i < 2; ++i)
         if ((e = cudaStreamWaitEvent(p->s[i], p->start, 0)) != cudaSuccess) return (int)e;
     pm_env_desc dc = *d;
-    int used = 0;
-    for (int64_t b = 0; b < N; b += per, ++used) {
+    int used = 0, rc = 0;
+    for (int64_t b = 0; b < N && rc == 0; b += per, ++used) {
         const int64_t cnt = (N - b < per) ? N - b : per;
         cudaStream_t st = p->s[used & 1];
         e = cudaMemcpyAsync(actions_dev + 4 * b, actions_host + 4 * b, (size_t)cnt * 4, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) return (int)e;
+        if (e != cudaSuccess) { rc = (int)e; break; }
         dc.env_begin = b; dc.env_count = cnt;
-        if (int rc = pm_step(&dc, actions_dev, 1, od, (pm_stream_t)st)) return rc;
+        if ((rc = pm_step(&dc, actions_dev, 1, od, (pm_stream_t)st)) != 0) break;
         e = cudaMemcpyAsync(records_host + b, od->packed + b, (size_t)cnt * sizeof(pm_host_record), cudaMemcpyDeviceToHost, st);
-        if (e != cudaSuccess) return (int)e;
+        if (e != cudaSuccess) rc = (int)e;
     }
+    // Always join both internal streams back into the caller's stream - also after a failure, so that later work
+    // on the caller's stream cannot overtake the ranges that were already queued.
     for (int i = 0; i < 2; ++i) {
-        if ((e = cudaEventRecord(p->done[i], p->s[i])) != cudaSuccess) return (int)e;
-        if ((e = cudaStreamWaitEvent(caller, p->done[i], 0)) != cudaSuccess) return (int)e;
+        if ((e = cudaEventRecord(p->done[i], p->s[i])) == cudaSuccess) e = cudaStreamWaitEvent(caller, p->done[i], 0);
+        if (e != cudaSuccess && rc == 0) rc = (int)e;
     }
     for (int i = 0; i < 2; ++i)
-        if ((e = cudaStreamSynchronize(p->s[i])) != cudaSuccess) return (int)e;
-    return 0;
+        if ((e = cudaStreamSynchronize(p->s[i])) != cudaSuccess && rc == 0) rc = (int)e;
+    return rc;
 }
 
 // ---- zero-copy host step ----------------------------------------------------------
@@ -375,6 +443,13 @@ extern "C" int pm_step_host_mapped_async(const pm_env_desc *d, const uint8_t *ac
     if (e != cudaSuccess) { cudaGetLastError(); return PM_EINVAL; }
     pm_step_out o = *od;
     o.packed = (pm_host_record *)r_dev;
+    if (o.obs_bits) {                                   // may itself be mapped pinned host memory (zero-copy bits)
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, o.obs_bits) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            o.obs_bits = (uint32_t *)at.devicePointer;
+        else
+            cudaGetLastError();
+    }
     return pm_step(d, a_dev, 1, &o, stream);
 }
 

@@ -110,6 +110,11 @@ struct PmParams {
     // learner views (pm_step_out.view_*): canonicalised actor observations of one team + the merged critic observation
     uint8_t *view_actor; int64_t view_actor_stride; uint8_t *view_critic; int view_red;
     const uint8_t *mask;                // reset only
+    // ABI 7
+    int layout_pool; uint32_t *layout_id_rw;     // a new board per episode: hash(seed, env, episode) % L, kept in layout_id
+    const uint32_t *bot_draws;          // [N][4] externally supplied random.choice indices for the on-device bots
+    uint32_t *obs_bits; int64_t obs_bits_stride; int NB;   // packed observations: NB words per observation
+    int epc;                            // pm_env_desc.envs_per_cta (0 = auto)
 };
 
 #ifndef PM_TMA_STORE
@@ -277,13 +282,21 @@ PM_HD uint32_t pm_random_u32(unsigned long long seed, unsigned long long n, unsi
     z ^= z >> 31;
     return (uint32_t)(z >> 32);
 }
-PM_HD int pm_random_legal(int legal, unsigned long long seed, unsigned long long n, unsigned episode, unsigned ctr) {
-    const unsigned long long z32 = pm_random_u32(seed, n, episode, ctr);
+// The board an env plays in episode `episode` when the batch draws from a layout pool (pm_env_desc.layout_pool).
+PM_HD uint32_t pm_pool_layout(unsigned long long seed, unsigned long long n, unsigned episode, int L) {
+    return pm_random_u32(seed ^ 0x6c61796f75747321ull, n, episode, 0xfffffff0u) % (uint32_t)L;
+}
+// random.choice over the legal-action LIST, which the reference builds in the order N, S, E, W, Stop
+// (game.py:295-299, 344-348).  `draw`: a 32-bit uniform word (scaled to the list length), or with `is_index`
+// the list index itself (pm_env_desc.bot_draws; wraps past the end).
+PM_HD int pm_random_legal(int legal, uint32_t draw, bool is_index) {
+    const int order[5] = {0, 2, 1, 3, 4};
     int cnt = 0;
     for (int b = 0; b < 5; ++b) cnt += (legal >> b) & 1;
-    int pick = (int)((z32 * (unsigned long long)cnt) >> 32);
-    for (int b = 0; b < 5; ++b)
-        if ((legal >> b) & 1) { if (pick == 0) return b; --pick; }
+    int pick = is_index ? (int)(draw % (uint32_t)cnt) : (int)(((unsigned long long)draw * (unsigned long long)cnt) >> 32);
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if ((legal >> order[k]) & 1) { if (pick == 0) return order[k]; --pick; }
     return 4;
 }
 
@@ -467,7 +480,7 @@ PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2,
 template <int A>
 PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAgents &g, const uint32_t *fk, const uint32_t *ck,
                              uint32_t *fs, uint32_t *cs, const PmBoard &b, int legal, int kind, uint32_t rnd,
-                             bool first_best) {
+                             bool first_best, bool rnd_is_index) {
     const int order[5] = {0, 2, 1, 3, 4};              // Actions.getPossibleActions: N, S, E, W, Stop (game.py:295-299)
     const int is_red = (X.teams >> A) & 1;
     const bool go_home = (is_red ? b.bf : b.rf) <= 0;  // foodLeft <= 0: walk towards self.start (:79-90)
@@ -495,7 +508,7 @@ PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAgents &g,
     int nb = 0;
 #pragma unroll
     for (int k = 0; k < 5; ++k) nb += (vals[k] == bestv && ((legal >> order[k]) & 1)) ? 1 : 0;
-    int pick = first_best ? 0 : (int)(((unsigned long long)rnd * (unsigned)nb) >> 32);
+    int pick = first_best ? 0 : rnd_is_index ? (int)(rnd % (unsigned)nb) : (int)(((unsigned long long)rnd * (unsigned)nb) >> 32);
 #pragma unroll
     for (int k = 0; k < 5; ++k)
         if (vals[k] == bestv && ((legal >> order[k]) & 1)) { if (pick == 0) return order[k]; --pick; }
@@ -533,16 +546,20 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
     const int legal = pm_legal_mask(X.walls, W, g.y[A] * W + g.x[A]);
     int u = (act4 >> (8 * A)) & 0xff;
     const int kind = (P.bot_kind >> (4 * A)) & 15;
+    const bool ext_draw = P.bot_draws != nullptr;
     if (kind == 1) {
-        u = pm_random_legal(legal, P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
+        const uint32_t rnd = ext_draw ? P.bot_draws[4 * n + A]
+                                      : pm_random_u32(P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
+        u = pm_random_legal(legal, rnd, ext_draw);
     } else if (BOTS && kind >= 2) {
         PmDist D;
         D.nmax = P.dist_nmax;
         D.dist = P.dist + (size_t)lid * P.dist_nmax * P.dist_nmax;
         D.node_of = P.node_of_cell + (size_t)lid * X.HW;
-        const uint32_t rnd = pm_random_u32(P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
+        const uint32_t rnd = ext_draw ? P.bot_draws[4 * n + A]
+                                      : pm_random_u32(P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
         u = pm_baseline_choose<A>(X, D, g, fk, ck, food + (size_t)4 * NW * E1, caps ? caps + (size_t)4 * NW * E1 : nullptr,
-                                  S.b, legal, kind, rnd, P.bot_first_best != 0);
+                                  S.b, legal, kind, rnd, P.bot_first_best != 0, ext_draw);
     }
     const bool req_legal = u <= 4 && ((legal >> u) & 1);
     if (!req_legal) u = 4;                             // illegal -> Stop, capture.py:472-475
@@ -580,7 +597,7 @@ template <int BOTS, int VIEWS>
 PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
     if (n >= P.n_end) { sm[M.lid + el] = 0xffffffffu; return; }
-    const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
+    uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
     sm[M.lid + el] = lid;
     const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
     const uint32_t *walls = lay + pm_l_walls(P.HW);
@@ -693,14 +710,24 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     // belong to the terminal step; state, the four observations and the legal masks below are
     // CaptureRules.newGame's (capture.py:369-382, game.py:490-508). ----
     if (term && P.auto_reset) {
+        episode += 1;
+        if (P.layout_pool) {                            // a new maze per episode (gymPacMan.py:98-100)
+            lid = pm_pool_layout(P.bot_seed, (unsigned long long)(P.n_base + n), episode, P.L);
+            P.layout_id_rw[n] = lid;
+            sm[M.lid + el] = lid;
+            lay = P.layouts + (size_t)lid * P.LS;
+            walls = lay + pm_l_walls(P.HW);
+            tail = lay + pm_l_tail(P.HW);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t s0 = tail[PM_L_START + i];
+            g.sx[i] = s0 & 0xff; g.sy[i] = (s0 >> 8) & 0xff;
             g.x[i] = g.sx[i]; g.y[i] = g.sy[i]; g.dir[i] = 4; g.pac[i] = (s0 >> 16) & 1; g.scared[i] = 0;
             g.carry[i] = 0; g.ret[i] = 0;
             snap[i] = s0 & 0xffff;
         }
-        score = 0; steps = 0; episode += 1;
+        score = 0; steps = 0;
         rf = (int)(tail[PM_L_FOODCNT] & 0xffff); bf = (int)(tail[PM_L_FOODCNT] >> 16);
         for (int w = 0; w < NW; ++w) {
             const uint32_t f = lay[pm_l_food(P.HW) + w];
@@ -770,7 +797,16 @@ template <int MODE, int VIEWS>
 PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm, const PmSmem &M, int el, int64_t n0) {
     const int64_t n = n0 + el;
     if (n >= P.n_end || (MODE == PM_MODE_RESET && P.mask && !P.mask[n])) { sm[M.lid + el] = 0xffffffffu; return; }
-    const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
+    uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
+    // episode counter: a full reset (mask == NULL) restarts it, a masked reset of an initialised batch advances it
+    uint32_t episode = 0;
+    if (MODE == PM_MODE_RESET) {
+        episode = P.mask ? reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n].w + 1u : 0u;
+        if (P.layout_pool) {                            // a new maze per episode (gymPacMan.py:98-100)
+            lid = pm_pool_layout(P.bot_seed, (unsigned long long)(P.n_base + n), episode, P.L);
+            P.layout_id_rw[n] = lid;
+        }
+    }
     sm[M.lid + el] = lid;
     const uint32_t *lay = (P.L == 1) ? st + M.lay : P.layouts + (size_t)lid * P.LS;
     const uint32_t *tail = lay + pm_l_tail(P.HW);
@@ -794,9 +830,8 @@ PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm,
         A.x = a[0]; A.y = a[1]; A.z = a[2]; A.w = a[3];
         B.x = B.y = B.z = B.w = 0;
         S.x = s[0]; S.y = s[1]; S.z = s[2]; S.w = s[3];
-        // episode counter: a full reset (mask == NULL) restarts it, a masked reset of an initialised batch advances it
         Mi.x = 0; Mi.y = 0; Mi.z = tail[PM_L_FOODCNT];
-        Mi.w = P.mask ? reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n].w + 1u : 0u;
+        Mi.w = episode;
         reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
         reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
         reinterpret_cast<pm_u4 *>(P.state + pm_st_snap(P.N))[n] = S;
@@ -1142,6 +1177,31 @@ PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t
     }
 }
 
+// ============================================================================
+// phase B'': packed observations (pm_step_out.obs_bits) for a host-side consumer
+// ============================================================================
+// The bit string the fp32 encoder expands is itself the output: NCAT words per observation, one patch word
+// (own-cell element index | value << 16, or 0xFFFFFFFF), zero padding up to NB words.  One warp per
+// observation, consecutive lanes = consecutive words (a 144-byte run on tinyCapture).
+template <int MODE>
+PM_HD void pm_phaseB_bits(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps,
+                          int lane, int64_t n0) {
+    const int NCAT = P.NCAT, NB = P.NB, E = P.E;
+    for (int u = warp; u < 4 * E; u += nwarps) {
+        const int k = u >> P.lgE, el = u & (E - 1);
+        PmUnit U;
+        if (!pm_unit_load<MODE>(P, sm, M, k, el, U)) continue;
+        uint32_t *dst = P.obs_bits + (size_t)k * P.obs_bits_stride + (size_t)(n0 + el) * NB;
+#if defined(__CUDA_ARCH__)
+        for (int j = lane; j < NB; j += 32)
+#else
+        if (lane != 0) continue;                        // host emulation: lane 0 plays the whole warp
+        for (int j = 0; j < NB; ++j)
+#endif
+            dst[j] = j < NCAT ? pm_cat_word(P, st, M, U, j) : (j == NCAT ? U.patch : 0u);
+    }
+}
+
 // ---- pm_env_desc -> PmParams (shared by the C ABI glue and the test emulation) ----
 #ifdef PACMAN_B200_H
 static inline int pm_fill_params(const pm_env_desc *d, PmParams &P, int E) {
@@ -1156,6 +1216,13 @@ static inline int pm_fill_params(const pm_env_desc *d, PmParams &P, int E) {
     P.ND = pm_nd(P.W, P.H); P.LS = pm_layout_words_(P.HW);
     P.L = d->n_layouts; P.has_caps = d->has_caps != 0; P.N = d->n_envs;
     P.geom = d->geom; P.layouts = d->layouts; P.layout_id = d->layout_id; P.state = (uint8_t *)d->state;
+    P.layout_pool = d->layout_pool != 0 && d->n_layouts > 1;
+    if (d->layout_pool && !d->layout_id) return PM_EINVAL;
+    P.layout_id_rw = const_cast<uint32_t *>(d->layout_id);
+    P.bot_draws = d->bot_draws;
+    P.NB = pm_obs_bits_words_(P.HW);
+    if (d->envs_per_cta != 0 && d->envs_per_cta != 8 && d->envs_per_cta != 32) return PM_EINVAL;
+    P.epc = d->envs_per_cta;
     P.length = d->length; P.reward_legal = d->reward_for_legal_action != 0; P.defence = d->defence_reward != 0;
     P.shaping_scale = d->shaping_scale;
     P.bot_kind = 0;

@@ -35,6 +35,8 @@ enum { PM_G_W = 0, PM_G_H, PM_G_HW, PM_G_NW, PM_G_NCAT, PM_G_ND, PM_G_LS, PM_G_R
 
 PM_HD int pm_nw(int HW) { return (HW + 31) >> 5; }
 PM_HD int pm_ncat(int HW) { return (8 * HW + 31) >> 5; }
+// packed observation (pm_step_out.obs_bits): NCAT bit-string words + 1 patch word, padded to a multiple of 4 words
+PM_HD int pm_obs_bits_words_(int HW) { return (pm_ncat(HW) + 1 + 3) & ~3; }
 PM_HD int pm_dump_radius(int W, int H) { return (W > H ? W : H) - 1; }
 PM_HD int pm_nd(int W, int H) { int r = pm_dump_radius(W, H); return (2 * r + 1) * (2 * r + 1); }
 #define PM_G_NMASKS 8

@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(256) pm_adv_norm_kernel(const float *__restric
     const float mean = block_sum(part, red) / (float)k;
     part = 0.f;
     for (int i = threadIdx.x; i < k; i += blockDim.x) { const float dlt = adv[inds[s + i]] - mean; part += dlt * dlt; }
-    const float var = block_sum(part, red) / (float)(k - 1);
+    // unbiased variance; a trailing group of ONE sample has none (torch.std gives NaN there): treat it as 0, so the
+    // lone sample normalises to (a - a) / 1e-8 = 0 instead of poisoning the loss
+    const float ssq = block_sum(part, red);
+    const float var = k > 1 ? ssq / (float)(k - 1) : 0.0f;
     const float denom = sqrtf(var) + 1e-8f;
     for (int i = threadIdx.x; i < k; i += blockDim.x) out[s + i] = (adv[inds[s + i]] - mean) / denom;
 }

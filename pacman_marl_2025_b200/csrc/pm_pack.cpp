@@ -23,6 +23,7 @@ static int check_dims(int W, int H) {
 
 extern "C" int pm_geom_words(int W, int H) { return check_dims(W, H) ? check_dims(W, H) : pm_geom_words_(W, H); }
 extern "C" int pm_layout_words(int W, int H) { return check_dims(W, H) ? check_dims(W, H) : pm_layout_words_(W * H); }
+extern "C" int pm_obs_bits_words(int W, int H) { return check_dims(W, H) ? check_dims(W, H) : pm_obs_bits_words_(W * H); }
 extern "C" size_t pm_state_bytes(int W, int H, int64_t n_envs) {
     if (check_dims(W, H) || n_envs <= 0) return 0;
     return pm_state_bytes_(n_envs, W * H);

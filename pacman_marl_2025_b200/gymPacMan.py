@@ -48,6 +48,33 @@ def legal_mask_to_list(mask: int) -> List[int]:
     return [a for a in LEGAL_LIST_ORDER if (int(mask) >> a) & 1]
 
 
+def decode_obs_bits(bits, H: int, W: int):
+    """Packed observations (``set_bits_output`` / ``observe_bits``; numpy or torch int32 [..., NB]) -> float32
+    [..., 8, H, W], the tensors ``get_Observation`` returns (gymPacMan.py:195-229).  Host-side helper for consumers
+    of the packed format; runs on whatever device / library the input lives on."""
+    HW = H * W
+    ncat = (8 * HW + 31) // 32
+    if isinstance(bits, torch.Tensor):
+        w = bits[..., :ncat].to(torch.int64) & 0xFFFFFFFF
+        sh = torch.arange(32, device=bits.device, dtype=torch.int64)
+        planes = ((w.unsqueeze(-1) >> sh) & 1).reshape(*bits.shape[:-1], ncat * 32)[..., :8 * HW].to(torch.float32)
+        patch = bits[..., ncat].to(torch.int64) & 0xFFFFFFFF
+        has = patch != 0xFFFFFFFF
+        idx = torch.where(has, patch & 0xFFFF, torch.zeros_like(patch))
+        val = torch.where(has, (patch >> 16).to(torch.float32), planes.gather(-1, idx.unsqueeze(-1)).squeeze(-1))
+        planes.scatter_(-1, idx.unsqueeze(-1), val.unsqueeze(-1))
+        return planes.reshape(*bits.shape[:-1], 8, H, W)
+    b = np.ascontiguousarray(bits).view(np.uint32)
+    planes = np.unpackbits(np.ascontiguousarray(b[..., :ncat]).view(np.uint8), axis=-1, bitorder="little")[..., :8 * HW]
+    planes = planes.astype(np.float32)
+    patch = b[..., ncat]
+    flat = planes.reshape(-1, 8 * HW)
+    pf = patch.reshape(-1)
+    rows = np.nonzero(pf != 0xFFFFFFFF)[0]
+    flat[rows, pf[rows] & 0xFFFF] = (pf[rows] >> 16).astype(np.float32)
+    return flat.reshape(*b.shape[:-1], 8, H, W)
+
+
 def pack_tables(layouts: Sequence[_layout.Layout]):
     """Layout objects -> (geom[u32], table[L, LS] u32, has_caps) via the library's host packer."""
     L = _lib.load()
@@ -69,6 +96,41 @@ def pack_tables(layouts: Sequence[_layout.Layout]):
         _lib.check(L.pm_pack_layout(text.encode("ascii"), W, H, table[i].ctypes.data, C.byref(hc)), "pm_pack_layout")
         has_caps |= hc.value
     return geom, table, has_caps
+
+
+class OnDeviceAgent:
+    """Stands where the reference keeps the bot object of a red agent (``env.agents[0]``, ``env.agents[2]`` in
+    non-self-play, gymPacMan.py:33-40).  The bot itself runs inside the step kernel at its own sub-move; what it
+    played comes back in ``actions_used``."""
+
+    def __init__(self, index: int, team: str, kind: int):
+        self.index, self.team, self.kind = index, team, kind
+        self.red = True
+
+    def registerInitialState(self, state):
+        pass
+
+    def getAction(self, state):
+        raise RuntimeError(f"agent {self.index} ({self.team}) decides inside the step kernel; its moves are reported "
+                           "in the step's actions_used output")
+
+    def __repr__(self):
+        return f"OnDeviceAgent(index={self.index}, team={self.team!r})"
+
+
+class _AgentDict(dict):
+    """The dicts ``reset`` / ``step`` return are keyed like the reference's: by ``env.agents[i]`` - ints, or the bot
+    objects of the red agents in non-self-play (gymPacMan.py:186).  Plain agent indices resolve too."""
+
+    def __init__(self, agents, items):
+        super().__init__(items)
+        self._agents = agents
+
+    def __missing__(self, k):
+        if isinstance(k, int) and not isinstance(k, bool) and 0 <= k < len(self._agents) and self._agents[k] is not k \
+                and dict.__contains__(self, self._agents[k]):
+            return dict.__getitem__(self, self._agents[k])
+        raise KeyError(k)
 
 
 class _AgentStateView:
@@ -107,11 +169,7 @@ class _StateView:
         self.data = self
 
     def _pull(self):
-        e = self._env
-        if e._state_cache_version != e._version:
-            e._state_cache = e.export_state()
-            e._state_cache_version = e._version
-        return e._state_cache
+        return self._env.cached_state()
 
     # GameStateData-ish
     @property
@@ -227,7 +285,7 @@ class gymPacMan_parallel_env:
                  self_play=False, *, num_envs: int = 1, device=None, layouts: Optional[Sequence] = None,
                  shaping_scale: float = 0.1, opponent_seed: int = 0, auto_reset: bool = False,
                  env_index_base: int = 0, opponent_tiebreak: str = "random", layout_ids=None,
-                 bot_team=None, state_factory=None):
+                 bot_team=None, state_factory=None, layout_pool: int = 0, envs_per_cta: int = 0):
         if display:
             raise NotImplementedError("display=True (tkinter viewer) is outside the batched GPU path")
         if not torch.cuda.is_available():
@@ -253,8 +311,8 @@ class gymPacMan_parallel_env:
         self.reversed_action_mapping = {"North": 0, "East": 1, "South": 2, "West": 3, "Stop": 4,
                                         0: 0, 1: 1, 2: 2, 3: 3, 4: 4}
         self._name_to_int = {"North": 0, "East": 1, "South": 2, "West": 3, "Stop": 4}
-        # agent keys: ints in self-play (gymPacMan.py:33-40).  Without self-play the red side is driven by an
-        # on-device opponent and still addressed by its index.
+        # agent keys (gymPacMan.py:33-40): ints in self-play; without self-play agents 0 and 2 are the red team's bot
+        # objects - the caller's host bots, or OnDeviceAgent placeholders for the teams that run inside the kernel
         self.agents = [0, 1, 2, 3]
         # host-side opponents (the reference's agents/*.py teams): two objects with getAction(state) [and
         # registerInitialState(state)] playing agents 0 and 2 at their own sub-move; `state_factory(env, n)` builds
@@ -273,6 +331,8 @@ class gymPacMan_parallel_env:
             raise ValueError("opponent_tiebreak must be 'random' (random.choice, baselineTeam.py:92) or 'first'")
         self._opponent_tiebreak = opponent_tiebreak
         self._opponent_seed = int(opponent_seed)
+        self._envs_per_cta = int(envs_per_cta)
+        self._submoves_in_step = 0
         # batched extensions: restart finished envs inside the step launch; global index of env 0 when
         # this batch is one shard of a larger one (keys the on-device opponent's random draws)
         self.auto_reset = bool(auto_reset)
@@ -280,38 +340,82 @@ class gymPacMan_parallel_env:
         # with several `layouts`: env n plays layouts[layout_ids[n]] (default: n % len(layouts))
         self._layout_ids_arg = layout_ids
 
+        # random_layout: the reference draws a NEW maze on every reset (gymPacMan.py:98-100 -> capture.py:905-911).
+        # One env does exactly that (host generator, same global-RNG draw).  A batch keeps a POOL of `layout_pool`
+        # host-generated mazes on the device and every env moves to pool[hash(seed, env, episode) % pool] whenever
+        # it (re)starts - inside pm_reset / the auto_reset of pm_step (pm_env_desc.layout_pool).
+        self._pool_mode = False
+        self._pool_epoch = 0
         if layouts is not None:
             lays = [l if isinstance(l, _layout.Layout) else _layout.Layout(list(l)) for l in layouts]
+            self._pool_mode = bool(layout_pool) and len(lays) > 1
         elif os.path.exists(layout_file) and not random_layout:
             lays = [_layout.getLayout(layout_file)]
+        elif self.num_envs > 1:
+            lays = [_layout.Layout(_maze.randomLayout().split("\n")) for _ in range(int(layout_pool) or 256)]
+            self._pool_mode = len(lays) > 1
         else:
             lays = [_layout.Layout(_maze.randomLayout().split("\n"))]
-        self._install_layouts(lays)
         self._version = 0
         self._state_cache_version = -1
         self._state_cache = None
+        self._install_layouts(lays)
         self.game = _GameView(self)
-        self.reset()
+        self.reset(_first=True)
         self.max_score = int(self.game.state.getBlueFood().count())
 
     # ------------------------------------------------------------------ setup
+    _CACHED = ("_mapped_out", "_rec_mapped", "_rec_mapped_views", "_rec_np", "_pipe_out", "_rec_dev", "_rec_host",
+               "_rec_views", "_host", "_host_out", "_act_dev", "_views", "_bits")
+
     def _install_layouts(self, lays: List[_layout.Layout]):
-        self._layouts = lays
-        self.layout = lays[0]
-        W, H = self.layout.width, self.layout.height
+        """(Re)build the device tables for `lays`.  Boards of the size already installed are copied into the existing
+        tables, so every device buffer (and every cached descriptor that points into one) stays where it is; a new
+        board size reallocates and drops the cached descriptors and host staging buffers."""
+        W, H = lays[0].width, lays[0].height
         geom, table, has_caps = pack_tables(lays)
         dev = self.device
-        self._geom = torch.from_numpy(geom.view(np.int32)).to(dev)
-        self._table = torch.from_numpy(table.view(np.int32)).to(dev)
         N = self.num_envs
-        nbytes = int(self._L.pm_state_bytes(W, H, N))
-        self._state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-        self._desc = _lib.PmEnvDesc(W, H, len(lays), int(has_caps), N, self._geom.data_ptr(), self._table.data_ptr(),
-                                    None, self._state.data_ptr(), int(self.length), int(bool(self.reward_forLegalAction)),
-                                    int(bool(self.defenceReward)), 0,
-                                    self.shaping_scale, int(self._opponent_seed), int(self.auto_reset), 0,
-                                    self.env_index_base, 0, 0)
-        if self._layout_ids_arg is not None and len(lays) > 1:
+        self._layouts = lays
+        self.layout = lays[0]
+        key = (W, H, len(lays))
+        if getattr(self, "_alloc_key", None) == key:
+            self._table.copy_(torch.from_numpy(table.view(np.int32)))
+            self._desc.has_caps = int(has_caps)
+        else:
+            for name in self._CACHED:                  # they hold pointers / strides of the buffers replaced below
+                self.__dict__.pop(name, None)
+            self._alloc_key = key
+            self._geom = torch.from_numpy(geom.view(np.int32)).to(dev)
+            self._table = torch.from_numpy(table.view(np.int32)).to(dev)
+            nbytes = int(self._L.pm_state_bytes(W, H, N))
+            self._state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self._desc = _lib.PmEnvDesc(W, H, len(lays), int(has_caps), N, self._geom.data_ptr(), self._table.data_ptr(),
+                                        None, self._state.data_ptr(), int(self.length),
+                                        int(bool(self.reward_forLegalAction)), int(bool(self.defenceReward)), 0,
+                                        self.shaping_scale, int(self._opponent_seed), int(self.auto_reset),
+                                        self._envs_per_cta, self.env_index_base, 0, 0)
+            self.obs_shape = (8, H, W)
+            self._obs = torch.empty((4, N, 8, H, W), dtype=torch.float32, device=dev)
+            self._reward = torch.zeros((2, N), dtype=torch.float64, device=dev)
+            self._done = torch.zeros(N, dtype=torch.uint8, device=dev)
+            self._legal = torch.zeros((N, 4), dtype=torch.uint8, device=dev)
+            self._score_change = torch.zeros(N, dtype=torch.int32, device=dev)
+            self._shaping = torch.zeros((4, N), dtype=torch.float64, device=dev)
+            self._shaped = torch.zeros((4, N), dtype=torch.float32, device=dev)
+            self._actions_used = torch.zeros((N, 4), dtype=torch.uint8, device=dev)
+            self._step_out = _lib.PmStepOut(self._obs.data_ptr(), self._obs[0].numel(), self._reward.data_ptr(),
+                                            self._done.data_ptr(), self._legal.data_ptr(), self._score_change.data_ptr(),
+                                            self._shaping.data_ptr(), self._shaped.data_ptr(), None,
+                                            self._actions_used.data_ptr())
+            self._layout_id = None
+        self._desc.layout_pool = int(self._pool_mode and len(lays) > 1)
+        if self._pool_mode and len(lays) > 1:
+            if self._layout_id is None:
+                self._layout_id = torch.zeros(N, dtype=torch.int32, device=dev)      # written by the kernels
+            self._layout_id_host = None
+            self._desc.layout_id = self._layout_id.data_ptr()
+        elif self._layout_ids_arg is not None and len(lays) > 1:
             ids = torch.as_tensor(np.asarray(self._layout_ids_arg), dtype=torch.int32)
             if ids.numel() != N or int(ids.min()) < 0 or int(ids.max()) >= len(lays):
                 raise ValueError("layout_ids must hold one index into `layouts` per env")
@@ -320,30 +424,25 @@ class gymPacMan_parallel_env:
             self._desc.layout_id = self._layout_id.data_ptr()
         else:
             self._layout_id_host = None
+            self._desc.layout_id = None
         self._set_opponent(self.enemieName)
-        self.obs_shape = (8, H, W)
-        self._obs = torch.empty((4, N, 8, H, W), dtype=torch.float32, device=dev)
-        self._reward = torch.zeros((2, N), dtype=torch.float64, device=dev)
-        self._done = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self._legal = torch.zeros((N, 4), dtype=torch.uint8, device=dev)
-        self._score_change = torch.zeros(N, dtype=torch.int32, device=dev)
-        self._shaping = torch.zeros((4, N), dtype=torch.float64, device=dev)
-        self._shaped = torch.zeros((4, N), dtype=torch.float32, device=dev)
-        self._actions_used = torch.zeros((N, 4), dtype=torch.uint8, device=dev)
-        self._step_out = _lib.PmStepOut(self._obs.data_ptr(), self._obs[0].numel(), self._reward.data_ptr(),
-                                        self._done.data_ptr(), self._legal.data_ptr(), self._score_change.data_ptr(),
-                                        self._shaping.data_ptr(), self._shaped.data_ptr(), None,
-                                        self._actions_used.data_ptr())
+        self._version += 1
 
     def _set_opponent(self, name):
         """Red side = the named on-device team (loadAgents(True, ...) puts bots on agents 0 and 2,
         gymPacMan.py:33-40).  baselineTeam needs the maze-distance tables: every reset of the reference
         rebuilds them per bot (captureAgents.py:91-109); here one BFS launch per layout set."""
         d = self._desc
-        if self.self_play or self._bot_team is not None:
+        if self.self_play:
             d.bot_kind = 0
+            self.agents = [0, 1, 2, 3]
+            return
+        if self._bot_team is not None:
+            d.bot_kind = 0
+            self.agents = [self._bot_team[0], 1, self._bot_team[1], 3]
             return
         k0, k2 = ON_DEVICE_TEAMS[name]
+        self.agents = [OnDeviceAgent(0, name, k0), 1, OnDeviceAgent(2, name, k2), 3]
         d.bot_kind = k0 | (k2 << 8)
         d.bot_first_best = int(self._opponent_tiebreak == "first")
         if max(k0, k2) >= 2 and getattr(self, "_dist_for", None) is not self._layouts:
@@ -355,9 +454,18 @@ class gymPacMan_parallel_env:
             d.dist, d.node_of_cell, d.dist_nmax = t.dist.data_ptr(), t.node_of_cell.data_ptr(), int(t.dist.shape[1])
 
     def _layout_of(self, n):
+        if self._pool_mode and len(self._layouts) > 1:
+            return self._layouts[int(self.cached_state()["layout_id"][n])]
         if getattr(self, "_layout_id_host", None) is not None:
             return self._layouts[int(self._layout_id_host[n])]
         return self._layouts[n % len(self._layouts)]
+
+    def cached_state(self):
+        """``export_state()`` of the current state, pulled from the device at most once per step / sub-move launch."""
+        if self._state_cache_version != self._version:
+            self._state_cache = self.export_state()
+            self._state_cache_version = self._version
+        return self._state_cache
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -371,6 +479,11 @@ class gymPacMan_parallel_env:
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             mptr = mask.data_ptr()
+        elif self._pool_mode:
+            # a full reset restarts the episode counters; a fresh epoch in the seed keeps the boards (and the
+            # on-device opponents' draws) of successive rollouts from repeating
+            self._desc.random_seed = (self._opponent_seed + 0x9E3779B97F4A7C15 * self._pool_epoch) & 0xFFFFFFFFFFFFFFFF
+            self._pool_epoch += 1
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_reset(C.byref(self._desc), mptr, self._obs.data_ptr(), self._obs[0].numel(),
                                         self._legal.data_ptr(), self._stream()), "pm_reset")
@@ -387,17 +500,7 @@ class gymPacMan_parallel_env:
         actions = actions.contiguous()
         if actions.numel() != 4 * self.num_envs:
             raise ValueError(f"expected {self.num_envs}x4 actions, got {tuple(actions.shape)}")
-        with torch.cuda.device(self.device):
-            _lib.check(self._L.pm_step(C.byref(self._desc), actions.data_ptr(), actions.element_size(),
-                                       C.byref(self._step_out), self._stream()), "pm_step")
-        self._version += 1
-        self.steps += 1
-        out = dict(obs=self._obs, reward=self._reward, done=self._done, legal=self._legal,
-                   score_change=self._score_change, shaping=self._shaping, shaped_reward=self._shaped,
-                   actions_used=self._actions_used)
-        if getattr(self, "_views", None):
-            out["view_actor"], out["view_critic"] = self._views[0], self._views[1]
-        return out
+        return self._launch_step(actions)
 
     # ---- learner views: the trainer's network inputs written by the encoder (pm_step_out.view_*) ----
     def set_view_outputs(self, red: Optional[bool], actor: Optional[torch.Tensor] = None,
@@ -410,6 +513,8 @@ class gymPacMan_parallel_env:
         4*32*H*W).  Returns (actor, critic)."""
         so = self._step_out
         so.obs = self._obs.data_ptr() if raw_obs else None
+        self.__dict__.pop("_mapped_out", None)           # the host-step descriptors mirror these pointers: rebuild them
+        self.__dict__.pop("_pipe_out", None)
         if red is None:
             so.view_actor, so.view_critic = None, None
             self._views = None
@@ -431,6 +536,42 @@ class gymPacMan_parallel_env:
         self._views = (actor, critic, bool(red))
         return actor, critic
 
+    # ---- packed observations: the 8*H*W-bit string + own-cell patch per observation (pm_step_out.obs_bits) ----
+    def obs_bits_words(self) -> int:
+        return int(self._L.pm_obs_bits_words(self.layout.width, self.layout.height))
+
+    def set_bits_output(self, on: bool = True, raw_obs: bool = True, host_mapped: bool = False):
+        """Make every following step also write the PACKED observations: int32 [4, N, NB] words (NB =
+        ``obs_bits_words()``; layout in include/pacman_b200.h).  144 B per observation on tinyCapture instead of
+        4 480 B of fp32 - the format for a consumer on the host.  ``host_mapped=True`` puts the buffer in pinned
+        host memory that the kernel writes itself across PCIe (use with ``step_host_mapped``).  ``raw_obs=False``
+        skips the fp32 observations.  Returns the buffer (``decode_obs_bits`` expands it)."""
+        so = self._step_out
+        so.obs = self._obs.data_ptr() if raw_obs else None
+        if not on:
+            so.obs_bits = None
+            self._bits = None
+            self.__dict__.pop("_mapped_out", None)
+            return None
+        NB = self.obs_bits_words()
+        if host_mapped:
+            bits = torch.zeros((4, self.num_envs, NB), dtype=torch.int32).pin_memory()
+        else:
+            bits = torch.zeros((4, self.num_envs, NB), dtype=torch.int32, device=self.device)
+        so.obs_bits, so.obs_bits_agent_stride = bits.data_ptr(), bits.stride(0)
+        self._bits = bits
+        self.__dict__.pop("_mapped_out", None)           # rebuilt with the new pointers on the next mapped step
+        return bits
+
+    def observe_bits(self, out: Optional[torch.Tensor] = None):
+        """Packed observations of the CURRENT state (e.g. right after a reset): int32 [4, N, NB] on the device."""
+        if out is None:
+            out = torch.zeros((4, self.num_envs, self.obs_bits_words()), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_observe_bits(C.byref(self._desc), out.data_ptr(), out.stride(0), self._stream()),
+                       "pm_observe_bits")
+        return out
+
     def observe_views(self, red: bool, actor: Optional[torch.Tensor] = None, critic: Optional[torch.Tensor] = None):
         """The learner views of the CURRENT state (e.g. right after a reset)."""
         N, shp = self.num_envs, self.obs_shape
@@ -443,11 +584,14 @@ class gymPacMan_parallel_env:
                                                 critic.data_ptr(), self._stream()), "pm_observe_views")
         return actor, critic
 
-    def step_host(self, actions_host: torch.Tensor, want_obs: bool = False):
+    def step_host(self, actions_host: torch.Tensor, want_obs: bool = False, want_views: bool = False,
+                  want_bits: bool = False):
         """One step with HOST buffers through the C ABI's ``pm_step_host``: ``actions_host``
         is a CPU uint8 [N,4] tensor (pinned memory makes the copy asynchronous);
         rewards / done / legal / score_change / shaped rewards come back in pinned
         host tensors; observations stay in HBM (``self._obs``) unless ``want_obs``.
+        ``want_views`` / ``want_bits`` also bring the uint8 learner views (``set_view_outputs``) / the packed
+        observations (``set_bits_output``) to pinned host tensors ``view_actor``, ``view_critic`` / ``obs_bits``.
         The call returns after the stream has been synchronised."""
         if actions_host.device.type != "cpu" or actions_host.dtype != torch.uint8 or not actions_host.is_contiguous():
             raise ValueError("actions_host must be a contiguous CPU uint8 [N,4] tensor")
@@ -464,11 +608,26 @@ class gymPacMan_parallel_env:
             self._host_out = _lib.PmStepOut(None, 0, h["reward"].data_ptr(), h["done"].data_ptr(), h["legal"].data_ptr(),
                                             h["score_change"].data_ptr(), None, h["shaped_reward"].data_ptr())
         ho = self._host_out
+        if want_obs or want_views or want_bits:
+            ho = _lib.PmStepOut(None, 0, ho.reward, ho.done, ho.legal, ho.score_change, None, ho.shaped_reward)
         if want_obs:
             if "obs" not in self._host:
                 self._host["obs"] = torch.empty(self._obs.shape, dtype=torch.float32).pin_memory()
-            ho = _lib.PmStepOut(self._host["obs"].data_ptr(), self._obs[0].numel(), ho.reward, ho.done, ho.legal,
-                                ho.score_change, None, ho.shaped_reward)
+            ho.obs, ho.obs_agent_stride = self._host["obs"].data_ptr(), self._obs[0].numel()
+        if want_views:
+            if not getattr(self, "_views", None):
+                raise RuntimeError("want_views needs set_view_outputs(...) first")
+            if "view_actor" not in self._host:
+                self._host["view_actor"] = torch.empty(self._views[0].shape, dtype=torch.uint8).pin_memory()
+                self._host["view_critic"] = torch.empty(self._views[1].shape, dtype=torch.uint8).pin_memory()
+            ho.view_actor, ho.view_actor_stride = self._host["view_actor"].data_ptr(), self._host["view_actor"].stride(0)
+            ho.view_critic = self._host["view_critic"].data_ptr()
+        if want_bits:
+            if getattr(self, "_bits", None) is None or self._bits.device.type != "cuda":
+                raise RuntimeError("want_bits needs set_bits_output(on=True, host_mapped=False) first")
+            if "obs_bits" not in self._host:
+                self._host["obs_bits"] = torch.empty(self._bits.shape, dtype=torch.int32).pin_memory()
+            ho.obs_bits, ho.obs_bits_agent_stride = self._host["obs_bits"].data_ptr(), self._host["obs_bits"].stride(0)
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host(C.byref(self._desc), actions_host.data_ptr(), self._act_dev.data_ptr(),
                                             C.byref(self._step_out), C.byref(ho), self._stream()), "pm_step_host")
@@ -498,12 +657,13 @@ class gymPacMan_parallel_env:
         if not hasattr(self, "_rec_host"):
             self._rec_dev = torch.empty((N, 48), dtype=torch.uint8, device=self.device)
             self._rec_host = torch.empty((N, 48), dtype=torch.uint8).pin_memory()
-            if not hasattr(self, "_act_dev"):
-                self._act_dev = torch.empty((N, 4), dtype=torch.uint8, device=self.device)
+            self._rec_views = self._record_views(self._rec_host)
+        if not hasattr(self, "_act_dev"):
+            self._act_dev = torch.empty((N, 4), dtype=torch.uint8, device=self.device)
+        if not hasattr(self, "_pipe_out"):
             so = self._step_out
             self._pipe_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None,
                                             self._rec_dev.data_ptr())
-            self._rec_views = self._record_views(self._rec_host)
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host_pipelined(C.byref(self._desc), self._pipe, actions_host.data_ptr(),
                                                       self._act_dev.data_ptr(), C.byref(self._pipe_out),
@@ -527,12 +687,7 @@ class gymPacMan_parallel_env:
             raise ValueError("actions_host must be a contiguous, pinned CPU uint8 [N,4] tensor")
         if actions_host.numel() != 4 * self.num_envs:
             raise ValueError(f"expected {self.num_envs}x4 actions")
-        if not hasattr(self, "_rec_mapped"):
-            self._rec_mapped = torch.zeros((self.num_envs, 48), dtype=torch.uint8).pin_memory()
-            self._rec_mapped_views = self._record_views(self._rec_mapped)
-            so = self._step_out
-            self._mapped_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None, None,
-                                              self._actions_used.data_ptr())
+        self._ensure_mapped()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host_mapped(C.byref(self._desc), actions_host.data_ptr(),
                                                    C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
@@ -540,6 +695,21 @@ class gymPacMan_parallel_env:
         self._version += 1
         self.steps += 1
         return self._rec_mapped_views
+
+    def _ensure_mapped(self):
+        """Pinned record buffer + the pm_step_out the zero-copy entry uses (observations / views / packed bits as the
+        env is currently configured; the small outputs travel in the records)."""
+        if not hasattr(self, "_rec_mapped"):
+            self._rec_mapped = torch.zeros((self.num_envs, 48), dtype=torch.uint8).pin_memory()
+            self._rec_mapped_views = self._record_views(self._rec_mapped)
+            dt = np.dtype([("reward", "<f8", 2), ("shaped", "<f4", 4), ("score_change", "<i4"), ("legal", "u1", 4),
+                           ("done", "u1"), ("pad", "u1", 7)])
+            self._rec_np = self._rec_mapped.numpy().view(dt)[:, 0]
+        if not hasattr(self, "_mapped_out"):
+            so = self._step_out
+            self._mapped_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None, None,
+                                              self._actions_used.data_ptr(), so.view_actor, so.view_actor_stride,
+                                              so.view_critic, so.view_red, 0, so.obs_bits, so.obs_bits_agent_stride)
 
     def __del__(self):
         try:
@@ -565,20 +735,28 @@ class gymPacMan_parallel_env:
         ag = torch.empty((N, 4, 7), dtype=torch.int32, device=dev)
         food = torch.empty((N, HW), dtype=torch.uint8, device=dev)
         caps = torch.empty((N, HW), dtype=torch.uint8, device=dev)
-        misc = torch.empty((N, 2), dtype=torch.int32, device=dev)
+        misc = torch.empty((N, 3), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(self._L.pm_get_state(C.byref(self._desc), ag.data_ptr(), food.data_ptr(), caps.data_ptr(),
                                             misc.data_ptr(), self._stream()), "pm_get_state")
         misc = misc.cpu().numpy()
-        return dict(agents=ag.cpu().numpy(), food=food.cpu().numpy(), caps=caps.cpu().numpy(),
-                    score=misc[:, 0].copy(), steps=misc[:, 1].copy())
+        out = dict(agents=ag.cpu().numpy(), food=food.cpu().numpy(), caps=caps.cpu().numpy(),
+                   score=misc[:, 0].copy(), steps=misc[:, 1].copy(), episode=misc[:, 2].copy())
+        if self._layout_id is not None:
+            out["layout_id"] = self._layout_id.cpu().numpy()
+        return out
 
-    def import_state(self, agents, food, caps, score, steps):
-        """Inverse of :meth:`export_state` (checkpoint restore / crafted test states)."""
+    def import_state(self, agents, food, caps, score, steps, episode=None, layout_id=None):
+        """Inverse of :meth:`export_state` (checkpoint restore / crafted test states).  Valid between whole steps:
+        the parked accumulators of a step that is being played in several launches are not part of the state.
+        ``episode`` (restarts so far) keys the on-device opponents' draws and the layout pool; default 0."""
         dev = self.device
         t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(dev).contiguous()
         ag, fo, ca = t(agents, torch.int32), t(food, torch.uint8), t(caps, torch.uint8)
-        misc = t(np.stack([np.asarray(score), np.asarray(steps)], axis=1), torch.int32)
+        ep = np.zeros_like(np.asarray(score)) if episode is None else np.asarray(episode)
+        misc = t(np.stack([np.asarray(score), np.asarray(steps), ep], axis=1), torch.int32)
+        if layout_id is not None and self._layout_id is not None:
+            self._layout_id.copy_(torch.as_tensor(np.asarray(layout_id), dtype=torch.int32))
         with torch.cuda.device(dev):
             _lib.check(self._L.pm_set_state(C.byref(self._desc), ag.data_ptr(), fo.data_ptr(), ca.data_ptr(),
                                             misc.data_ptr(), self._stream()), "pm_set_state")
@@ -589,24 +767,29 @@ class gymPacMan_parallel_env:
     def _legal_dict(self):
         if self.num_envs == 1:
             m = self._legal[0].cpu().tolist()
-            return {self.agents[i]: legal_mask_to_list(m[i]) for i in range(4)}
-        return {self.agents[i]: self._legal[:, i] for i in range(4)}
+            return self._by_agent(lambda i: legal_mask_to_list(m[i]))
+        return self._by_agent(lambda i: self._legal[:, i])
+
+    def _by_agent(self, fn):
+        return _AgentDict(self.agents, ((self.agents[i], fn(i)) for i in range(4)))
 
     def _obs_dict(self):
         if self.num_envs == 1:
-            return {self.agents[i]: self._obs[i, 0].clone() for i in range(4)}
-        return {self.agents[i]: self._obs[i].clone() for i in range(4)}
+            return self._by_agent(lambda i: self._obs[i, 0].clone())
+        return self._by_agent(lambda i: self._obs[i].clone())
 
-    def reset(self, layout_file="None", enemieName="None", mask=None):
+    def reset(self, layout_file="None", enemieName="None", mask=None, _first=False):
         """gymPacMan.reset (gymPacMan.py:92-141).  ``mask`` (batched extension)
         resets only the selected envs."""
         self.steps = 0
         self.num_moves = 0
+        self._submoves_in_step = 0
         new_lays = None
         if os.path.exists(layout_file):
             new_lays = [_layout.getLayout(layout_file)]
-        if self.random_layout:
-            new_lays = [_layout.Layout(_maze.randomLayout().split("\n"))]
+            self._pool_mode = False
+        if self.random_layout and not _first and not self._pool_mode:
+            new_lays = [_layout.Layout(_maze.randomLayout().split("\n"))]      # one env: a new maze per reset, like the reference
         if new_lays is not None:
             self._install_layouts(new_lays)
         if enemieName != "None":
@@ -616,6 +799,9 @@ class gymPacMan_parallel_env:
             self._set_opponent(enemieName)
         self.reset_batched(mask)
         if self._bot_team is not None:                 # gymPacMan.py:130-132: every bot sees the initial state
+            if len(self._layouts) > 1:
+                raise NotImplementedError("host-side bots keep one start position / distance table: bot_team mode "
+                                          "needs a single layout for the whole batch")
             for b in self._bot_team:
                 if hasattr(b, "registerInitialState"):
                     b.registerInitialState(self._bot_state(0))
@@ -660,29 +846,23 @@ class gymPacMan_parallel_env:
             self._single_np[0, i] = v if 0 <= v <= 4 else 255          # out of range = illegal -> Stop, like the kernel
         # launch (the kernel reads the pinned action word and writes the pinned record), clone the observation block
         # on the same stream, and only then synchronise: one wait covers both
-        if not hasattr(self, "_rec_mapped"):
-            self.step_host_mapped(self._single_act)          # first call: allocates the record buffer (and steps)
+        self._ensure_mapped()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_step_host_mapped_async(C.byref(self._desc), self._single_act.data_ptr(),
+                                                         C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
+                                                         self._stream()), "pm_step_host_mapped_async")
             o = self._obs.clone()
-            dt = np.dtype([("reward", "<f8", 2), ("shaped", "<f4", 4), ("score_change", "<i4"), ("legal", "u1", 4),
-                           ("done", "u1"), ("pad", "u1", 7)])
-            self._rec_np = self._rec_mapped.numpy().view(dt)[:, 0]
-        else:
-            with torch.cuda.device(self.device):
-                _lib.check(self._L.pm_step_host_mapped_async(C.byref(self._desc), self._single_act.data_ptr(),
-                                                             C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
-                                                             self._stream()), "pm_step_host_mapped_async")
-                o = self._obs.clone()
-                torch.cuda.current_stream(self.device).synchronize()
-            self._version += 1
-            self.steps += 1
+            torch.cuda.current_stream(self.device).synchronize()
+        self._version += 1
+        self.steps += 1
         r = self._rec_np[0]
-        obs = {self.agents[i]: o[i, 0] for i in range(4)}
-        red, blue = float(r["reward"][0]), float(r["reward"][1])
-        rewards = {self.agents[0]: red, self.agents[1]: blue, self.agents[2]: red, self.agents[3]: blue}
+        obs = self._by_agent(lambda i: o[i, 0])
+        rb = (float(r["reward"][0]), float(r["reward"][1]))
+        rewards = self._by_agent(lambda i: rb[i & 1])
         done = bool(r["done"])
-        terms = {a: done for a in self.agents}
+        terms = self._by_agent(lambda i: done)
         legal = r["legal"]
-        info = {"legal_actions": {self.agents[i]: legal_mask_to_list(legal[i]) for i in range(4)},
+        info = {"legal_actions": self._by_agent(lambda i: legal_mask_to_list(legal[i])),
                 "score_change": int(r["score_change"])}
         return obs, rewards, terms, info
 
@@ -693,56 +873,74 @@ class gymPacMan_parallel_env:
     def _step_with_host_bots(self, actions):
         """gymPacMan.step with `bot.getAction(state)` for the red agents (gymPacMan.py:149-167): agent 0's bot sees the
         state before the step; after the launch that plays agents 0 and 1, agent 2's bot sees the state as it is
-        then; the second launch plays agents 2 and 3 and finishes the step."""
+        then; the second launch plays agents 2 and 3 and finishes the step.  The device state is exported ONCE per
+        sub-move launch for the whole batch (``cached_state``); every env's bot call reads from that copy."""
         N = self.num_envs
         a = self._gather_actions(actions).to(torch.int64).clone()             # blue columns; red filled below
         name_to_int = self._name_to_int
         out = None
         for first, (lo, hi) in ((0, (0, 2)), (2, (2, 4))):
             bot = self._bot_team[first >> 1]
-            self._version += 1                                                # invalidate the cached state view
-            for n in range(N):
-                act = bot.getAction(self._bot_state(n))
-                a[n, first] = name_to_int[act] if isinstance(act, str) else int(act)
-            self._desc.agent_begin, self._desc.agent_end = lo, hi
-            try:
-                self.steps -= 0 if hi == 4 else 1                             # step_batched counts whole steps
-                out = self.step_batched(a)
-            finally:
-                self._desc.agent_begin, self._desc.agent_end = 0, 0
+            self._submoves_in_step = lo
+            red = [bot.getAction(self._bot_state(n)) for n in range(N)]
+            a[:, first] = torch.as_tensor([name_to_int[v] if isinstance(v, str) else int(v) for v in red],
+                                          dtype=torch.int64, device=a.device)
+            out = self._launch_step(a, (lo, hi))
             self.num_moves += hi - lo
+        self._submoves_in_step = 0
+        return out
+
+    def _launch_step(self, actions, sub_moves=None):
+        """One pm_step launch; ``sub_moves=(begin, end)`` plays only those agents' sub-moves (default: what the
+        descriptor says, normally the whole step).  Counts a step when the launch finishes one."""
+        d = self._desc
+        keep = (d.agent_begin, d.agent_end)
+        if sub_moves is not None:
+            d.agent_begin, d.agent_end = sub_moves
+        end = d.agent_end
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(self._L.pm_step(C.byref(d), actions.data_ptr(), actions.element_size(),
+                                           C.byref(self._step_out), self._stream()), "pm_step")
+        finally:
+            d.agent_begin, d.agent_end = keep
+        self._version += 1
+        if end in (0, 4):
+            self.steps += 1
+        return self._out_dict()
+
+    def _out_dict(self):
+        out = dict(obs=self._obs, reward=self._reward, done=self._done, legal=self._legal,
+                   score_change=self._score_change, shaping=self._shaping, shaped_reward=self._shaped,
+                   actions_used=self._actions_used)
+        if getattr(self, "_views", None):
+            out["view_actor"], out["view_critic"] = self._views[0], self._views[1]
+        if getattr(self, "_bits", None) is not None:
+            out["obs_bits"] = self._bits
         return out
 
     def step(self, actions):
         """gymPacMan.step (gymPacMan.py:143-193)."""
         if self._bot_team is not None:
             out = self._step_with_host_bots(actions)
-            obs = self._obs_dict()
-            if self.num_envs == 1:
-                rew = out["reward"][:, 0].cpu().tolist()
-                done = bool(out["done"][0].item())
-                return (obs, {self.agents[i]: rew[i & 1] for i in range(4)}, {self.agents[i]: done for i in range(4)},
-                        {"legal_actions": self._legal_dict(), "score_change": int(out["score_change"][0].item())})
-            d = out["done"].bool()
-            return (obs, {self.agents[i]: out["reward"][i & 1].clone() for i in range(4)},
-                    {self.agents[i]: d for i in range(4)},
-                    {"legal_actions": self._legal_dict(), "score_change": out["score_change"].clone()})
-        if self.num_envs == 1 and not isinstance(actions, torch.Tensor) and not any(
+        elif self.num_envs == 1 and not isinstance(actions, torch.Tensor) and not any(
                 isinstance(actions[self.agents[i]], torch.Tensor) for i in range(4)
                 if self.self_play or i in (1, 3)):
             return self._step_single(actions)
-        out = self.step_batched(self._gather_actions(actions))
+        else:
+            out = self.step_batched(self._gather_actions(actions))
         obs = self._obs_dict()
         if self.num_envs == 1:
             rew = out["reward"][:, 0].cpu().tolist()
             done = bool(out["done"][0].item())
-            rewards = {self.agents[i]: rew[i & 1] for i in range(4)}
-            terms = {self.agents[i]: done for i in range(4)}
+            rewards = self._by_agent(lambda i: rew[i & 1])
+            terms = self._by_agent(lambda i: done)
             sc = int(out["score_change"][0].item())
         else:
-            rewards = {self.agents[i]: out["reward"][i & 1].clone() for i in range(4)}
+            rb = (out["reward"][0].clone(), out["reward"][1].clone())
+            rewards = self._by_agent(lambda i: rb[i & 1])
             d = out["done"].bool()
-            terms = {self.agents[i]: d for i in range(4)}
+            terms = self._by_agent(lambda i: d)
             sc = out["score_change"].clone()
         return obs, rewards, terms, {"legal_actions": self._legal_dict(), "score_change": sc}
 

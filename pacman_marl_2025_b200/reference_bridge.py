@@ -85,12 +85,16 @@ def to_reference_state(mods: SimpleNamespace, layout_rows: Sequence[str], agents
 
 
 def state_factory(mods: SimpleNamespace):
-    """``state_factory(env, n) -> capture.GameState`` for :class:`gymPacMan_parallel_env` (host-bot mode)."""
+    """``state_factory(env, n) -> capture.GameState`` for :class:`gymPacMan_parallel_env` (host-bot mode).
+    Reads env ``n`` out of ``env.cached_state()`` - ONE export of the device state per sub-move launch for the whole
+    batch - so asking every env's bot costs O(N), not O(N^2).  ``timeleft`` counts down from ``length`` by the
+    sub-moves this env has played in its current episode (`capture.py:122`, `:377`)."""
     def make(env, n=0):
-        s = env.export_state()
+        s = env.cached_state()
         lay = env._layout_of(n)
+        played = 4 * int(s["steps"][n]) + int(getattr(env, "_submoves_in_step", 0))
         return to_reference_state(mods, lay.layoutText, s["agents"][n], s["food"][n], s["caps"][n], int(s["score"][n]),
-                                  env.length - env.num_moves)
+                                  env.length - played)
     return make
 
 

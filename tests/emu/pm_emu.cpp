@@ -53,6 +53,9 @@ static void run(const PmParams &P) {
             for (int w = 0; w < EMU_THREADS / 32; ++w)
                 for (int lane = 0; lane < 32; ++lane)
                     pm_phaseB_views<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0, 4 + (bots ? 1 : 0));
+        if (P.obs_bits)
+            for (int w = 0; w < EMU_THREADS / 32; ++w)
+                for (int lane = 0; lane < 32; ++lane) pm_phaseB_bits<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0);
     }
 }
 
@@ -82,7 +85,14 @@ extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize,
     P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
     P.view_actor = out->view_actor; P.view_actor_stride = out->view_actor_stride; P.view_critic = out->view_critic;
     P.view_red = out->view_red;
+    P.obs_bits = out->obs_bits; P.obs_bits_stride = out->obs_bits_agent_stride;
     run<PM_MODE_STEP>(P);
+    return 0;
+}
+extern "C" int emu_observe_bits(const pm_env_desc *d, uint32_t *bits, int64_t stride, int E, int KB) {
+    PmParams P; if (int rc = fill(d, P, E, KB)) return rc;
+    P.obs_bits = bits; P.obs_bits_stride = stride;
+    run<PM_MODE_OBSERVE>(P);
     return 0;
 }
 // host mirror of pm_get_state_kernel
@@ -99,7 +109,7 @@ extern "C" int emu_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *foo
             o[0] = a[i] & 0xff; o[1] = (a[i] >> 8) & 0xff; o[2] = (a[i] >> 16) & 7; o[3] = (a[i] >> 19) & 1;
             o[4] = (a[i] >> 20) & 0xff; o[5] = b[i] & 0xffff; o[6] = b[i] >> 16;
         }
-        misc[2 * n] = (int32_t)Mi.x; misc[2 * n + 1] = (int32_t)Mi.y;
+        misc[3 * n] = (int32_t)Mi.x; misc[3 * n + 1] = (int32_t)Mi.y; misc[3 * n + 2] = (int32_t)Mi.w;
         const uint32_t *gfood = reinterpret_cast<const uint32_t *>(P.state + pm_st_food(P.N));
         const uint32_t *gcaps = reinterpret_cast<const uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
         for (int c = 0; c < P.HW; ++c) {

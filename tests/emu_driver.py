@@ -33,7 +33,8 @@ def _p(a):
 class EmuEnv:
     def __init__(self, layouts, n_envs, length=299, reward_forLegalAction=True, defenceReward=True,
                  shaping_scale=0.1, E=64, KB=4, layout_id=None, random_agent_mask=0, random_seed=0,
-                 auto_reset=False, env_index_base=0, bot_kind=None, bot_first_best=True, layout_ids=None):
+                 auto_reset=False, env_index_base=0, bot_kind=None, bot_first_best=True, layout_ids=None,
+                 layout_pool=False, bot_draws=False):
         layout_id = layout_ids if layout_ids is not None else layout_id
         L = lib()
         per_env = not isinstance(layouts[0], str)
@@ -52,12 +53,19 @@ class EmuEnv:
             has_caps |= hc.value
         self.state = np.zeros(L.pm_state_bytes(self.W, self.H, self.N), np.uint8)
         self.layout_id = None if layout_id is None else np.ascontiguousarray(layout_id, np.uint32)
+        if layout_pool:
+            self.layout_id = np.zeros(self.N, np.uint32)
         self.desc = pmlib.PmEnvDesc(self.W, self.H, len(lays), has_caps, self.N, self.geom.ctypes.data,
                                     self.layouts.ctypes.data,
                                     None if self.layout_id is None else self.layout_id.ctypes.data,
                                     self.state.ctypes.data, int(length), int(reward_forLegalAction),
                                     int(defenceReward), int(random_agent_mask), float(shaping_scale), int(random_seed),
                                     int(auto_reset), 0, int(env_index_base), 0, 0)
+        self.desc.layout_pool = int(bool(layout_pool))
+        self.draws = np.zeros((self.N, 4), np.uint32) if bot_draws else None
+        if bot_draws:
+            self.desc.bot_draws = self.draws.ctypes.data
+        self.want_bits = False
         if bot_kind is not None and any(k >= 2 for k in bot_kind):
             # maze-distance tables in pm_distances' output format, built here by the ORACLE (the CUDA BFS kernel
             # cannot run in the CPU emulation; it is checked against the same oracle in the GPU tests)
@@ -107,6 +115,20 @@ class EmuEnv:
     def set_range(self, begin=0, count=0):
         self.desc.env_begin, self.desc.env_count = int(begin), int(count)
 
+    def set_draws(self, draws):
+        """random.choice indices for the on-device bots of the next step (pm_env_desc.bot_draws)."""
+        self.draws[:] = np.asarray(draws, np.uint32).reshape(self.N, 4)
+
+    def set_bits(self, on=True):
+        self.want_bits = bool(on)
+
+    def observe_bits(self):
+        NB = lib().pm_obs_bits_words(self.W, self.H)
+        bits = np.full((4, self.N, NB), 0xEEEEEEEE, np.uint32)
+        rc = lib().emu_observe_bits(C.byref(self.desc), _p(bits), C.c_int64(bits[0].size), self.E, self.KB)
+        assert rc == 0, rc
+        return bits
+
     def step(self, actions, dtype=np.uint8):
         a = np.ascontiguousarray(np.asarray(actions).reshape(self.N, 4), dtype)
         o = dict(obs=np.full((4, self.N) + self.obs_shape, np.nan, np.float32), reward=np.zeros((2, self.N)),
@@ -123,6 +145,10 @@ class EmuEnv:
             o["view_critic"] = np.full((self.N,) + self.obs_shape, 0xEE, np.uint8)
             so.view_actor, so.view_actor_stride = o["view_actor"].ctypes.data, o["view_actor"][0].size
             so.view_critic, so.view_red = o["view_critic"].ctypes.data, int(self.view_red)
+        if self.want_bits:
+            NB = lib().pm_obs_bits_words(self.W, self.H)
+            o["obs_bits"] = np.full((4, self.N, NB), 0xEEEEEEEE, np.uint32)
+            so.obs_bits, so.obs_bits_agent_stride = o["obs_bits"].ctypes.data, o["obs_bits"][0].size
         rc = lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
         assert rc == 0, rc
         return o
@@ -132,9 +158,12 @@ class EmuEnv:
         ag = np.zeros((self.N, 4, 7), np.int32)
         food = np.zeros((self.N, HW), np.uint8)
         caps = np.zeros((self.N, HW), np.uint8)
-        misc = np.zeros((self.N, 2), np.int32)
+        misc = np.zeros((self.N, 3), np.int32)
         lib().emu_get_state(C.byref(self.desc), _p(ag), _p(food), _p(caps), _p(misc))
-        return dict(agents=ag, food=food, caps=caps, score=misc[:, 0], steps=misc[:, 1])
+        out = dict(agents=ag, food=food, caps=caps, score=misc[:, 0], steps=misc[:, 1], episode=misc[:, 2])
+        if self.layout_id is not None:
+            out["layout_id"] = self.layout_id.astype(np.int32)
+        return out
 
 
 class SingleEnvDriver:
