@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 # algorithmic bytes per agent-step = obs write 32*H*W + 1/4 of the per-env
 # state read+write, actions and small outputs.
 ALGO_BYTES_PER_AGENT_STEP = {"tinyCapture": 4529, "smallCapture": 4985, "bloxCapture": 12875}
-PY_REFERENCE_AGENT_STEPS_PER_CORE = {"tinyCapture": 1819, "smallCapture": 1554, "bloxCapture": 1031}
+REF_ROOT = os.path.join(ROOT, "baseline", "_ref")       # the unmodified Python reference (copied there by build(); git-ignored,
+                                                        # shipped to the GPU box with the snapshot)
 
 
 def layout_path(name):
@@ -90,6 +91,99 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------------
+# The reference itself (unmodified Python: gymPacMan.py:143-193 + capture.py + agents/baselineTeam.py) timed on
+# this box's host cores: one process per core, `torch.set_num_threads(1)`, a bounded number of seconds.
+# ---------------------------------------------------------------------------------------------------------
+def _pyref_worker(job):
+    """One process = one env.  job = (rank, variant, layout, seconds).  -> (env_steps, seconds, episodes)"""
+    rank, variant, layout, seconds = job
+    import contextlib, io, random
+    sys.dont_write_bytecode = True
+    sys.path.insert(0, REF_ROOT)
+    os.chdir(REF_ROOT)                                  # loadAgents resolves agents/<team>.py from the checkout
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    with quiet:
+        from gymPacMan import gymPacMan_parallel_env
+        lay = os.path.join(REF_ROOT, "layouts", layout + ".lay")
+        if variant == "config1":                        # BASELINE config 1: red = baselineTeam bots, blue = uniform over legal lists
+            env = gymPacMan_parallel_env(layout_file=lay, enemieName="baselineTeam", self_play=False, length=299)
+        else:                                           # env only: self-play, uniform random actions for all four agents
+            env = gymPacMan_parallel_env(layout_file=lay, enemieName="randomTeam", self_play=True, length=299)
+        random.seed(1 + rank)
+        rng = np.random.default_rng(12345 + rank)
+        obs, info = env.reset()
+    steps = episodes = 0
+    t0 = time.perf_counter()
+    with quiet:
+        while True:
+            if variant == "config1":
+                la = info["legal_actions"]
+                acts = {env.agents[i]: (random.choice(la[env.agents[i]]) if i in (1, 3) else 0) for i in range(4)}
+            else:
+                a = rng.integers(0, 5, 4)
+                acts = {i: int(a[i]) for i in range(4)}
+            obs, rew, term, info = env.step(acts)
+            steps += 1
+            if any(term.values()):
+                obs, info = env.reset()
+                episodes += 1
+            if (steps & 15) == 0 and time.perf_counter() - t0 >= seconds:
+                break
+    return steps, time.perf_counter() - t0, episodes
+
+
+def python_reference_rate(layout, seconds=3.0, variants=("config1", "env_only")):
+    """agent-steps/s of the unmodified Python reference on all host cores of this box, or a one-line reason why not.
+    Workers are plain subprocesses of this script (`--pyref-worker`), one per core, each with a hard timeout."""
+    if not os.path.exists(os.path.join(REF_ROOT, "gymPacMan.py")):
+        return {"unavailable": "baseline/_ref/ holds no copy of the reference (build() copies it when /root/reference exists)"}
+    cores = len(os.sched_getaffinity(0))
+    out = {"cores": cores, "seconds_per_variant": seconds, "layout": layout,
+           "how": "one process per host core, one env each, torch.set_num_threads(1), step loop incl. resets"}
+    env = dict(os.environ, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    try:
+        for v in variants:
+            procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--pyref-worker", f"{r},{v},{layout},{seconds}"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env, cwd=ROOT)
+                     for r in range(cores)]
+            res = []
+            for pr in procs:
+                try:
+                    so, _ = pr.communicate(timeout=seconds + 120)
+                    res.append(json.loads(so.strip().splitlines()[-1]))
+                except Exception:                        # noqa: BLE001
+                    pr.kill()
+            if not res:
+                out["unavailable"] = f"no worker of variant {v} finished"
+                break
+            rates = [4.0 * r["steps"] / r["seconds"] for r in res]
+            out[v] = {"value": sum(rates), "per_core": sum(rates) / len(rates), "unit": "agent-steps/s",
+                      "workers": len(res), "env_steps": int(sum(r["steps"] for r in res)),
+                      "episodes": int(sum(r["episodes"] for r in res))}
+    except Exception as e:                              # noqa: BLE001 - report, never fail the bench on the baseline leg
+        out["unavailable"] = f"{type(e).__name__}: {e}"
+    return out
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line - built the same way by both arms so the driver can match them."""
+    rows = [ln.strip() for ln in open(layout_path(args.layout)) if ln.strip()]
+    H, Wd = len(rows), len(rows[0])
+    N = args.envs
+    return {"workload": f"{args.layout}, {N} envs/GPU x 4 agents, self-play uniform random actions, length {args.length}, "
+                        "finished envs restart inside the step (auto_reset)",
+            "envs_per_gpu": N, "layout": args.layout, "n_gpus": world,
+            "obs_bytes_per_step_per_gpu": 4 * N * 32 * H * Wd,
+            "l2": "no flush: each step writes %.2f GB of observations per GPU (>> 126 MB L2)" % (4 * N * 32 * H * Wd / 1e9),
+            "parallelism": f"env-sharded x{world}, no data-path collective"}
+
+
 def oracle_rate(layout, n_envs, steps, warmup, length, nthreads=0):
     """agent-steps/s of the CPU port (oracle/pm_oracle.c, OpenMP over envs) incl. observations."""
     import numpy as np
@@ -121,24 +215,26 @@ def oracle_rate(layout, n_envs, steps, warmup, length, nthreads=0):
 
 
 def run_reference(args, rank, world):
-    """Reference arm: the reference's CPU implementation of the path on the box's host
-    cores.  The reference is pure Python (cannot travel to the GPU box), so
-    this times the oracle port with all host threads; rank 0 only."""
+    """Reference arm: the reference's CPU implementation of the path on the box's host cores; rank 0 only.
+    `value` is the C port of capture.py / gymPacMan.py (oracle/pm_oracle.c, OpenMP over envs, all host threads) on
+    one GPU's worth of the same workload - the FASTEST CPU form of the reference's algorithm, so the ratio the driver
+    computes is conservative.  The unmodified Python reference is timed in the same run, on the same cores
+    (`cpu_baseline.python_reference`): BASELINE config 1 and the env-only loop, one process per core."""
     if rank != 0:
         return
     n = args.envs
     v, sps, threads = oracle_rate(args.layout, n, args.steps, args.warmup, args.length)
+    pyref = python_reference_rate(args.layout, seconds=3.0)
     line = {
         "impl": "reference", "metric": "agent-steps/sec (env step+obs)", "value": v, "unit": "agent-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bitsets + f64 rewards -> f32 obs",
         "data": "synthetic (uniform random actions, seeded)",
-        "config": {"workload": f"{args.layout}, {n} envs x 4 agents, self-play random actions, length {args.length}, "
-                               "auto-reset", "envs": n, "layout": args.layout},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} steps of the full {n}-env batch on {threads} OpenMP threads "
-                                   f"(C port of capture.py/gymPacMan.py; the Python reference itself ran "
-                                   f"{PY_REFERENCE_AGENT_STEPS_PER_CORE.get(args.layout)} agent-steps/s/core at survey time)"},
+                         "sample": f"{args.steps} steps of one GPU's batch ({n} envs) on {threads} OpenMP threads "
+                                   "(C port of capture.py/gymPacMan.py incl. observations)",
+                         "python_reference": pyref},
         "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -181,12 +277,12 @@ def other_kernels(torch, device, N, peak):
     # (3) all-pairs maze distances: one shipped board, and 256 distinct mazeGenerator boards in one launch (config 4)
     blox = [getLayout(layout_path("bloxCapture"))]
     ms = timed(lambda: compute_distances(blox, device=device), 20)
-    out["bfs_bloxCapture"] = {"ms": ms, "n_open": 190, "reference_python_ms": 100.0}
+    out["bfs_bloxCapture"] = {"ms": ms, "n_open": 190, "reference_python_ms_survey_container": 100.0}
     mazes = [Layout(mazeGenerator.generateMaze(1000 + s).split("\n")) for s in range(256)]
     tabs = compute_distances(mazes, device=device)
     ms = timed(lambda: compute_distances(mazes, device=device), 5)
     out["bfs_256_random_mazes"] = {"ms": ms, "ms_per_maze": ms / 256, "table_bytes": int(tabs.dist.numel() * 2),
-                                   "reference_python_ms_per_maze": "190-335"}
+                                   "reference_python_ms_per_maze_survey_container": "190-335"}
     # (4) GAE over a [T, M] rollout: 20 algorithmic bytes per element (read r, V, done; write A, ret)
     T, M = 256, 2 * N
     r, v = torch.randn(T, M, device=device), torch.randn(T, M, device=device)
@@ -259,13 +355,17 @@ def other_kernels(torch, device, N, peak):
     dt = time.perf_counter() - t0
     out["single_env_reference_api_tinyCapture_vs_baselineTeam"] = {
         "env_steps_per_s": n_steps / dt, "agent_steps_per_s": 4.0 * n_steps / dt,
-        "reference_python_agent_steps_per_s_1core": 1414, "note": "one env, env.step({agent: action}) per step"}
+        "note": "one env, env.step({agent: action}) per step; the Python reference on the same config, same box: "
+                                                               "cpu_baseline.python_reference.config1.per_core"}
     return out
 
 
-def mappo_sps(torch, device):
-    """BASELINE's second metric, MAPPO SPS: learner-agent samples per second of rollout + GAE + PPO update on
-    smallCapture (short run: 1 warm-up update + 1 timed; tools/bench_mappo.py is the long form)."""
+def mappo_sps(torch, device, world=1):
+    """BASELINE's second metric, MAPPO SPS (config 5): learner-agent samples per second of rollout + GAE + PPO update
+    on smallCapture, whole job (every rank runs the same trainer on its env shard; one flat-bucket NCCL gradient
+    all-reduce per optimizer step).  Short run: 1 warm-up update + 2 timed.  Two arithmetic modes, labelled: the
+    reference's nets are fp32; `fp32_tf32` keeps fp32 storage with TF32 tensor-core matmuls (narrower than fp32
+    inside the matmul), `bf16_autocast` is narrower still."""
     from pacman_marl_2025_b200 import pacman_mappo_resnet as M
     out = {}
     for name, amp in (("fp32_tf32", False), ("bf16_autocast", True)):
@@ -273,12 +373,25 @@ def mappo_sps(torch, device):
                             checkpoint_every=0)
         tr = M.MAPPOTrainer(cfg, device=device)
         tr.train_one(0)
-        rec = tr.train_one(1)
-        out[name] = {"samples_per_s": rec["sps"], "seconds_per_update": rec["seconds"]}
+        recs = [tr.train_one(1), tr.train_one(2)]
+        best = max(recs, key=lambda r: r["sps"])
+        out[name] = {"samples_per_s": best["sps"], "seconds_per_update": best["seconds"]}
         del tr
         torch.cuda.empty_cache()
-    out["config"] = "smallCapture, 1024 envs x 32 steps x 2 learners per update, 3 epochs x 8 minibatches, randomTeam opponent, 1 GPU"
+    out["config"] = (f"smallCapture, 1024 envs/GPU x 32 steps x 2 learners per update, 3 epochs x 8 minibatches, randomTeam "
+                     f"opponent, {world} GPU(s), NCCL gradient all-reduce per optimizer step" )
+    out["reference"] = "no figure: the reference publishes none and its trainer (1 env, CPU env loop) is bound by the env: ~350 env-steps/s/core"
     return out
+
+
+def time_launches(torch, fn, reps):
+    """-> (avg ms per call from one event pair per call, total ms of the back-to-back loop)"""
+    ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    torch.cuda.synchronize()
+    for i in range(reps):
+        ee[i][0].record(); fn(i); ee[i][1].record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ee) / reps, ee[0][0].elapsed_time(ee[-1][1])
 
 
 def main():
@@ -291,7 +404,13 @@ def main():
     ap.add_argument("--envs", type=int, default=65536, help="envs per GPU")
     ap.add_argument("--length", type=int, default=300)
     ap.add_argument("--no-extras", action="store_true", help="skip cpu_baseline / other layouts (profiling runs)")
+    ap.add_argument("--pyref-worker", default="", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.pyref_worker:                               # internal: one worker of python_reference_rate
+        r, v, lay, sec = args.pyref_worker.split(",")
+        st, dt, ep = _pyref_worker((int(r), v, lay, float(sec)))
+        print(json.dumps({"steps": st, "seconds": dt, "episodes": ep}), flush=True)
+        return
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     args.warmup = max(args.warmup, 3)
@@ -314,14 +433,23 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
     N, K, W = args.envs, args.steps, args.warmup
+    cfg = workload_config(args, world)
     H, Wd = gymPacMan_parallel_env(layout_file=layout_path(args.layout), self_play=True, num_envs=1,
                                    device=device).obs_shape[1:]
     env, acts, one = measure_layout(torch, gymPacMan_parallel_env, args.layout, N, K, W, args.length, device)
     pool = acts.shape[0]
+    NB = env.obs_bits_words()
 
     with ClockSampler(local) as clk:
-        # ---- (1) whole-step throughput: K x (pm_step + pm_reset(done)), inputs resident in HBM ----
+        # ---- (1) whole-step throughput: K x pm_step (auto_reset), inputs resident in HBM ----
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
@@ -329,66 +457,59 @@ def main():
             one(i)
         ev1.record()
         barrier()
-        loop_ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([loop_ms], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            loop_ms = float(t.item())
+        loop_ms = max_over_ranks(ev0.elapsed_time(ev1))
 
         # ---- (2) the dominant kernel alone (pm_env_kernel<STEP>): event pair around every launch ----
         KK = min(K, 200)
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KK)]
-        torch.cuda.synchronize()
-        for i in range(KK):
-            evs[i][0].record()
-            env.step_batched(acts[i % pool])
-            evs[i][1].record()
-        torch.cuda.synchronize()
-        kern_ms = sum(a.elapsed_time(b) for a, b in evs) / KK
+        kern_ms, _ = time_launches(torch, lambda i: env.step_batched(acts[i % pool]), KK)
 
-        # ---- (3) end to end through the C ABI with HOST buffers (pm_step_host_pipelined): pinned actions in,
-        #          one 48-byte record per env (rewards, shaped rewards, score_change, legal, done) back to pinned
-        #          host memory every step, call returns when the host has the results; obs stay in HBM for the policy
+        # ---- (3) end to end through the C ABI with HOST buffers: pinned actions in, results on the host when the call
+        #          returns.  Four variants of WHAT comes back, each with its bytes per step:
+        #            e2e        one 48-byte record per env (rewards, shaped rewards, score_change, legal, done); the fp32
+        #                       observations stay in HBM for a policy net on the same GPU (the reference trainer's consumer)
+        #            e2e_bits   + the PACKED observations (8*H*W-bit string + patch word per observation): everything a
+        #                       HOST-side policy needs, 32x smaller than the fp32 planes
+        #            e2e_views  + the uint8 learner views the batched trainer consumes (2 actor + 1 critic per env)
+        #            with_obs   + the 4 fp32 [8,H,W] planes per env, i.e. the reference API's full return value
         acts_host = [acts[i].cpu().pin_memory() for i in range(pool)]
         chunks = int(os.environ.get("PM_BENCH_CHUNKS", "0"))      # 0 = zero-copy entry, n = memcpy pipeline with n ranges
         host_step = (lambda a: env.step_host_mapped(a)) if chunks == 0 else (lambda a: env.step_host_pipelined(a, n_chunks=chunks))
-        for i in range(3):
-            host_step(acts_host[i % pool])
-        KE = min(K, 200)
-        barrier()
-        t0 = time.perf_counter()
-        ev0.record()
-        for i in range(KE):
-            host_step(acts_host[i % pool])
-        ev1.record()
-        torch.cuda.synchronize()
-        e2e_wall_ms = (time.perf_counter() - t0) * 1e3         # every call is host-synchronous: wall clock is the truth
-        e2e_ms = max(ev0.elapsed_time(ev1), e2e_wall_ms)
-        barrier()
-        if world > 1:
-            t = torch.tensor([e2e_ms], device=device, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        # the unpipelined entry (pm_step_host: one launch, six separate copies) for comparison
-        for i in range(3):
-            env.step_host(acts_host[i % pool])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(50):
-            env.step_host(acts_host[i % pool])
-        torch.cuda.synchronize()
-        e2e_plain = 4.0 * N * 50 / (time.perf_counter() - t0)
-        # same, but also hauling the 4 x [N,8,H,W] fp32 observations to the host (a CPU-side consumer)
-        e2e_obs = None
-        if rank == 0 and not args.no_extras:
-            for i in range(2):
-                env.step_host(acts_host[i % pool], want_obs=True)
-            torch.cuda.synchronize()
+
+        def e2e_loop(fn, reps):
+            for i in range(3):
+                fn(acts_host[i % pool])
+            barrier()
             t0 = time.perf_counter()
-            for i in range(5):
-                env.step_host(acts_host[i % pool], want_obs=True)
+            ev0.record()
+            for i in range(reps):
+                fn(acts_host[i % pool])
+            ev1.record()
             torch.cuda.synchronize()
-            e2e_obs = 4.0 * N * 5 / (time.perf_counter() - t0)
+            wall = (time.perf_counter() - t0) * 1e3          # every call is host-synchronous: wall clock is the truth
+            ms = max(ev0.elapsed_time(ev1), wall)
+            barrier()
+            return max_over_ranks(ms), wall
+
+        KE = min(K, 200)
+        e2e_ms, e2e_wall_ms = e2e_loop(host_step, KE)
+        # the unpipelined entry (pm_step_host: one launch, six separate copies) for comparison
+        plain_ms, _ = e2e_loop(lambda a: env.step_host(a), 50)
+        e2e_plain = 4.0 * N * 50 * world / (plain_ms * 1e-3)
+        # packed observations to the host: (a) zero-copy, the kernel writes them into pinned host memory itself;
+        # (b) device buffer + cudaMemcpyAsync inside pm_step_host
+        KB = min(K, 60)
+        env.set_bits_output(True, raw_obs=False, host_mapped=True)
+        bits_mapped_ms, _ = e2e_loop(lambda a: env.step_host_mapped(a), KB)
+        env.set_bits_output(True, raw_obs=False, host_mapped=False)
+        bits_copy_ms, _ = e2e_loop(lambda a: env.step_host(a, want_bits=True), KB)
+        env.set_bits_output(False)
+        bits_ms = min(bits_mapped_ms, bits_copy_ms)
+        # uint8 learner views to the host (what the batched trainer reads, if its nets lived on the host)
+        env.set_view_outputs(False, raw_obs=False)
+        views_ms, _ = e2e_loop(lambda a: env.step_host(a, want_views=True), min(K, 20))
+        env.set_view_outputs(None)
+        # the reference API's full return value: fp32 observations to the host as well (PCIe-bound)
+        obs_ms, _ = e2e_loop(lambda a: env.step_host(a, want_obs=True), 5)
     clocks = clk.summary()
 
     h2d = N * 4
@@ -401,79 +522,84 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp)).get(f"{args.layout}:{N}")
+    rate = lambda ms, reps: 4.0 * N * reps * world / (ms * 1e-3)
 
     line = {
         "metric": "agent-steps/sec (env step+obs)", "value": value, "unit": "agent-steps/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": loop_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32 bitsets + f64 rewards -> f32 obs", "data": "synthetic (uniform random actions, seeded)",
-        "config": {"workload": f"{args.layout}, {N} envs/GPU x 4 agents, self-play random actions, length {args.length}, "
-                               "finished envs restart inside the step launch (auto_reset)", "envs_per_gpu": N, "layout": args.layout,
-                   "obs_bytes_per_step_per_gpu": 4 * N * 32 * H * Wd,
-                   "l2": "no flush: each step writes %.2f GB of observations per GPU (>> 126 MB L2)" % (4 * N * 32 * H * Wd / 1e9),
-                   "parallelism": f"env-sharded x{world}, no data-path collective"},
+        "config": cfg,
         "roofline": {"bound": "hbm", "kernel": "pm_env_kernel<STEP>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo * 4 * N, "kernel_ms": kern_ms},
-        "e2e": {"value": 4.0 * N * KE * world / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+        "e2e": {"value": rate(e2e_ms, KE), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": KE, "wall_ms_rank0": e2e_wall_ms,
                 "note": ("pm_step_host_mapped (zero-copy: the step kernel itself reads the pinned host actions and writes "
                          if chunks == 0 else f"pm_step_host_pipelined ({chunks} env ranges on two streams, cudaMemcpyAsync: ") +
                         "one 48-byte record per env (rewards, shaped rewards, score_change, legal, done) to pinned host "
-                        "memory across PCIe every step); the call returns when the host holds the results; observations "
-                        "stay in HBM for the policy net",
-                "unpipelined_pm_step_host_agent_steps_per_s": e2e_plain,
-                "with_obs_to_host_agent_steps_per_s": e2e_obs},
+                        "memory across PCIe every step); the call returns when the host holds the results; the fp32 "
+                        "observations stay in HBM for a policy net on the same GPU.  e2e_bits / e2e_views / e2e_obs are the "
+                        "same call with the observations ALSO delivered to the host in three formats",
+                "unpipelined_pm_step_host_agent_steps_per_s": e2e_plain},
+        "e2e_bits": {"value": rate(bits_ms, KB), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h + 4 * N * NB * 4, "steps": KB,
+                     "zero_copy_agent_steps_per_s": rate(bits_mapped_ms, KB), "memcpy_agent_steps_per_s": rate(bits_copy_ms, KB),
+                     "note": f"records + packed observations ({NB * 4} B per observation instead of {32 * H * Wd}): "
+                             "everything a host-side policy needs (gymPacMan.decode_obs_bits expands them)"},
+        "e2e_views": {"value": rate(views_ms, min(K, 20)), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": N * (16 + 1 + 4 + 4 + 16) + 3 * N * 8 * H * Wd, "steps": min(K, 20),
+                      "note": "small outputs + the uint8 learner views (2 actor + 1 critic, 8*H*W B each) the batched trainer consumes"},
+        "e2e_obs": {"value": rate(obs_ms, 5), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": N * (16 + 1 + 4 + 4 + 16) + 4 * N * 32 * H * Wd, "steps": 5,
+                    "note": "the reference API's full return value: four fp32 [8,H,W] observations per env to the host (PCIe-bound)"},
         "gpu_launches": K,
         "clocks": clocks,
     }
 
+    # ---- BASELINE configs 3 and 5 at every N: bloxCapture step+obs (+ one distance table) and MAPPO SPS ----
+    also = {}
+    del env, acts, one
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        for lay in ("smallCapture", "bloxCapture"):
+            if lay == args.layout or (lay == "smallCapture" and world > 1):
+                continue
+            e2, a2, one2 = measure_layout(torch, gymPacMan_parallel_env, lay, N, 0, 5, args.length, device)
+            kk = 60
+            barrier()
+            km, tot = time_launches(torch, lambda i: e2.step_batched(a2[i % a2.shape[0]]), kk)
+            barrier()
+            tot = max_over_ranks(tot)
+            ab = ALGO_BYTES_PER_AGENT_STEP[lay]
+            also[lay] = {"value": 4.0 * N * kk * world / (tot * 1e-3), "unit": "agent-steps/s", "n_gpus": world,
+                         "envs_per_gpu": N, "kernel_ms": km, "roofline_frac": ab * 4.0 * N / (km * 1e-3) / 1e9 / peak}
+            if lay == "bloxCapture":
+                from pacman_marl_2025_b200.distanceCalculator import compute_distances
+                dms, _ = time_launches(torch, lambda i: compute_distances([e2.layout], device=device), 10)
+                also[lay]["distance_table_ms"] = dms
+            del e2, a2, one2
+            torch.cuda.empty_cache()
+        also["mappo"] = mappo_sps(torch, device, world)
+
     if rank == 0 and world == 1 and not args.no_extras:
-        # CPU port on this box's host cores: bounded sample of the same workload
+        # CPU side on this box's host cores: the C port (bounded sample of the same workload) and the Python reference
         ncpu = min(N, 16384)
         v, sps, threads = oracle_rate(args.layout, ncpu, 6, 2, args.length)
         line["cpu_baseline"] = {"value": v, "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                                "sample": f"6 steps x {ncpu} envs of the same workload, {threads} OpenMP threads; "
-                                          f"Python reference at survey time: {PY_REFERENCE_AGENT_STEPS_PER_CORE.get(args.layout)} agent-steps/s/core"}
+                                "sample": f"6 steps x {ncpu} envs of the same workload, {threads} OpenMP threads"}
         v1, _, _ = oracle_rate(args.layout, 4096, 4, 1, args.length, nthreads=1)
         line["cpu_baseline"]["one_core_value"] = v1
-        # the other shipped layouts, same batch, short loop (informational)
-        also = {}
-        del env, acts, one
-        torch.cuda.empty_cache()
-        for lay in ("smallCapture", "bloxCapture"):
-            if lay == args.layout:
-                continue
-            e2, a2, one2 = measure_layout(torch, gymPacMan_parallel_env, lay, N, 0, 5, args.length, device)
-            h2, w2 = e2.obs_shape[1:]
-            kk = 60
-            ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(kk)]
-            torch.cuda.synchronize()
-            ev0.record()
-            for i in range(kk):
-                ee[i][0].record(); e2.step_batched(a2[i % a2.shape[0]]); ee[i][1].record()
-            ev1.record()
-            torch.cuda.synchronize()
-            km = sum(a.elapsed_time(b) for a, b in ee) / kk
-            ab = ALGO_BYTES_PER_AGENT_STEP[lay]
-            also[lay] = {"value": 4.0 * N * kk / (ev0.elapsed_time(ev1) * 1e-3), "kernel_ms": km,
-                         "roofline_frac": ab * 4.0 * N / (km * 1e-3) / 1e9 / peak}
-            del e2, a2, one2
-            torch.cuda.empty_cache()
+        line["cpu_baseline"]["python_reference"] = python_reference_rate(args.layout, seconds=3.0)
         # the same layout at 4x the batch: the fixed cost of a launch (the store-free rules phase at its start) weighs less
         e4, a4, one4 = measure_layout(torch, gymPacMan_parallel_env, args.layout, 4 * N, 0, 5, args.length, device, pool=2)
-        ee = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
-        torch.cuda.synchronize()
-        for i in range(30):
-            ee[i][0].record(); e4.step_batched(a4[i % 2]); ee[i][1].record()
-        torch.cuda.synchronize()
-        km = sum(a.elapsed_time(b) for a, b in ee) / 30
+        km, _ = time_launches(torch, lambda i: e4.step_batched(a4[i % 2]), 30)
         also[f"{args.layout}_x4_envs"] = {"envs": 4 * N, "value": 16.0 * N / (km * 1e-3), "kernel_ms": km,
                                           "roofline_frac": algo * 16.0 * N / (km * 1e-3) / 1e9 / peak}
         del e4, a4, one4
         torch.cuda.empty_cache()
         # the other kernels of the path, each timed alone (CUDA events, this stream)
         also["kernels"] = other_kernels(torch, device, N, peak)
-        also["mappo"] = mappo_sps(torch, device)
+    if also:
         line["also"] = also
 
     if rank == 0:

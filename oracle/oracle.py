@@ -38,11 +38,13 @@ def lib():
         L.pmo_reset_outputs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pmo_get_state.argtypes = [C.c_void_p] * 5
         L.pmo_step_batch.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 7 + [C.c_int, C.c_int]
+        L.pmo_step_batch_digest.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 8 + [C.c_int, C.c_int]
         L.pmo_step_batch_bots.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 10 + [C.c_int, C.c_int]
         L.pmo_sizeof_dist_table.restype = C.c_size_t
         L.pmo_build_dist_table.restype = C.c_int
         L.pmo_build_dist_table.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.pmo_set_distances.argtypes = [C.c_void_p, C.c_void_p]
+        L.pmo_set_draws.argtypes = [C.c_void_p, C.c_void_p]
         L.pmo_max_threads.restype = C.c_int
         L.pmo_distances.restype = C.c_int
         L.pmo_distances.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
@@ -122,12 +124,29 @@ class OracleBatch:
                          int(auto_reset), int(nthreads))
         return out
 
+    def step_digest(self, actions, weights, auto_reset=True, nthreads=0):
+        """Like step(), but instead of the observations it returns their digests [N,4] uint64 (see pm_oracle.c,
+        obs_digest; `weights` = digest_weights(8*H*W)) - for parity at batch sizes whose observations cannot be
+        hauled to the host every step."""
+        L = lib()
+        assert weights.dtype == np.uint64 and weights.size >= 8 * self.W * self.H
+        a = np.ascontiguousarray(np.asarray(actions, dtype=np.int32).reshape(self.N, 4))
+        out = dict(digest=np.zeros((self.N, 4), np.uint64), reward=np.zeros((self.N, 2), np.float64),
+                   done=np.zeros(self.N, np.uint8), legal=np.zeros((self.N, 4), np.uint8),
+                   score_change=np.zeros(self.N, np.int32), shaping=np.zeros((self.N, 4), np.float64))
+        L.pmo_step_batch_digest(C.c_void_p(self.buf.ctypes.data), self.N, _p(a), _p(weights), _p(out["digest"]), _p(out["reward"]),
+                                _p(out["done"]), _p(out["legal"]), _p(out["score_change"]), _p(out["shaping"]),
+                                int(auto_reset), int(nthreads))
+        return out
+
     def set_bots(self, bot_kind):
         """bot_kind[4]: 0 = driven by the caller's actions, 2 / 3 = baselineTeam Offensive / Defensive reflex
         agent.  Builds the maze-distance table(s) the bots look up (one per distinct board)."""
         L = lib()
         self.bot_kind = np.ascontiguousarray(bot_kind, np.uint8)
         self._tables = {}
+        if not any(int(k) >= 2 for k in self.bot_kind):
+            return
         cap = self.W * self.H
         for n in range(self.N):
             key = bytes(self.buf[n * self.esz:(n + 1) * self.esz][:8 + 64 * 64])       # W, H, walls
@@ -137,6 +156,19 @@ class OracleBatch:
                 assert L.pmo_build_dist_table(self._env(n), _p(t), _p(d), cap) > 0
                 self._tables[key] = (t, d)
             L.pmo_set_distances(self._env(n), _p(self._tables[key][0]))
+
+    def set_draws(self, draws):
+        """draws [N,4] uint32 (or None): the index random.choice returned for each agent's bot decision of the NEXT
+        step(s) - into the legal list (kind 1, randomTeam) or the best-action list (kinds 2/3, baselineTeam)."""
+        L = lib()
+        if draws is None:
+            self._draws = None
+            for n in range(self.N):
+                L.pmo_set_draws(self._env(n), None)
+            return
+        self._draws = np.ascontiguousarray(np.asarray(draws).reshape(self.N, 4), np.uint32)
+        for n in range(self.N):
+            L.pmo_set_draws(self._env(n), C.c_void_p(self._draws.ctypes.data + 16 * n))
 
     def step_bots(self, actions, with_obs=True, auto_reset=False, nthreads=1):
         """Like step(), with the agents flagged by set_bots() choosing their own action at their sub-move
@@ -167,6 +199,14 @@ class OracleBatch:
         misc = np.zeros(3, np.int32)
         lib().pmo_get_state(self._env(n), _p(agents), _p(food), _p(caps), _p(misc))
         return dict(agents=agents, food=food, caps=caps, score=int(misc[0]), steps=int(misc[1]), win=int(misc[2]))
+
+
+def digest_weights(n: int) -> np.ndarray:
+    """Pseudo-random 64-bit weight per observation element (splitmix64 of the index)."""
+    z = (np.arange(1, n + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return np.ascontiguousarray(z ^ (z >> np.uint64(31)))
 
 
 def max_threads() -> int:

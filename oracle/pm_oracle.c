@@ -76,6 +76,9 @@ typedef struct {
     int snap_x[4], snap_y[4], snap_carry[4];
     /* bot support (agents/baselineTeam.py): shared all-pairs table, set by pmo_set_distances */
     const struct pmo_dist_table *dt;
+    /* random.choice indices for this step's bot decisions (one per agent), or NULL: ties -> first best.
+     * Lets a replay follow a trajectory the reference played with its real MT19937 stream. */
+    const uint32_t *draws;
 } pmo_env;
 
 /* distanceCalculator.Distancer as the bots use it (distanceCalculator.py:38-62): a lookup
@@ -362,6 +365,7 @@ static double shaping_value(int py, int px, int pcarry, int ny, int nx) {
  * obs: [4][8][H][W] fp32 or NULL; reward[2] = {red, blue}; legal[4] bitmasks from
  * the FINAL state; shaping[4] vs. the previous observation of each agent.       */
 static int baseline_choose(const pmo_env *e, int idx, int kind, int *best_mask);
+static int random_choose(const pmo_env *e, int idx);
 
 /* bot_kind[4] (or NULL): 0 = agent plays actions_in[idx]; 2 / 3 = baselineTeam Offensive / Defensive reflex agent
  * choosing at its own sub-move from the live state (gymPacMan.py:157), ties -> FIRST best action in the
@@ -377,6 +381,7 @@ void pmo_step_bots(pmo_env *e, const int32_t *actions_in, const uint8_t *bot_kin
         actions[idx] = actions_in[idx];
         int bm = 0;
         if (bot_kind && bot_kind[idx] >= 2) actions[idx] = baseline_choose(e, idx, bot_kind[idx], &bm);
+        else if (bot_kind && bot_kind[idx] == 1) actions[idx] = random_choose(e, idx);
         if (actions_used) actions_used[idx] = actions[idx];
         if (best_masks) best_masks[idx] = (uint8_t)bm;
         pmo_env next = *e;
@@ -497,8 +502,23 @@ static int baseline_choose(const pmo_env *e, int idx, int kind, int *best_mask) 
         return besta;
     }
     if (best_mask) *best_mask = mask;
+    if (e->draws) {                                    /* random.choice(bestActions), baselineTeam.py:92 */
+        int best[5], nb = 0;
+        for (int k = 0; k < na; ++k) if (vals[k] == mx) best[nb++] = acts[k];
+        return best[e->draws[idx] % (uint32_t)nb];
+    }
     return first;
 }
+
+/* agents/randomTeam.py:94-100: random.choice(gameState.getLegalActions(self.index)); the index comes from
+ * e->draws (recorded from the reference's own stream) - without draws the first legal action is taken. */
+static int random_choose(const pmo_env *e, int idx) {
+    int legal = legal_mask(e, idx), acts[5], na = 0;
+    for (int k = 0; k < 5; ++k) if ((legal >> REF_ORDER[k]) & 1) acts[na++] = REF_ORDER[k];
+    return acts[e->draws ? e->draws[idx] % (uint32_t)na : 0];
+}
+
+void pmo_set_draws(pmo_env *e, const uint32_t *draws4) { e->draws = draws4; }
 
 /* reset outputs: obs[4][8][H][W] (all from the initial state) and legal masks */
 void pmo_reset_outputs(const pmo_env *e, float *obs, uint8_t *legal) {
@@ -560,6 +580,47 @@ void pmo_step_batch_bots(pmo_env *envs, int64_t N, const int32_t *actions, const
                       legal + 4 * n, score_change + n, shaping ? shaping + 4 * n : NULL,
                       actions_used ? actions_used + 4 * n : NULL, best_masks ? best_masks + 4 * n : NULL);
         if (auto_reset && done[n]) pmo_reset(&envs[n]);
+    }
+}
+
+/* Observation digests for parity at full batch size (65,536 envs x 4 observations per step never cross PCIe):
+ * digest(o) = sum_i bits(o[i]) * K[i] mod 2^64 over the 8*H*W fp32 elements, K = a table of pseudo-random 64-bit
+ * weights supplied by the caller (position-dependent and non-linear in i, so moves of different agents cannot
+ * cancel).  The GPU side computes the same sum with integer tensor ops on the kernel's output
+ * (tests/test_gpu_full_size.py).  With auto_reset the digests (and legal masks) of a finished env are those of its
+ * freshly reset state, like the fused restart of pm_step.  digest[N][4].                                        */
+static uint64_t obs_digest(const float *o, int n, const uint64_t *K) {
+    uint64_t d = 0;
+    for (int i = 0; i < n; ++i) {
+        uint32_t u; memcpy(&u, &o[i], 4);
+        if (u) d += (uint64_t)u * K[i];
+    }
+    return d;
+}
+
+void pmo_step_batch_digest(pmo_env *envs, int64_t N, const int32_t *actions, const uint64_t *K, uint64_t *digest,
+                           double *reward, uint8_t *done, uint8_t *legal, int32_t *score_change, double *shaping,
+                           int auto_reset, int nthreads) {
+    if (N <= 0) return;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel
+#endif
+    {
+        /* one scratch block per worker thread, kept for the life of the thread */
+        static _Thread_local float *obs = NULL;
+        if (!obs) obs = (float *)malloc(sizeof(float) * 4 * 8 * PMO_MAXW * PMO_MAXH);
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int64_t n = 0; n < N; ++n) {
+            pmo_env *e = &envs[n];
+            int per = 8 * e->W * e->H;
+            pmo_step(e, actions + 4 * n, obs, reward + 2 * n, done + n, legal + 4 * n, score_change + n,
+                     shaping ? shaping + 4 * n : NULL);
+            if (auto_reset && done[n]) { pmo_reset(e); pmo_reset_outputs(e, obs, legal + 4 * n); }
+            for (int i = 0; i < 4; ++i) digest[4 * n + i] = obs_digest(obs + (size_t)i * per, per, K);
+        }
     }
 }
 

@@ -572,6 +572,21 @@ class gymPacMan_parallel_env:
                        "pm_observe_bits")
         return out
 
+    def set_bot_draws(self, draws: Optional[torch.Tensor]):
+        """``pm_env_desc.bot_draws``: [N,4] int32 tensor on the env's device holding, for each agent's on-device bot,
+        the index ``random.choice`` returns at its next decision (None = the kernel hashes its own draws).  The
+        tensor is read by every following step; update it in place between steps.  Feeding indices recorded from
+        the reference's MT19937 stream replays the reference's trajectories exactly (tests/golden/traj_rng_*)."""
+        if draws is None:
+            self._bot_draws = None
+            self._desc.bot_draws = None
+            return
+        if draws.dtype != torch.int32 or draws.device != self.device or draws.numel() != 4 * self.num_envs \
+                or not draws.is_contiguous():
+            raise ValueError("bot draws must be a contiguous int32 [N,4] tensor on the env's device")
+        self._bot_draws = draws
+        self._desc.bot_draws = draws.data_ptr()
+
     def observe_views(self, red: bool, actor: Optional[torch.Tensor] = None, critic: Optional[torch.Tensor] = None):
         """The learner views of the CURRENT state (e.g. right after a reset)."""
         N, shp = self.num_envs, self.obs_shape

@@ -185,6 +185,9 @@ class SingleEnvDriver:
                     shaping=np.asarray(o["shaping"])[:, n], shaped=np.asarray(o["shaped"])[:, n],
                     actions_used=None if o.get("actions_used") is None else np.asarray(o["actions_used"])[n])
 
+    def set_draws(self, d4):
+        self.env.set_draws(np.tile(np.asarray(d4, np.uint32), (self.env.N, 1)))
+
     def state(self):
         s = self.env.get_state()
         n = self.n

@@ -183,10 +183,16 @@ class BotSpy:
     actions it was offered is kept, so a replay can either follow the same trajectory (tie-break =
     first) or check that a randomly tie-broken choice lies inside the recorded set."""
 
-    def __init__(self, env):
+    def __init__(self, env, real_rng=False):
+        """real_rng=True: `random.choice` is NOT pinned - it draws from the global MT19937 exactly like the stock
+        function (one `_randbelow(len(seq))`), and the index it returned is recorded per bot decision, so a replay
+        can be fed the reference's own draws (`pm_env_desc.bot_draws`)."""
         self.env = env
+        self.real_rng = real_rng
         self.choice_sets = []
+        self.choice_idx = []
         self.taken = {}
+        self.draw = {}
         self._orig_choice = random.choice
         random.choice = self._choice
         for i, ag in enumerate(env.agents):
@@ -195,16 +201,22 @@ class BotSpy:
 
     def _choice(self, seq):
         self.choice_sets.append(list(seq))
-        return seq[0]
+        if not self.real_rng:
+            self.choice_idx.append(0)
+            return seq[0]
+        i = random.randrange(len(seq))          # == random.choice: seq[self._randbelow(len(seq))]
+        self.choice_idx.append(i)
+        return seq[i]
 
     def _wrap(self, i, fn):
         def inner(state):
-            self.choice_sets = []
+            self.choice_sets, self.choice_idx = [], []
             a = fn(state)
             m = 0
             for name in (self.choice_sets[-1] if self.choice_sets else [a]):
                 m |= 1 << DIR_ID[name]
             self.taken[i] = (DIR_ID[a], m)
+            self.draw[i] = self.choice_idx[-1] if self.choice_idx else 0
             return a
         return inner
 
@@ -330,6 +342,21 @@ class SmartPolicy:
         return acts
 
 
+class GlobalRngBluePolicy:
+    """BASELINE config 1's caller: the red side is played by the env's bots, blue picks uniformly from the legal
+    lists of the last info dict with the GLOBAL `random` (what randomTeam.chooseAction does, randomTeam.py:94-100)."""
+
+    def __init__(self, env, rng):
+        self.info = None
+
+    def new_episode(self):
+        pass
+
+    def act(self, env):
+        la = self.info["legal_actions"]
+        return [0, random.choice(la[1]), 0, random.choice(la[3])]
+
+
 class RandomPolicy:
     def __init__(self, env, rng):
         self.rng = rng
@@ -345,20 +372,23 @@ class RandomPolicy:
 # trajectory recorder
 # ---------------------------------------------------------------------------
 def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48, max_steps=None, enemie=None,
-           **envkw):
+           real_rng=False, **envkw):
     rows = layout_text(lay_name)
     kw = dict(length=300, reward_forLegalAction=True, defenceReward=True)
     kw.update(envkw)
+    if real_rng:
+        random.seed(seed)                          # BASELINE config 1: random.seed(1)
     env = make_env(rows, enemie=enemie, **kw)
-    spy = BotSpy(env) if enemie else None
+    spy = BotSpy(env, real_rng=real_rng) if enemie else None
     byidx = lambda d: {i: d[env.agents[i]] for i in range(4)}      # bot objects key the dicts of the red side
     rng = np.random.default_rng(seed)
-    pol = SmartPolicy(env, rng) if policy == "smart" else RandomPolicy(env, rng)
+    pol = (SmartPolicy(env, rng) if policy == "smart" else GlobalRngBluePolicy(env, rng) if policy == "global_rng"
+           else RandomPolicy(env, rng))
     W, H = env.layout.width, env.layout.height
 
     R = dict(actions=[], pos=[], misc=[], food=[], caps=[], score=[], score_change=[], reward=[],
              done=[], legal=[], obs_dig=[], shaping=[], ep_start=[], reset_legal=[], reset_obs_dig=[],
-             full_obs=[], bot_best=[])
+             full_obs=[], bot_best=[], draws=[])
     cover = dict(steps=0, eats=0, returns=0, kills=0, dumps=0, scared_kills=0, caps=0, food_end=0,
                  rebinding=0, nonzero_final=0)
     _REBIND["n"] = _REBIND["ate"] = 0
@@ -367,6 +397,7 @@ def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48
         with _quiet:
             obs, info = env.reset()
         obs, info["legal_actions"] = byidx(obs), byidx(info["legal_actions"])
+        pol.info = info
         R["ep_start"].append(len(R["actions"]))
         R["reset_legal"].append([legal_mask(info["legal_actions"][i]) for i in range(4)])
         R["reset_obs_dig"].append([obs_digest(obs[i]) for i in range(4)])
@@ -377,12 +408,14 @@ def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48
             with _quiet:
                 nobs, rew, term, info = env.step({i: acts[i] for i in range(4)})
             nobs, rew, info["legal_actions"] = byidx(nobs), byidx(rew), byidx(info["legal_actions"])
-            best = [0, 0, 0, 0]
+            pol.info = info
+            best, draws = [0, 0, 0, 0], [0, 0, 0, 0]
             if spy:                                   # what the bots really played replaces the ignored red entries
                 acts = list(acts)
                 for i, (a, m) in spy.taken.items():
-                    acts[i], best[i] = a, m
+                    acts[i], best[i], draws[i] = a, m, spy.draw.get(i, 0)
             R["bot_best"].append(best)
+            R["draws"].append(draws)
             done = any(term.values())
             pos, misc, food, caps, score = snapshot(env)
             R["actions"].append(acts)
@@ -434,7 +467,10 @@ def record(name, lay_name, policy="smart", episodes=4, seed=0, full_obs_steps=48
     out["WH"] = np.array([W, H], np.int32)
     out["bot_best"] = out["bot_best"].astype(np.uint8)
     # 0 = driven by `actions`, 2 / 3 = baselineTeam Offensive / Defensive reflex agent (createTeam order, baselineTeam.py:34-51)
-    out["bot_kind"] = np.array([2, 0, 3, 0] if enemie == "baselineTeam" else [0, 0, 0, 0], np.uint8)
+    out["bot_kind"] = np.array([2, 0, 3, 0] if enemie == "baselineTeam" else [1, 0, 1, 0] if enemie == "randomTeam"
+                               else [0, 0, 0, 0], np.uint8)
+    out["draws"] = out["draws"].astype(np.uint32)
+    out["real_rng"] = np.uint8(real_rng)
     if spy:
         spy.close()
     np.savez_compressed(os.path.join(HERE, f"traj_{name}.npz"), **out)
@@ -566,6 +602,18 @@ def main():
         for lay, eps in (("tinyCapture", 3), ("smallCapture", 3), ("bloxCapture", 2), ("capsSmall", 2), ("maze7", 1)):
             cov[f"bots_{lay}"] = record(f"bots_{lay}", lay, "smart", episodes=eps, seed=31, enemie="baselineTeam",
                                         full_obs_steps=8)
+        digests["coverage"] = cov
+
+    if want("rngbots"):
+        # BASELINE config 1 and its randomTeam twin with the bots' REAL random.choice (global MT19937, random.seed(1)):
+        # red = the env's bots deciding at their own sub-move, blue = uniform over the legal lists from the same stream
+        cov = digests.get("coverage", {})
+        cov["rng_baselineTeam_tinyCapture"] = record("rng_baselineTeam_tinyCapture", "tinyCapture", "global_rng", episodes=3,
+                                                      seed=1, enemie="baselineTeam", real_rng=True, full_obs_steps=8, length=299)
+        cov["rng_randomTeam_tinyCapture"] = record("rng_randomTeam_tinyCapture", "tinyCapture", "global_rng", episodes=3,
+                                                    seed=1, enemie="randomTeam", real_rng=True, full_obs_steps=8, length=299)
+        cov["rng_baselineTeam_capsSmall"] = record("rng_baselineTeam_capsSmall", "capsSmall", "global_rng", episodes=2,
+                                                    seed=1, enemie="baselineTeam", real_rng=True, full_obs_steps=8, length=150)
         digests["coverage"] = cov
 
     if want("survey"):

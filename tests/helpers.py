@@ -85,20 +85,25 @@ def replay(fx, drv, where=""):
 
 
 class BotReplayDriver:
-    """Wraps a single-env driver for fixtures recorded with the reference's baselineTeam on the red side: the
-    env under test runs its OWN bots (tie-break = first best, as pinned while recording); the recorded red
-    actions are withheld (garbage is fed in their place) and must come back in `actions_used`."""
+    """Wraps a single-env driver for fixtures recorded with the reference's bots on the red side: the env under
+    test runs its OWN bots; the recorded red actions are withheld (garbage is fed in their place) and must come
+    back in `actions_used`.  `bots_*` fixtures were recorded with `random.choice` pinned to the first best action
+    (replay: tie-break = first); `rng_*` fixtures with the bots' REAL `random.choice` on the global MT19937 - the
+    index each call returned is in `draws` and is fed back through `inner.set_draws` (pm_env_desc.bot_draws)."""
 
     def __init__(self, inner, fx):
         self.inner, self.fx, self.t = inner, fx, 0
+        self.real_rng = bool(fx.get("real_rng", 0))
 
     def reset(self):
         return self.inner.reset()
 
     def step(self, a):
-        fed = np.where(self.fx["bot_kind"] >= 2, 9, np.asarray(a)).astype(np.uint8)
+        bots = self.fx["bot_kind"] >= 1             # (non-bot columns report the EFFECTIVE action: illegal -> Stop)
+        fed = np.where(bots, 9, np.asarray(a)).astype(np.uint8)
+        if self.real_rng:
+            self.inner.set_draws(self.fx["draws"][self.t])
         out = self.inner.step(fed)
-        bots = self.fx["bot_kind"] >= 2             # (non-bot columns report the EFFECTIVE action: illegal -> Stop)
         np.testing.assert_array_equal(np.asarray(out["actions_used"])[bots], np.asarray(a)[bots],
                                       err_msg=f"step {self.t}: bot actions")
         self.t += 1

@@ -391,3 +391,87 @@ def body_step_in_several_launches(make_env, set_agents, rows, N=40, T=120, split
     s1, s2 = whole.get_state(), parts.get_state()
     for k in s1:
         np.testing.assert_array_equal(s1[k], s2[k])
+
+
+# ---- ABI 7 ---------------------------------------------------------------------------------------------------
+def body_obs_bits(make_env, rows, N=40, T=130, **kw):
+    """pm_step_out.obs_bits / pm_observe_bits: the packed observation (8*H*W-bit string + own-cell patch word + zero
+    padding) decodes to exactly the fp32 observation of the same step."""
+    from pacman_marl_2025_b200.gymPacMan import decode_obs_bits
+    H, W = len(rows), len(rows[0])
+    ncat = (8 * H * W + 31) // 32
+    env = make_env(rows, N, length=100, auto_reset=True, **kw)
+    obs, _ = env.reset()
+    np.testing.assert_array_equal(decode_obs_bits(env.observe_bits(), H, W), obs)
+    env.set_bits(True)
+    rng = np.random.default_rng(3)
+    patched = 0
+    for t in range(T):
+        o = env.step(biased_actions(rng, N, 0.6, t))
+        bits = np.asarray(o["obs_bits"]).view(np.uint32)
+        np.testing.assert_array_equal(decode_obs_bits(bits, H, W), o["obs"], err_msg=f"t={t}")
+        assert not bits[..., ncat + 1:].any(), "padding words must be zero"
+        patched += int((bits[..., ncat] != 0xFFFFFFFF).sum())
+    assert patched > 0                # own-cell values above 1 (carrying) were exercised
+
+
+M64 = (1 << 64) - 1
+
+
+def py_random_u32(seed, n, episode, ctr):
+    """pm_random_u32 (csrc/pm_env_core.cuh) restated."""
+    z = (seed + 0x9E3779B97F4A7C15 * (n + 1) + 0xD1B54A32D192ED03 * ((episode << 32) + ctr + 1)) & M64
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M64
+    z ^= z >> 31
+    return z >> 32
+
+
+def py_pool_layout(seed, n, episode, L):
+    return py_random_u32(seed ^ 0x6C61796F75747321, n, episode, 0xFFFFFFF0) % L
+
+
+def body_layout_pool(make_env, N=24, T=140, L=7, seed=77, base=0):
+    """pm_env_desc.layout_pool: a new maze every episode (gymPacMan.py:98-100).  Env n plays board
+    hash(seed, global env index, episode) % L; the oracle is re-initialised on that board whenever an env restarts."""
+    from pacman_marl_2025_b200 import mazeGenerator
+    mazes = [mazeGenerator.generateMaze(7000 + s).split("\n") for s in range(L)]
+    env = make_env(mazes, N, length=30, auto_reset=True, layout_pool=True, random_seed=seed, env_index_base=base)
+    ids = np.array([py_pool_layout(seed, base + n, 0, L) for n in range(N)])
+    episode = np.zeros(N, np.int64)
+    ref = oracle.OracleBatch([mazes[i] for i in ids], N, length=30)
+    obs, legal = env.reset()
+    robs, rlegal = ref.reset()
+    np.testing.assert_array_equal(env.get_state()["layout_id"], ids)
+    np.testing.assert_array_equal(legal, rlegal)
+    np.testing.assert_array_equal(obs.transpose(1, 0, 2, 3, 4), robs)
+    rng = np.random.default_rng(8)
+    L_ = oracle.lib()
+    moved = 0
+    for t in range(T):
+        a = biased_actions(rng, N, 0.6, t)
+        o = env.step(a)
+        r = ref.step(a, with_obs=True, nthreads=0)
+        d = r["done"].astype(bool)
+        np.testing.assert_array_equal(o["done"], r["done"], err_msg=f"t={t}")
+        np.testing.assert_array_equal(o["reward"].view(np.uint64), r["reward"].T.copy().view(np.uint64), err_msg=f"t={t}")
+        np.testing.assert_array_equal(o["score_change"], r["score_change"])
+        want_obs, want_legal = r["obs"].copy(), r["legal"].copy()
+        for n in np.nonzero(d)[0]:                  # restart on the next board of this env's sequence
+            episode[n] += 1
+            new = py_pool_layout(seed, base + int(n), int(episode[n]), L)
+            moved += int(new != ids[n])
+            ids[n] = new
+            text, W, H = oracle._rows(mazes[new])
+            assert L_.pmo_env_init(ref._env(int(n)), text, W, H, 30, 1, 1) == 0
+            L_.pmo_reset(ref._env(int(n)))
+        if d.any():
+            idx = np.nonzero(d)[0]
+            ro, rl = ref.reset_outputs_for(idx)
+            want_obs[idx], want_legal[idx] = ro, rl
+        np.testing.assert_array_equal(o["legal"], want_legal, err_msg=f"t={t} legal")
+        np.testing.assert_array_equal(o["obs"].transpose(1, 0, 2, 3, 4), want_obs, err_msg=f"t={t} obs")
+        s = env.get_state()
+        np.testing.assert_array_equal(s["layout_id"], ids, err_msg=f"t={t} layout ids")
+        np.testing.assert_array_equal(s["episode"], episode)
+    assert moved > N                  # envs really changed boards

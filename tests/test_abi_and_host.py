@@ -49,6 +49,48 @@ def test_struct_layouts_match_the_header():
     assert _lib.PmEnvDesc.env_index_base.offset == c and _lib.PmEnvDesc.shaping_scale.offset == d
 
 
+def _header_struct_fields(name):
+    """Field names of `typedef struct <name> {...} <name>;` in the header, in declaration order."""
+    text = open(os.path.join(ROOT, "include", "pacman_b200.h")).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        # "const uint32_t *geom" / "int32_t W, H" / "struct pm_host_record *packed"
+        first, *rest = decl.split(",")
+        fields.append(re.search(r"(\w+)\s*$", first.replace("*", " ")).group(1))
+        fields += [r.replace("*", " ").strip() for r in rest]
+    return fields
+
+
+def test_structs_match_header_ctypes_and_integration_doc_field_by_field():
+    """pm_env_desc / pm_step_out: the header's fields, the ctypes classes of _lib.py and the binding printed in
+    INTEGRATION.md section 4 list the same names in the same order, and every ctypes offset equals the C
+    compiler's offsetof (a maintainer who copies the doc gets the real struct, not a truncated one)."""
+    import subprocess, tempfile
+    from pacman_marl_2025_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for cname, cls in (("pm_env_desc", _lib.PmEnvDesc), ("pm_step_out", _lib.PmStepOut)):
+        hdr = _header_struct_fields(cname)
+        assert [n for n, _ in cls._fields_] == hdr, cname
+        blk = re.search(r"class %s\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n" % cname, doc, re.S).group(1)
+        assert re.findall(r'\("(\w+)",', blk) == hdr, f"INTEGRATION.md lists other fields for {cname}"
+        doc_types = dict(re.findall(r'\("(\w+)", C\.(\w+)\)', blk))
+        for n, t in cls._fields_:
+            assert getattr(C, doc_types[n]) is t, (cname, n)           # (c_int32 is an alias of c_int: compare the types)
+        with tempfile.TemporaryDirectory() as td:
+            src = os.path.join(td, "p.c")
+            prints = "".join('printf("%%zu\\n", offsetof(%s, %s));' % (cname, f) for f in hdr)
+            open(src, "w").write('#include <stdio.h>\n#include <stddef.h>\n#include "pacman_b200.h"\nint main(){%s return 0;}\n' % prints)
+            exe = os.path.join(td, "p")
+            subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, src])
+            offs = list(map(int, subprocess.check_output([exe]).split()))
+        assert [getattr(cls, f).offset for f in hdr] == offs, cname
+
+
 def test_argument_errors_without_touching_the_gpu():
     from pacman_marl_2025_b200 import _lib
     L = _lib.load()

@@ -30,10 +30,25 @@ class CudaEnv:
         if bot_kind is not None and list(bot_kind) == [2, 0, 3, 0]:
             team, self_play = "baselineTeam", False
             kw["opponent_tiebreak"] = "first" if bot_first_best else "random"
+        elif bot_kind is not None and list(bot_kind) == [1, 0, 1, 0]:
+            team, self_play = "randomTeam", False
+        want_draws = kw.pop("bot_draws", False)
         self.env = gymPacMan_parallel_env(length=length, reward_forLegalAction=reward_forLegalAction,
                                           defenceReward=defenceReward, self_play=self_play, enemieName=team,
                                           num_envs=n_envs, layouts=lays, opponent_seed=random_seed, **kw)
         self.N = n_envs
+        if want_draws:
+            self.draws = torch.zeros((n_envs, 4), dtype=torch.int32, device="cuda")
+            self.env.set_bot_draws(self.draws)
+
+    def set_draws(self, draws):
+        self.draws.copy_(torch.as_tensor(np.asarray(draws, np.int64).reshape(self.N, 4).astype(np.int32)))
+
+    def set_bits(self, on=True):
+        self.env.set_bits_output(on)
+
+    def observe_bits(self):
+        return self.env.observe_bits().cpu().numpy().view(np.uint32)
 
     def reset(self, mask=None):
         m = None if mask is None else torch.as_tensor(np.asarray(mask, np.uint8))
@@ -47,6 +62,7 @@ class CudaEnv:
                     legal=o["legal"].cpu().numpy(), score_change=o["score_change"].cpu().numpy(),
                     shaping=o["shaping"].cpu().numpy(), shaped=o["shaped_reward"].cpu().numpy(),
                     actions_used=o["actions_used"].cpu().numpy(),
+                    **({"obs_bits": o["obs_bits"].cpu().numpy().view(np.uint32)} if "obs_bits" in o else {}),
                     **({k: o[k].cpu().numpy() for k in ("view_actor", "view_critic")} if "view_actor" in o else {}))
 
     def set_views(self, red=None):
@@ -629,15 +645,16 @@ def test_reference_api_single_env_with_baseline_team(name):
     helpers.replay(fx, helpers.BotReplayDriver(RefApiDriver(fx, bots=True), fx), where=name)
 
 
-def test_envs_per_cta_choice_does_not_change_results(monkeypatch):
+def test_envs_per_cta_choice_does_not_change_results():
     """Launch geometry only: small batches run 8 envs per CTA, large ones 32 (pm_env.cu); forcing either through
-    PM_ENVS_PER_CTA must give identical outputs, states and learner views."""
+    pm_env_desc.envs_per_cta must give identical outputs, states and learner views."""
     rows = lay_rows("smallCapture")
     N = 1000
     res = {}
+    with pytest.raises(RuntimeError, match="PM_EINVAL"):
+        CudaEnv(rows, 8, envs_per_cta=16)
     for epc in ("8", "32"):
-        monkeypatch.setenv("PM_ENVS_PER_CTA", epc)
-        env = CudaEnv(rows, N, length=35, auto_reset=True, bot_kind=[2, 0, 3, 0])
+        env = CudaEnv(rows, N, length=35, auto_reset=True, bot_kind=[2, 0, 3, 0], envs_per_cta=int(epc))
         env.reset()
         env.set_views(True)
         rng = np.random.default_rng(8)
@@ -713,3 +730,180 @@ def test_host_side_bots_play_at_their_own_sub_move():
         if bool(term[1].any()):
             break
     assert env.steps == t + 1 and env.num_moves == 4 * (t + 1)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ABI 7: the reference's real RNG stream, packed observations, a new maze every episode, layout changes
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in helpers.traj_names() if n.startswith("rng_")])
+def test_cuda_bots_follow_the_references_real_rng_stream(name):
+    """BASELINE config 1 exactly as the reference plays it: tinyCapture, red = baselineTeam (or randomTeam) bots
+    whose `random.choice` draws from the global MT19937 under `random.seed(1)`, blue = uniform over the legal lists
+    from the same stream.  Fed the recorded choice indices (`pm_env_desc.bot_draws`), the in-kernel bots reproduce
+    the reference's trajectory bit for bit - every state field, reward, mask and observation of every step."""
+    fx = helpers.load_traj(name)
+    env = CudaEnv(fx["layout"], 3, length=int(fx["length"]), bot_kind=list(fx["bot_kind"]), bot_first_best=False,
+                  bot_draws=True)
+    helpers.replay(fx, helpers.BotReplayDriver(SingleEnvDriver(env, n=1), fx), where=name)
+
+
+@pytest.mark.parametrize("lay", ["tinyCapture", "smallCapture", "bloxCapture", "capsSmall", "odd15"])
+def test_cuda_packed_observation_bits(lay):
+    from parity_bodies import body_obs_bits
+    rows = lay_rows(lay) if lay.endswith("Capture") else helpers.load_traj(lay)["layout"]
+    body_obs_bits(CudaEnv, rows, N=300, T=130)
+
+
+def test_cuda_packed_bits_reach_the_host_three_ways():
+    """The packed observations and the uint8 learner views through the host-buffer entries: pm_step_host (device
+    buffer + copies inside the call) and pm_step_host_mapped with the bits buffer itself in pinned host memory
+    (the kernel writes it across PCIe) - all equal to the device-side outputs of an identical env."""
+    from pacman_marl_2025_b200.gymPacMan import decode_obs_bits
+    rows = lay_rows("tinyCapture")
+    N = 513
+    mk = lambda: CudaEnv(rows, N, length=45, auto_reset=True).env
+    dev, cpy, mapped = mk(), mk(), mk()
+    for e in (dev, cpy, mapped):
+        e.reset_batched()
+    dev.set_bits_output(True); dev.set_view_outputs(False)
+    cpy.set_bits_output(True); cpy.set_view_outputs(False)
+    hbits = mapped.set_bits_output(True, host_mapped=True)
+    assert hbits.is_pinned()
+    rng = np.random.default_rng(6)
+    for t in range(70):
+        a = torch.as_tensor(biased_actions(rng, N, 0.6, t))
+        o = dev.step_batched(a.cuda())
+        h = cpy.step_host(a.pin_memory(), want_bits=True, want_views=True)
+        mapped.step_host_mapped(a.pin_memory())
+        want = o["obs_bits"].cpu()
+        assert torch.equal(h["obs_bits"], want), f"t={t} pm_step_host bits"
+        assert torch.equal(hbits, want), f"t={t} zero-copy bits"
+        assert torch.equal(h["view_actor"], o["view_actor"].cpu()) and torch.equal(h["view_critic"], o["view_critic"].cpu())
+        if t % 10 == 0:
+            np.testing.assert_array_equal(decode_obs_bits(hbits.numpy(), 7, 20), o["obs"].cpu().numpy())
+            assert torch.equal(decode_obs_bits(o["obs_bits"], 7, 20), o["obs"])      # torch decoder, on the device
+
+
+def test_cuda_layout_pool_new_maze_every_episode():
+    from parity_bodies import body_layout_pool
+    body_layout_pool(CudaEnv, N=600, T=150, L=37)
+    body_layout_pool(CudaEnv, N=100, T=90, L=5, seed=9, base=123456)
+
+
+def test_reset_to_another_layout_then_step_every_host_entry(tmp_path):
+    """reset(layout_file=...) to a board of the same and of a different size, then step through the single-env
+    reference API, pm_step_host_mapped and pm_step_host_pipelined: outputs follow the oracle on the NEW board
+    (cached descriptors / staging buffers must not point at the buffers of the old one)."""
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    names = ["tinyCapture", "smallCapture", "tinyCapture", "bloxCapture"]
+    env = gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, "tinyCapture.lay"), self_play=True, length=300)
+    rng = np.random.default_rng(12)
+    for name in names + ["capsSmall"]:
+        if name == "capsSmall":                                    # same size as smallCapture? no: a crafted board file
+            rows = helpers.load_traj("capsSmall")["layout"]
+            f = tmp_path / "capsSmall.lay"
+            f.write_text("\n".join(rows))
+            path = str(f)
+        else:
+            rows, path = lay_rows(name), os.path.join(LAYDIR, name + ".lay")
+        ref = oracle.OracleBatch(rows, 1, length=300)
+        obs, info = env.reset(layout_file=path)
+        robs, rlegal = ref.reset()
+        assert tuple(obs[0].shape) == (8, len(rows), len(rows[0]))
+        np.testing.assert_array_equal(torch.stack([obs[i] for i in range(4)]).cpu().numpy(), robs[0])
+        for t in range(25):
+            a = biased_actions(rng, 1, 0.6, t)[0]
+            o, rew, term, info = env.step({i: int(a[i]) for i in range(4)})        # the fast single-env path
+            r = ref.step(a[None])
+            np.testing.assert_array_equal(torch.stack([o[i] for i in range(4)]).cpu().numpy(), r["obs"][0], err_msg=f"{name} t={t}")
+            assert [rew[0], rew[1]] == list(r["reward"][0]) and info["score_change"] == int(r["score_change"][0])
+            assert [sum(1 << x for x in info["legal_actions"][i]) for i in range(4)] == list(r["legal"][0])
+    # batched env, host entries, after a change of board size
+    N = 200
+    benv = gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, "tinyCapture.lay"), self_play=True, length=300, num_envs=N)
+    a0 = torch.as_tensor(biased_actions(rng, N)).pin_memory()
+    benv.step_host_mapped(a0); benv.step_host_pipelined(a0, n_chunks=2); benv.step_host(a0)     # warm every cached descriptor
+    for name in ("smallCapture", "tinyCapture"):
+        rows = lay_rows(name)
+        benv.reset(layout_file=os.path.join(LAYDIR, name + ".lay"))
+        ref = oracle.OracleBatch(rows, N, length=300)
+        ref.reset()
+        for t in range(12):
+            a = biased_actions(rng, N, 0.6, t)
+            ah = torch.as_tensor(a).pin_memory()
+            h = (benv.step_host_mapped, lambda x: benv.step_host_pipelined(x, n_chunks=3), None)[t % 3]
+            r = ref.step(a)
+            if h is None:
+                out = benv.step_host(ah, want_obs=True)
+                np.testing.assert_array_equal(out["reward"].numpy().T, r["reward"])
+                np.testing.assert_array_equal(out["obs"].numpy().transpose(1, 0, 2, 3, 4), r["obs"])
+            else:
+                out = h(ah)
+                np.testing.assert_array_equal(out["reward"].numpy(), r["reward"], err_msg=f"{name} t={t}")
+                np.testing.assert_array_equal(out["legal"].numpy(), r["legal"])
+            np.testing.assert_array_equal(benv._obs.cpu().numpy().transpose(1, 0, 2, 3, 4), r["obs"], err_msg=f"{name} t={t} obs")
+
+
+def test_random_layout_single_env_new_maze_every_reset():
+    """random_layout=True, one env (the reference's own shape): every reset() draws a fresh mazeGenerator board from
+    the global `random` stream (gymPacMan.py:98-100, capture.py:905-911) and the episode that follows matches the
+    oracle on that board - across several episodes on one env object."""
+    import random
+    from pacman_marl_2025_b200 import mazeGenerator
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    random.seed(99)
+    env = gymPacMan_parallel_env(random_layout=True, self_play=True, length=40)
+    random.seed(99)
+    first = mazeGenerator.randomLayout().split("\n")
+    assert env.layout.layoutText == first
+    rng = np.random.default_rng(3)
+    seen = set()
+    for ep in range(4):
+        random.seed(1000 + ep)
+        want_rows = mazeGenerator.randomLayout().split("\n")
+        random.seed(1000 + ep)
+        obs, info = env.reset()
+        assert env.layout.layoutText == want_rows
+        seen.add("".join(want_rows))
+        ref = oracle.OracleBatch(want_rows, 1, length=40)
+        robs, _ = ref.reset()
+        np.testing.assert_array_equal(torch.stack([obs[i] for i in range(4)]).cpu().numpy(), robs[0])
+        done = False
+        t = 0
+        while not done:
+            a = biased_actions(rng, 1, 0.6, t)[0]
+            o, rew, term, info = env.step({i: int(a[i]) for i in range(4)})
+            r = ref.step(a[None])
+            np.testing.assert_array_equal(torch.stack([o[i] for i in range(4)]).cpu().numpy(), r["obs"][0], err_msg=f"ep {ep} t={t}")
+            assert [rew[0], rew[1]] == list(r["reward"][0])
+            done = term[0]
+            t += 1
+        assert t == 41
+    assert len(seen) == 4
+
+
+def test_random_layout_batched_pool_and_agent_keys():
+    """random_layout=True with num_envs > 1: a pool of host-generated mazes on the device, a new board per episode
+    picked in-kernel; envs really play different boards, and all invariants hold.  Also: in non-self-play the red
+    agents are keyed by objects like in the reference (gymPacMan.py:33-40), and plain indices still resolve."""
+    from pacman_marl_2025_b200.gymPacMan import OnDeviceAgent, gymPacMan_parallel_env
+    N = 512
+    env = gymPacMan_parallel_env(random_layout=True, self_play=False, enemieName="baselineTeam", length=30, num_envs=N,
+                                 auto_reset=True, layout_pool=16, opponent_seed=3)
+    assert isinstance(env.agents[0], OnDeviceAgent) and env.agents[1] == 1 and isinstance(env.agents[2], OnDeviceAgent)
+    obs, info = env.reset()
+    assert torch.equal(obs[env.agents[0]], obs[0]) and torch.equal(info["legal_actions"][2], info["legal_actions"][env.agents[2]])
+    ids0 = env.export_state()["layout_id"].copy()
+    assert len(set(ids0.tolist())) > 8
+    g = torch.Generator().manual_seed(0)
+    changed = 0
+    for t in range(70):
+        a = torch.randint(0, 5, (N, 4), generator=g)
+        o, rew, term, info = env.step({1: a[:, 1], 3: a[:, 3]})
+        assert set(o.keys()) == set(env.agents)
+    s = env.export_state()
+    changed = int((s["layout_id"] != ids0).sum())
+    assert changed > N // 2 and int(s["episode"].min()) >= 2
+    # walls of each env's CURRENT board show in plane 0 of its observation
+    walls = np.stack([env._layouts[i].walls.array.T for i in s["layout_id"]]).astype(np.float32)
+    np.testing.assert_array_equal(o[1][:, 0].cpu().numpy(), walls)

@@ -96,6 +96,16 @@ def test_emulated_baseline_team_matches_reference(name):
     helpers.replay(fx, helpers.BotReplayDriver(SingleEnvDriver(env, n=1), fx), where=name)
 
 
+@pytest.mark.parametrize("name", [n for n in helpers.traj_names() if n.startswith("rng_")])
+def test_emulated_bots_follow_the_references_real_rng_stream(name):
+    """pm_env_desc.bot_draws: fed the indices the reference's own `random.choice` returned (global MT19937,
+    random.seed(1)), the in-kernel randomTeam / baselineTeam replay BASELINE config 1 bit for bit."""
+    fx = helpers.load_traj(name)
+    env = EmuEnv(fx["layout"], 2, length=int(fx["length"]), E=2, KB=1, bot_kind=list(fx["bot_kind"]),
+                 bot_first_best=False, bot_draws=True)
+    helpers.replay(fx, helpers.BotReplayDriver(SingleEnvDriver(env, n=1), fx), where=name)
+
+
 def test_emulated_max_size_board():
     from parity_bodies import body_max_size_board
     body_max_size_board(lambda rows, n, **kw: EmuEnv(rows, n, E=8, KB=1, **kw), N=10, T=90)
@@ -131,3 +141,16 @@ def test_emulated_step_in_several_launches():
     body_step_in_several_launches(mk, sa, lay_rows("tinyCapture"), N=16, T=110)
     body_step_in_several_launches(mk, sa, helpers.load_traj("capsSmall")["layout"], N=12, T=90, splits=((0, 2), (2, 3), (3, 4)))
     body_step_in_several_launches(mk, sa, lay_rows("smallCapture"), N=10, T=60, splits=((0, 1), (1, 4)), bot_kind=[0, 0, 3, 0])
+
+
+@pytest.mark.parametrize("lay", ["tinyCapture", "smallCapture", "capsSmall", "odd15"])
+def test_emulated_packed_observation_bits(lay):
+    from parity_bodies import body_obs_bits
+    rows = lay_rows(lay) if lay.endswith("Capture") else helpers.load_traj(lay)["layout"]
+    body_obs_bits(lambda r, n, **kw: EmuEnv(r, n, E=8, KB=1, **kw), rows, N=20, T=130)
+
+
+def test_emulated_layout_pool_new_maze_every_episode():
+    from parity_bodies import body_layout_pool
+    body_layout_pool(lambda lays, n, **kw: EmuEnv(lays, n, E=8, KB=1, **kw), N=12, T=100, L=5)
+    body_layout_pool(lambda lays, n, **kw: EmuEnv(lays, n, E=4, KB=1, **kw), N=6, T=70, L=3, seed=5, base=1000)

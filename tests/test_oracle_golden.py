@@ -106,10 +106,14 @@ class OracleBotDriver(OracleDriver):
 
     def step(self, a):
         kind = self.fx["bot_kind"]
-        fed = np.where(kind >= 2, 7, np.asarray(a, np.int32))          # bot columns get garbage: must be ignored
+        fed = np.where(kind >= 1, 7, np.asarray(a, np.int32))          # bot columns get garbage: must be ignored
+        if int(self.fx.get("real_rng", 0)):
+            self.env.set_draws(self.fx["draws"][self.t][None])           # the reference's own random.choice indices
         o = self.env.step_bots(fed)
         np.testing.assert_array_equal(o["actions_used"][0], a, err_msg=f"step {self.t}: bot actions")
-        np.testing.assert_array_equal(o["best_masks"][0], self.fx["bot_best"][self.t], err_msg=f"step {self.t}: best sets")
+        if (kind >= 2).any():
+            np.testing.assert_array_equal(o["best_masks"][0][kind >= 2], self.fx["bot_best"][self.t][kind >= 2],
+                                          err_msg=f"step {self.t}: best sets")
         self.t += 1
         return {k: (v[0] if v is not None else None) for k, v in o.items()}
 
@@ -119,4 +123,14 @@ def test_baseline_team_bots_match_reference(name):
     """agents/baselineTeam.py (Offensive + Defensive reflex agents on the red side, gymPacMan.py:157)."""
     fx = helpers.load_traj(name)
     assert list(fx["bot_kind"]) == [2, 0, 3, 0]
+    helpers.replay(fx, OracleBotDriver(fx), where=name)
+
+
+@pytest.mark.parametrize("name", [n for n in helpers.traj_names() if n.startswith("rng_")])
+def test_bots_with_the_references_real_rng_stream(name):
+    """BASELINE config 1 as the reference plays it: the bots' `random.choice` draws from the global MT19937
+    (`random.seed(1)`; baselineTeam.py:92, randomTeam.py:100).  The fixture holds the index every call returned;
+    fed those indices, the oracle's bots reproduce the reference's trajectory bit for bit."""
+    fx = helpers.load_traj(name)
+    assert int(fx["real_rng"]) == 1 and list(fx["bot_kind"]) in ([2, 0, 3, 0], [1, 0, 1, 0])
     helpers.replay(fx, OracleBotDriver(fx), where=name)
