@@ -287,6 +287,35 @@ int pm_gae(const float *rew, const float *val, const float *done, const float *l
  * consecutive group of mb indices, out = (adv[idx]-mean)/(std_unbiased+1e-8). */
 int pm_adv_norm(const float *adv, const int64_t *inds, float *out, int64_t n, int mb, pm_stream_t stream);
 
+/* ---- ABI 7: the PPO minibatch pipeline around the networks -------- */
+/* b_obs[mb].to(device) / b_merged[mb] (pacman_mappo_resnet.py:569-573) over the uint8 rollout buffer:
+ * dst[r][:] = (float or bf16) src[idx[r]][:], rows of row_bytes bytes (a multiple of 8).  src [dev] 8-byte
+ * aligned, dst [dev] 16-byte aligned, idx [dev] int64 [n_rows].                                          */
+int pm_gather_rows(const uint8_t *src, const int64_t *idx, int64_t n_rows, int row_bytes, void *dst, int dst_bf16,
+                   pm_stream_t stream);
+/* The minibatch loss of pacman_mappo_resnet.py:575-585 and its gradient in one launch:
+ *   lp = log_softmax(logits)[action]; ratio = exp(lp - old_logp);
+ *   pg = -min(adv*ratio, adv*clamp(ratio, 1-eps, 1+eps)).mean(); vl = 0.5*((value - ret)^2).mean();
+ *   loss = pg + vf_coef*vl - ent_coef*entropy.mean()
+ * logits [B][n_actions <= 8] fp32; values [n_values] with sample i reading values[i % n_values] (n_values = B, or
+ * B/2 when both learners of an env-step share one critic value); actions int64; old_logp / adv / ret fp32 [B].
+ * Outputs: dlogits [B][n_actions], dvalues [B] (per sample) = d loss / d input; stats[8] = loss, pg, vl,
+ * entropy mean, clip fraction (`:597-600`).  scratch: pm_ppo_scratch_bytes() bytes, zeroed once by the caller.  */
+size_t pm_ppo_scratch_bytes(void);
+int pm_ppo_loss(const float *logits, const float *values, const int64_t *actions, const float *old_logp,
+                const float *adv, const float *ret, int64_t B, int64_t n_values, int n_actions, double clip_eps,
+                double vf_coef, double ent_coef, float *dlogits, float *dvalues, float *stats, void *scratch,
+                pm_stream_t stream);
+/* nn.utils.clip_grad_norm_ + optimizer.step() (Adam, eps as given, no weight decay) + the EMA of the policy
+ * (pacman_mappo_resnet.py:588-595) over FLAT fp32 buffers of n elements: grads are first scaled by grad_scale
+ * (1/world after a sum all-reduce) and clipped to max_grad_norm; ema (may be NULL) = ema*decay + p*(1-decay).
+ * step = 1 for the first update.  grad_norm_out [dev] float: the norm before clipping.  scratch:
+ * pm_adam_scratch_bytes() bytes, zeroed once by the caller.  No host synchronisation.                      */
+size_t pm_adam_scratch_bytes(void);
+int pm_adam_ema(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, float *ema, int64_t n, int64_t step,
+                double lr, double beta1, double beta2, double eps, double max_grad_norm, double grad_scale,
+                double ema_decay, float *grad_norm_out, void *scratch, pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

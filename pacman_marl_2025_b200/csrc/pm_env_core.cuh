@@ -965,11 +965,14 @@ PM_HD uint32_t pm_cat_word(const PmParams &P, const uint32_t *st, const PmSmem &
 #endif
     }
     const int b0 = 32 * j;
-    w |= pm_extract32(U.food, E1, NW, b0 - 6 * HW) & m6[j];
-    w |= pm_extract32(U.food, E1, NW, b0 - 7 * HW) & m7[j];
+    // a word overlaps at most two of the eight planes: the half-board masks are zero everywhere else, and consecutive
+    // lanes hold consecutive words, so these branches are nearly uniform within a warp
+    uint32_t mk;
+    if ((mk = m6[j]) != 0) w |= pm_extract32(U.food, E1, NW, b0 - 6 * HW) & mk;
+    if ((mk = m7[j]) != 0) w |= pm_extract32(U.food, E1, NW, b0 - 7 * HW) & mk;
     if (U.caps) {
-        w |= pm_extract32(U.caps, E1, NW, b0 - 2 * HW) & m2[j];
-        w |= pm_extract32(U.caps, E1, NW, b0 - 3 * HW) & m3[j];
+        if ((mk = m2[j]) != 0) w |= pm_extract32(U.caps, E1, NW, b0 - 2 * HW) & mk;
+        if ((mk = m3[j]) != 0) w |= pm_extract32(U.caps, E1, NW, b0 - 3 * HW) & mk;
     }
     unsigned d;
     d = U.p_own - (unsigned)b0;  if (d < 32u) w |= 1u << d;
@@ -1124,56 +1127,77 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
 // the group = byte (L & 3) of word 32g + 8r + (L >> 2), spread to one bit per byte by a multiply-and-mask.
 PM_HD uint32_t pm_spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x01010101u; }
 
+// One (view, word) ITEM per lane: the CTA's E x 3 views x NCAT words form one flat list that the warps walk in
+// chunks of 32, so no lane idles on the short tail of a view (35 words on tinyCapture = one full pass + 3 lanes in
+// the per-view schedule this replaces).  Each lane expands its own word: 32 bits -> 32 bytes, written as ONE
+// 256-bit store (two 128-bit / four 64-bit stores when the view's row pitch is not 32- / 16-byte aligned); the
+// lanes of a warp cover a contiguous 1 KB run.  No shuffles, no second pass for the own-cell values: the lane that
+// owns the word holding the patched element substitutes the byte before storing.
 template <int MODE>
 PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps,
                            int lane, int64_t n0, int mslot0) {
     const int NCAT = P.NCAT, E = P.E;
-    const int n8 = P.HW;                               // 8-byte chunks per view (8*HW / 8)
-    const int ngroups = (NCAT + 31) >> 5;
-    for (int u = warp; u < 3 * E; u += nwarps) {
+    const int nbytes = 8 * P.HW;                        // bytes per view
+    const int nitems = 3 * E * NCAT;
+    const uint32_t magic = 0xffffffffu / (uint32_t)NCAT + 1u;      // i / NCAT == (i * magic) >> 32 for i < 2^16
+#if defined(__CUDA_ARCH__)
+    const int lanes = 32, first = lane;
+#else
+    if (lane != 0) return;                              // host emulation: lane 0 plays the whole warp
+    const int lanes = 1, first = 0;
+#endif
+    for (int i = warp * 32 + first; i < nitems; i += (lanes == 1 ? 1 : nwarps * 32)) {
+#if !defined(__CUDA_ARCH__)
+        if ((i >> 5) % nwarps != warp) continue;        // the chunks of 32 items this warp owns
+#endif
+        const int u = (int)(((unsigned long long)(uint32_t)i * magic) >> 32), j = i - u * NCAT;
         const int v = u >> P.lgE, el = u & (E - 1);
         PmUnit U;
         if (!pm_view_unit_load<MODE>(P, sm, M, v, el, mslot0, U)) continue;
-        uint8_t *dstb = (v == 2 ? P.view_critic : P.view_actor + (size_t)v * P.view_actor_stride) + (size_t)(n0 + el) * 8 * P.HW;
-        unsigned long long *dst = reinterpret_cast<unsigned long long *>(dstb);
+        uint8_t *dstb = (v == 2 ? P.view_critic : P.view_actor + (size_t)v * P.view_actor_stride) + (size_t)(n0 + el) * nbytes;
+        const uint32_t word = pm_cat_word(P, st, M, U, j);
+        uint32_t o[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = pm_spread4((word >> (4 * q)) & 15u);
+        // own-cell values 1 + numCarrying (gymPacMan.py:205); merged view: elementwise max of the two learners' planes
+        const uint32_t lo = 32u * (uint32_t)j;
+        uint32_t pv = 0, pe = 0xffffffffu;
+        if (U.patch != 0xffffffffu && (U.patch & 0xffff) - lo < 32u) { pe = (U.patch & 0xffff) - lo; pv = U.patch >> 16; }
+        if (U.patch2 != 0xffffffffu && (U.patch2 & 0xffff) - lo < 32u) {
+            const uint32_t e2 = (U.patch2 & 0xffff) - lo, v2 = U.patch2 >> 16;
+            if (pe == e2) pv = v2 > pv ? v2 : pv;
+            else if (pe == 0xffffffffu) { pe = e2; pv = v2; }
+            else {                                      // two different cells inside one word: apply the first now
+                const uint32_t sh0 = 8 * (pe & 3);
+                o[pe >> 2] = (o[pe >> 2] & ~(0xffu << sh0)) | ((pv > 255 ? 255u : pv) << sh0);
+                pe = e2; pv = v2;
+            }
+        }
+        if (pe != 0xffffffffu) {
+            const uint32_t sh0 = 8 * (pe & 3);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if ((int)(pe >> 2) == q) o[q] = (o[q] & ~(0xffu << sh0)) | ((pv > 255 ? 255u : pv) << sh0);
+        }
+        uint8_t *d = dstb + 32 * j;
+        const int left = nbytes - 32 * j;               // >= 8 and a multiple of 8
 #if defined(__CUDA_ARCH__)
-        const int sh = (lane & 3) * 8, src = lane >> 2;
-        for (int g = 0; g < ngroups; ++g) {
-            const int j = 32 * g + lane;
-            const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
-            const int fbase = 128 * g + lane;
-            const int left = n8 - 128 * g, nr = left >= 128 ? 4 : (left + 31) >> 5;     // only the rounds that hold data
-            for (int r = 0; r < nr; ++r) {
-                const uint32_t w = __shfl_sync(0xffffffffu, word, 8 * r + src) >> sh;
-                const int f = fbase + 32 * r;
-                if (f < n8) dst[f] = (unsigned long long)pm_spread4(w & 15u) | (unsigned long long)pm_spread4((w >> 4) & 15u) << 32;
-            }
+        if (left >= 32 && ((size_t)d & 31) == 0) {
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]),
+                         "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7])
+                         : "memory");
+        } else if (left >= 32 && ((size_t)d & 15) == 0) {
+            reinterpret_cast<pm_u4 *>(d)[0] = pm_u4{o[0], o[1], o[2], o[3]};
+            reinterpret_cast<pm_u4 *>(d)[1] = pm_u4{o[4], o[5], o[6], o[7]};
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (8 * q < left) reinterpret_cast<unsigned long long *>(d)[q] = (unsigned long long)o[2 * q] | (unsigned long long)o[2 * q + 1] << 32;
         }
-        __syncwarp();
-        if (lane == 0) {
 #else
-        if (lane != 0) continue;
-        for (int j = 0; j < NCAT; ++j) {
-            const uint32_t word = pm_cat_word(P, st, M, U, j);
-            for (int b = 0; b < 4; ++b) {
-                const int f = 4 * j + b;
-                if (f < n8) {
-                    const uint32_t w = word >> (8 * b);
-                    dst[f] = (unsigned long long)pm_spread4(w & 15u) | (unsigned long long)pm_spread4((w >> 4) & 15u) << 32;
-                }
-            }
-        }
-        {
+        for (int q = 0; q < 4; ++q)
+            if (8 * q < left) reinterpret_cast<unsigned long long *>(d)[q] = (unsigned long long)o[2 * q] | (unsigned long long)o[2 * q + 1] << 32;
 #endif
-            // own-cell values 1 + numCarrying; merged view: elementwise max of the two learners' planes
-            if (U.patch != 0xffffffffu) dstb[U.patch & 0xffff] = (uint8_t)(U.patch >> 16 > 255 ? 255 : U.patch >> 16);
-            if (U.patch2 != 0xffffffffu) {
-                const uint32_t v2 = U.patch2 >> 16 > 255 ? 255 : U.patch2 >> 16;
-                uint8_t *q = dstb + (U.patch2 & 0xffff);
-                const bool same = U.patch != 0xffffffffu && (U.patch & 0xffff) == (U.patch2 & 0xffff);
-                if (!same || v2 > *q) *q = (uint8_t)v2;
-            }
-        }
     }
 }
 

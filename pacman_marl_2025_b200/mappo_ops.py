@@ -64,3 +64,120 @@ def normalize_advantages(adv_flat, inds, minibatch):
         _lib.check(L.pm_adv_norm(a.data_ptr(), idx.data_ptr(), out.data_ptr(), int(idx.numel()), int(minibatch),
                                  _stream(dev)), "pm_adv_norm")
     return out
+
+
+# ---- the PPO minibatch pipeline around the networks (pacman_mappo_resnet.py:555-600) -----------
+def gather_rows(src_u8: torch.Tensor, idx: torch.Tensor, out_dtype=torch.float32, out: torch.Tensor | None = None):
+    """``b_obs[mb].to(device)`` (`:569-573`) on the uint8 rollout buffer: ``src_u8`` [S, ...] uint8 (contiguous
+    rows), ``idx`` int64 [n] -> [n, ...] in ``out_dtype`` (fp32 or bf16); the widening is fused into the gather."""
+    L = _lib.load()
+    if not src_u8.is_cuda or src_u8.dtype != torch.uint8 or not src_u8.is_contiguous():
+        raise RuntimeError("gather_rows expects a contiguous uint8 CUDA tensor; there is no CPU fallback")
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("out_dtype must be float32 or bfloat16")
+    dev = src_u8.device
+    row = int(src_u8[0].numel())
+    idx = idx.to(device=dev, dtype=torch.int64).contiguous()
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n,) + tuple(src_u8.shape[1:]), dtype=out_dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.pm_gather_rows(src_u8.data_ptr(), idx.data_ptr(), n, row, out.data_ptr(),
+                                    int(out_dtype == torch.bfloat16), _stream(dev)), "pm_gather_rows")
+    return out
+
+
+_scratch = {}
+
+
+def _zeroed_scratch(kind: str, nbytes: int, dev):
+    key = (kind, dev.index)
+    if key not in _scratch:
+        _scratch[key] = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    return _scratch[key]
+
+
+class _PPOLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, values, actions, old_logp, adv, ret, clip_eps, vf_coef, ent_coef):
+        L = _lib.load()
+        dev = logits.device
+        lg, v = logits.contiguous().float(), values.contiguous().float()
+        B, A = lg.shape
+        dl = torch.empty_like(lg)
+        dv = torch.empty(B, dtype=torch.float32, device=dev)
+        stats = torch.empty(8, dtype=torch.float32, device=dev)
+        scratch = _zeroed_scratch("ppo", int(L.pm_ppo_scratch_bytes()), dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.pm_ppo_loss(lg.data_ptr(), v.data_ptr(), actions.contiguous().data_ptr(),
+                                     old_logp.contiguous().float().data_ptr(), adv.contiguous().float().data_ptr(),
+                                     ret.contiguous().float().data_ptr(), B, v.numel(), A, float(clip_eps), float(vf_coef),
+                                     float(ent_coef), dl.data_ptr(), dv.data_ptr(), stats.data_ptr(), scratch.data_ptr(),
+                                     _stream(dev)), "pm_ppo_loss")
+        ctx.save_for_backward(dl, dv)
+        ctx.nv = v.numel()
+        ctx.mark_non_differentiable(stats)
+        return stats[0], stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_stats):
+        dl, dv = ctx.saved_tensors
+        if ctx.nv != dv.numel():                        # both learners of an env-step share one critic value
+            dv = dv.view(-1, ctx.nv).sum(0)
+        return dl * g_loss, dv * g_loss, None, None, None, None, None, None, None
+
+
+def ppo_loss(logits, values, actions, old_logp, norm_adv, returns, clip_eps, vf_coef, ent_coef):
+    """The minibatch loss of `pacman_mappo_resnet.py:575-585` and its gradient in ONE kernel launch.
+    ``logits`` [B, 5] (actor head output), ``values`` [B] or [B/2] (sample i reads ``values[i % len]``).  Returns
+    (loss, stats) with stats[1:5] = pg loss, value loss, entropy mean, clip fraction (`:597-600`); ``loss`` is
+    differentiable w.r.t. logits and values."""
+    if not logits.is_cuda:
+        raise RuntimeError("ppo_loss expects CUDA tensors; there is no CPU fallback")
+    return _PPOLoss.apply(logits, values, actions, old_logp, norm_adv, returns, clip_eps, vf_coef, ent_coef)
+
+
+class FlatAdamEMA:
+    """``clip_grad_norm_`` + ``Adam.step`` + the EMA copy of the policy (`pacman_mappo_resnet.py:588-595`) as two
+    kernels over flat buffers.  The module's parameters (and the EMA module's) are re-pointed to views of one flat
+    fp32 buffer each; gradients come from :class:`sharding.FlatGradBucket`'s flat buffer.  Same arithmetic as
+    ``torch.optim.Adam(lr, eps=1e-5)`` followed by ``ema.mul_(d).add_(p, alpha=1-d)``."""
+
+    def __init__(self, module, ema_module, grad_flat, lr, betas=(0.9, 0.999), eps=1e-5, ema_decay=0.995, max_grad_norm=0.5):
+        self.L = _lib.load()
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        self.flat = self._flatten(self.params)
+        self.ema_flat = self._flatten([p for p in ema_module.parameters() if p.requires_grad]) if ema_module is not None else None
+        if grad_flat.numel() != self.flat.numel():
+            raise ValueError("gradient bucket and parameters differ in size")
+        self.grad = grad_flat
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.lr, self.betas, self.eps, self.ema_decay, self.max_grad_norm = lr, betas, eps, ema_decay, max_grad_norm
+        self.step_count = 0
+        dev = self.flat.device
+        self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.scratch = torch.zeros(int(self.L.pm_adam_scratch_bytes()), dtype=torch.uint8, device=dev)
+
+    @staticmethod
+    def _flatten(params):
+        flat = torch.cat([p.data.reshape(-1) for p in params]).contiguous()
+        o = 0
+        for p in params:
+            p.data = flat[o:o + p.numel()].view_as(p)
+            o += p.numel()
+        return flat
+
+    def step(self, grad_scale: float = 1.0):
+        """One optimizer step on the gradient bucket (scaled by ``grad_scale``, e.g. 1/world after a sum all-reduce).
+        Returns the device scalar holding the gradient norm before clipping."""
+        self.step_count += 1
+        dev = self.flat.device
+        with torch.cuda.device(dev):
+            _lib.check(self.L.pm_adam_ema(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                          self.ema_flat.data_ptr() if self.ema_flat is not None else None,
+                                          self.flat.numel(), self.step_count, float(self.lr), float(self.betas[0]),
+                                          float(self.betas[1]), float(self.eps), float(self.max_grad_norm), float(grad_scale),
+                                          float(self.ema_decay), self.norm.data_ptr(), self.scratch.data_ptr(), _stream(dev)),
+                       "pm_adam_ema")
+        return self.norm

@@ -57,10 +57,14 @@ SHAPING_SCALE = 0.1
 EVAL_FREQ = 50
 EVAL_EPISODES = 10
 EMA_DECAY = 0.995
-# the reference's curriculum pools (`:40-42`) restricted to the opponents that exist on the device
+# the reference's curriculum pools (`:40-42`).  randomTeam and baselineTeam run inside the step kernel; the other four
+# are the reference's CPU search bots: they join the pools when TrainConfig.reference_root points at a checkout of
+# the reference, and are then served through the host-bot hook (gymPacMan_parallel_env(bot_team=...), each bot asked
+# at its own sub-move on the reference's own GameState - reference_bridge.py).
 EASY_TEAMS = ["randomTeam"]
-MEDIUM_TEAMS: List[str] = []          # MCTSTeam / heuristicTeam: CPU search bots, outside the GPU path
-HARD_TEAMS = ["baselineTeam"]         # (AstarTeam / approxQTeam: likewise CPU-only)
+MEDIUM_TEAMS = ["MCTSTeam", "heuristicTeam"]
+HARD_TEAMS = ["baselineTeam", "AstarTeam", "approxQTeam"]
+ON_DEVICE = ("randomTeam", "baselineTeam")
 
 # canonical (blue-perspective) view of a red agent: mirror x, swap the capsule and food plane pairs
 _CANON_PLANES = [0, 1, 3, 2, 4, 5, 7, 6]
@@ -142,9 +146,36 @@ class MAPPOAgent(nn.Module):
     def logits(self, obs):
         return self.actor_head(self.actor_backbone(obs))
 
+    # How the critic's two encoder layers are evaluated.  The PARAMETERS are nn.TransformerEncoder's (identical
+    # state_dict keys); only the op sequence differs:
+    #   "module"  nn.TransformerEncoder.forward (the reference's call, `:168-176`)
+    #   "bmm"     the same post-norm layer written out with torch.bmm: scores = (q / sqrt(hd)) k^T, softmax, P v.
+    #             With 4 heads of dimension 8 over H*W tokens, PyTorch's fused fp32 attention kernels
+    #             (mem-efficient fmha) spend 22 ms per layer on a 4 096-sample minibatch, most of a PPO update;
+    #             batched TF32 GEMMs + one softmax do the same arithmetic in a fraction of that.
+    attn_impl = "bmm"
+
+    def _encoder_layer_bmm(self, layer, x):
+        """One nn.TransformerEncoderLayer (norm_first=False, relu, dropout 0) on x [S, B, E] with explicit ops."""
+        sa = layer.self_attn
+        S, B, E = x.shape
+        h = sa.num_heads
+        hd = E // h
+        qkv = nn.functional.linear(x, sa.in_proj_weight, sa.in_proj_bias)             # [S, B, 3E]
+        q, k, v = (t.reshape(S, B * h, hd).transpose(0, 1) for t in qkv.chunk(3, dim=-1))   # [B*h, S, hd]
+        p = torch.softmax(torch.bmm(q * (1.0 / math.sqrt(hd)), k.transpose(1, 2)), dim=-1)
+        o = torch.bmm(p, v).transpose(0, 1).reshape(S, B, E)
+        x = layer.norm1(x + sa.out_proj(o))
+        return layer.norm2(x + layer.linear2(nn.functional.relu(layer.linear1(x))))
+
     def _forward_critic(self, merged):
         x = self.pos_encoder(self.critic_projector(merged))
-        x = self.critic_transformer(x.flatten(2).permute(2, 0, 1))        # [H*W tokens, B, d]
+        x = x.flatten(2).permute(2, 0, 1)                                  # [H*W tokens, B, d]
+        if self.attn_impl == "bmm":
+            for layer in self.critic_transformer.layers:
+                x = self._encoder_layer_bmm(layer, x)
+        else:
+            x = self.critic_transformer(x)
         return self.critic_head(x.mean(dim=0))
 
     def get_value(self, merged):
@@ -205,6 +236,13 @@ def compute_gae(rewards, values, dones, last_value, gamma=GAMMA):
     return mappo_ops.compute_gae(rewards, values, dones, last_value, gamma, GAE_LAMBDA)
 
 
+def curriculum_pools(reference_root: str = ""):
+    """(easy, medium, hard) opponent pools of the curriculum (`:40-42, 396-438`).  With a checkout of the reference
+    they are the reference's lists; without one only the teams that run inside the step kernel remain."""
+    have = lambda teams: [t for t in teams if t in ON_DEVICE or reference_root]
+    return have(EASY_TEAMS), have(MEDIUM_TEAMS), have(HARD_TEAMS)
+
+
 # ---- the trainer ---------------------------------------------------------------------------------------
 @dataclass
 class TrainConfig:
@@ -222,11 +260,17 @@ class TrainConfig:
     pair_agents: bool = True          # minibatches are drawn over env-steps and hold BOTH learners of each, so the critic
                                       # runs once per env-step (the reference shuffles (step, agent) samples and runs it
                                       # once per sample on the same merged observation, `:563-575`); False = reference order
+    fused_pipeline: bool = True       # the minibatch pipeline around the nets as kernels (row f3): uint8 gather + widen,
+                                      # fused PPO loss + gradient, clip + Adam + EMA over flat buffers; False = the
+                                      # same steps as eager PyTorch ops (kept as the in-repo cross-check)
     easy_until: int = 200             # updates <= this: EASY_TEAMS only (`:396-402`)
     selfplay_after: int = 800         # update index after which self-play opponents enter the mix (`:404-438`)
     log_every: int = 1
     checkpoint_every: int = 250
     checkpoint_dir: str = "."
+    reference_root: str = ""          # a checkout of the reference: enables its CPU bot teams (MCTSTeam, heuristicTeam,
+                                      # AstarTeam, approxQTeam) as host-side opponents in the curriculum (`:40-42`);
+                                      # every env then asks a Python bot twice per step - use a modest num_envs
     load_checkpoint: str = ""         # LOAD_CHECKPOINT (`:44, 368-372`): a state_dict saved by this trainer or the reference's
     start_update: int = 0             # START_UPDATES (`:45`)
 
@@ -274,8 +318,13 @@ class MAPPOTrainer:
         self.opponent = copy.deepcopy(self.agent).eval()
         self._params = list(self.agent.parameters())
         self._ema_params = list(self.ema_agent.parameters())
-        self.optimizer = torch.optim.Adam(self.agent.parameters(), lr=LR_START, eps=1e-5, fused=cfg.fast_math)   # `:366`; one fused multi-tensor kernel per step
         self.bucket = sharding.FlatGradBucket(self.agent.parameters())
+        if cfg.fused_pipeline:
+            # parameters / EMA / Adam moments as flat fp32 buffers: clip + Adam + EMA are two kernels per step
+            self.optimizer = mappo_ops.FlatAdamEMA(self.agent, self.ema_agent, self.bucket.flat, lr=LR_START, eps=1e-5,
+                                                   ema_decay=EMA_DECAY, max_grad_norm=MAX_GRAD_NORM)   # `:366, 588-595`
+        else:
+            self.optimizer = torch.optim.Adam(self.agent.parameters(), lr=LR_START, eps=1e-5, fused=cfg.fast_math)   # `:366`
         self.opponent_pool = deque(maxlen=OPPONENT_POOL_SIZE)
         self.opponent_pool.append(copy.deepcopy(self.ema_agent.state_dict()))
         self.rollout = Rollout(cfg.num_steps, cfg.num_envs, self.obs_shape, self.device)
@@ -306,11 +355,12 @@ class MAPPOTrainer:
         lr = LR_START - (LR_START - LR_END) * progress
         ent_coef = ENT_COEF_START - (ENT_COEF_START - ENT_COEF_END) * progress
         clip_eps = 0.1 if update > cfg.selfplay_after else CLIP_EPS
+        easy, medium, hard = curriculum_pools(cfg.reference_root)
         pick = lambda pool: str(pool[int(self.rng.integers(len(pool)))])
         if update <= cfg.easy_until:
-            mode, play_as_red = pick(EASY_TEAMS), False
+            mode, play_as_red = pick(easy), False
         elif update <= cfg.selfplay_after:
-            mode, play_as_red = pick(EASY_TEAMS + MEDIUM_TEAMS + HARD_TEAMS * 5), False
+            mode, play_as_red = pick(easy + medium + hard * 5), False
         else:
             r = self.rng.random()
             if r < 0.40:
@@ -318,7 +368,7 @@ class MAPPOTrainer:
             elif r < 0.60:
                 mode, play_as_red = "Self(Old)", bool(self.rng.random() > 0.5)
             else:
-                mode, play_as_red = pick(HARD_TEAMS * 5 + MEDIUM_TEAMS + EASY_TEAMS), False
+                mode, play_as_red = pick(hard * 5 + medium + easy), False
         return dict(lr=lr, ent_coef=ent_coef, clip_eps=clip_eps, mode=mode, play_as_red=play_as_red)
 
     # ------------------------------------------------------------------ rollout
@@ -328,9 +378,15 @@ class MAPPOTrainer:
         cfg, ro = self.cfg, self.rollout
         T, N = cfg.num_steps, cfg.num_envs
         selfplay = mode.startswith("Self")
-        env = self.env_selfplay if selfplay else self.env_bot
-        if not selfplay and env.enemieName != mode:
-            env.reset(enemieName=mode)                                # `:399, 406, 436`: env.reset(enemieName=opp_name)
+        if selfplay:
+            env = self.env_selfplay
+        elif mode in ON_DEVICE:
+            env = self.env_bot
+            if env.enemieName != mode:
+                env.reset(enemieName=mode)                            # `:399, 406, 436`: env.reset(enemieName=opp_name)
+        else:
+            env = self._host_bot_env(mode)                            # the reference's CPU bots, asked at their own sub-move
+        use_views = cfg.use_views and env._bot_team is None           # (a step split over two launches has no fused views)
         if mode == "Self(Curr)":
             self.opponent.load_state_dict(self.agent.state_dict())
         elif mode == "Self(Old)":
@@ -348,7 +404,7 @@ class MAPPOTrainer:
             a_in, m = self._views(o4, learner_ids, play_as_red)
             ro.obs[slot] = a_in.view(2, N, *shp)
             ro.merged[slot] = m
-        if cfg.use_views:
+        if use_views:
             env.observe_views(play_as_red, ro.obs[0], ro.merged[0])
         else:
             store_views(0, obs4)
@@ -371,11 +427,11 @@ class MAPPOTrainer:
                     o_act = canonicalize_action(o_act.view(2, N), not play_as_red)
                     actions[:, opp_ids[0]] = o_act[0]
                     actions[:, opp_ids[1]] = o_act[1]
-                if cfg.use_views:                                     # next step's network inputs land in slot t+1;
+                if use_views:                                         # next step's network inputs land in slot t+1;
                     env.set_view_outputs(play_as_red, ro.obs[t + 1], ro.merged[t + 1], raw_obs=selfplay)   # raw obs only for the opponent net
-                out = env.step_batched(actions)
+                out = env._step_with_host_bots(actions) if env._bot_team is not None else env.step_batched(actions)
                 obs4 = out["obs"]                                     # finished envs already show the new episode
-                if not cfg.use_views:
+                if not use_views:
                     store_views(t + 1, obs4)
                 ro.reward[t, 0] = out["shaped_reward"][learner_ids[0]]
                 ro.reward[t, 1] = out["shaped_reward"][learner_ids[1]]
@@ -400,6 +456,24 @@ class MAPPOTrainer:
             last_value = self.agent.get_value(ro.merged[T].float()).float()
         return last_value, stats
 
+    def _host_bot_env(self, team: str):
+        """An env whose red side is played by the reference's own CPU bots of `team` (agents/<team>.py), one pair of
+        bot objects serving every env of the batch through the host-bot hook."""
+        if not hasattr(self, "_host_envs"):
+            self._host_envs = {}
+        if team not in self._host_envs:
+            from . import reference_bridge as RB
+            mods = RB.load_reference(self.cfg.reference_root)
+            e0 = self.env_bot
+            self._host_envs[team] = gymPacMan_parallel_env(
+                layouts=[e0.layout], length=self.cfg.length, reward_forLegalAction=True, defenceReward=True, self_play=False,
+                enemieName=team, bot_team=RB.make_bot_team(mods, team), state_factory=RB.state_factory(mods),
+                num_envs=self.cfg.num_envs, device=self.device, auto_reset=True, env_index_base=e0.env_index_base,
+                shaping_scale=SHAPING_SCALE)
+        env = self._host_envs[team]
+        env.reset()
+        return env
+
     # ------------------------------------------------------------------ update
     def update(self, last_value, sched):
         """GAE + PPO epochs (`:540-600`).  Returns dict of mean losses."""
@@ -413,11 +487,17 @@ class MAPPOTrainer:
         b_adv, b_ret = adv.reshape(-1), ret.reshape(-1)
         S = T * N * 2
         mb = S // cfg.num_minibatches
-        for g in self.optimizer.param_groups:
-            g["lr"] = sched["lr"]
+        fused = cfg.fused_pipeline
+        if fused:
+            self.optimizer.lr = sched["lr"]
+        else:
+            for g in self.optimizer.param_groups:
+                g["lr"] = sched["lr"]
         clip_eps, ent_coef = sched["clip_eps"], sched["ent_coef"]
         sums = torch.zeros(4, device=self.device)
         steps = 0
+        in_dtype = torch.bfloat16 if (fused and cfg.amp_bf16) else torch.float32
+        widen = (lambda buf, idx: mappo_ops.gather_rows(buf, idx, in_dtype)) if fused else (lambda buf, idx: buf[idx].float())
         for _ in range(cfg.update_epochs):
             if self._pair:
                 # shuffle env-steps e = (t, env); sample indices of its two learners: (t, 0, env) and (t, 1, env)
@@ -433,27 +513,42 @@ class MAPPOTrainer:
                 norm_adv = norm_adv_all[k * mb:(k + 1) * mb]
                 with self._autocast():
                     if self._pair:
-                        v1 = self.agent.get_value(b_merged[pe[k * half:(k + 1) * half]].float())
-                        _, lps, ent = self.agent.evaluate(b_obs[idx].float(), None, b_act[idx])
-                        vals = torch.cat([v1, v1])
+                        vals = self.agent.get_value(widen(b_merged, pe[k * half:(k + 1) * half]))      # one value per env-step
                     else:
                         midx = torch.div(idx, 2 * N, rounding_mode="floor") * N + idx % N   # (t, env) of sample (t, agent, env)
-                        vals, lps, ent = self.agent.evaluate(b_obs[idx].float(), b_merged[midx].float(), b_act[idx])
-                vals, lps, ent = vals.float(), lps.float(), ent.float()
-                ratio = (lps - b_logp[idx]).exp()
-                pg = -torch.min(norm_adv * ratio, norm_adv * torch.clamp(ratio, 1 - clip_eps, 1 + clip_eps)).mean()
-                vl = 0.5 * ((vals - b_ret[idx]) ** 2).mean()
-                loss = pg + VF_COEF * vl - ent_coef * ent.mean()
-                self.bucket.zero_()
-                loss.backward()
-                self.bucket.all_reduce_mean_()                        # the one data-path collective of the trainer
-                self.bucket.clip_grad_norm_(MAX_GRAD_NORM)
-                self.optimizer.step()
-                with torch.no_grad():
-                    torch._foreach_mul_(self._ema_params, EMA_DECAY)
-                    torch._foreach_add_(self._ema_params, self._params, alpha=1 - EMA_DECAY)
-                    sums += torch.stack([pg.detach(), vl.detach(), ent.mean().detach(),
-                                         ((ratio - 1).abs() > clip_eps).float().mean()])
+                        vals = self.agent.get_value(widen(b_merged, midx))
+                    logits = self.agent.logits(widen(b_obs, idx))
+                vals, logits = vals.float(), logits.float()
+                if fused:
+                    # log-softmax, ratio, clipped surrogate, value loss, entropy, the four logged scalars AND the
+                    # gradient w.r.t. logits / values: one launch (`:575-585, 597-600`)
+                    loss, st = mappo_ops.ppo_loss(logits, vals, b_act[idx], b_logp[idx], norm_adv, b_ret[idx], clip_eps,
+                                                  VF_COEF, ent_coef)
+                    self.bucket.zero_()
+                    loss.backward()
+                    self.bucket.all_reduce_sum_()                     # the one data-path collective of the trainer
+                    self.optimizer.step(grad_scale=1.0 / self.world)  # mean over ranks, clip, Adam, EMA: two kernels
+                    sums += st[1:5]
+                else:
+                    lg = torch.log_softmax(logits, dim=-1)
+                    lps = lg.gather(1, b_act[idx].unsqueeze(1)).squeeze(1)
+                    ent = -(lg.exp() * lg).sum(-1)
+                    if self._pair:
+                        vals = torch.cat([vals, vals])
+                    ratio = (lps - b_logp[idx]).exp()
+                    pg = -torch.min(norm_adv * ratio, norm_adv * torch.clamp(ratio, 1 - clip_eps, 1 + clip_eps)).mean()
+                    vl = 0.5 * ((vals - b_ret[idx]) ** 2).mean()
+                    loss = pg + VF_COEF * vl - ent_coef * ent.mean()
+                    self.bucket.zero_()
+                    loss.backward()
+                    self.bucket.all_reduce_mean_()
+                    self.bucket.clip_grad_norm_(MAX_GRAD_NORM)
+                    self.optimizer.step()
+                    with torch.no_grad():
+                        torch._foreach_mul_(self._ema_params, EMA_DECAY)
+                        torch._foreach_add_(self._ema_params, self._params, alpha=1 - EMA_DECAY)
+                        sums += torch.stack([pg.detach(), vl.detach(), ent.mean().detach(),
+                                             ((ratio - 1).abs() > clip_eps).float().mean()])
                 steps += 1
         sums /= max(steps, 1)
         return dict(pg_loss=sums[0], v_loss=sums[1], entropy=sums[2], clip_frac=sums[3])
@@ -489,10 +584,14 @@ class MAPPOTrainer:
                       f"Rew: {rec['reward']:7.1f} | EpRet: {rec['ep_return']:6.1f} | Ent: {rec['entropy']:.3f} | "
                       f"Clip: {rec['clip_frac']:.3f} | LR: {rec['lr']:.2e} | SPS: {rec['sps']:.0f}", flush=True)
             if self.rank == 0 and self.cfg.checkpoint_every and update % self.cfg.checkpoint_every == 0:
-                torch.save(self.ema_agent.state_dict(), os.path.join(self.cfg.checkpoint_dir, f"mappo_resnet_{update}.pt"))
+                torch.save(self._ema_state(), os.path.join(self.cfg.checkpoint_dir, f"mappo_resnet_{update}.pt"))
         if self.rank == 0:
-            torch.save(self.ema_agent.state_dict(), os.path.join(self.cfg.checkpoint_dir, "mappo_resnet_final.pt"))
+            torch.save(self._ema_state(), os.path.join(self.cfg.checkpoint_dir, "mappo_resnet_final.pt"))
         return self.log
+
+    def _ema_state(self):
+        """EMA weights as independent tensors (with the fused pipeline the live ones are views of one flat buffer)."""
+        return {k: v.detach().clone() for k, v in self.ema_agent.state_dict().items()}
 
     @torch.no_grad()
     def evaluate_vs_bots(self, agent: Optional[MAPPOAgent] = None, num_envs: int = 256, team: str = "baselineTeam"):

@@ -72,6 +72,13 @@ class FlatGradBucket:
             self.flat.div_(world)
         return self.flat
 
+    def all_reduce_sum_(self, group=None):
+        """In-place SUM over the group (no-op for world size 1); the caller folds the 1/world into its next kernel."""
+        rank, world = world_info(group)
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return self.flat
+
     def clip_grad_norm_(self, max_norm: float) -> torch.Tensor:
         """nn.utils.clip_grad_norm_ (pacman_mappo_resnet.py:589) on the flat view: one norm, one scale."""
         total = torch.linalg.vector_norm(self.flat)

@@ -115,6 +115,9 @@ class EmuEnv:
     def set_range(self, begin=0, count=0):
         self.desc.env_begin, self.desc.env_count = int(begin), int(count)
 
+    def pool_seed(self):
+        return int(self.desc.random_seed)
+
     def set_draws(self, draws):
         """random.choice indices for the on-device bots of the next step (pm_env_desc.bot_draws)."""
         self.draws[:] = np.asarray(draws, np.uint32).reshape(self.N, 4)

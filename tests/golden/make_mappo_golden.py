@@ -69,6 +69,33 @@ def main():
         out[f"{name}_eval"] = np.stack([v2.numpy(), lp.numpy(), ent.numpy()])
         out[f"{name}_merged"] = merged.numpy()
         out[f"{name}_canon"] = ref.canonicalize_obs(obs, True).numpy()
+    # The minibatch loss of the reference's update loop (`pacman_mappo_resnet.py:563-600`).  It is inline code in
+    # train(), so the lines are executed here verbatim on seeded tensors (Categorical as in MAPPOAgent.evaluate,
+    # `:199-207`), with autograd giving d loss / d logits and d loss / d values.
+    from torch.distributions import Categorical
+    g = torch.Generator().manual_seed(7)
+    B = 512
+    logits = (torch.randn(B, 5, generator=g) * 1.5).requires_grad_(True)
+    vals = torch.randn(B, generator=g).requires_grad_(True)
+    acts = torch.randint(0, 5, (B,), generator=g)
+    b_logp = Categorical(logits=logits.detach() + 0.4 * torch.randn(B, 5, generator=g)).log_prob(acts)   # an older policy
+    b_adv = torch.randn(B, generator=g) * 2 + 0.3
+    b_ret = torch.randn(B, generator=g)
+    clip_eps, ent_coef = ref.CLIP_EPS, ref.ENT_COEF_START
+    dist = Categorical(logits=logits)
+    lps, ent = dist.log_prob(acts), dist.entropy()
+    norm_adv = (b_adv - b_adv.mean()) / (b_adv.std() + 1e-8)
+    ratio = (lps - b_logp).exp()
+    pg = -torch.min(norm_adv * ratio, norm_adv * torch.clamp(ratio, 1 - clip_eps, 1 + clip_eps)).mean()
+    vl = 0.5 * ((vals - b_ret) ** 2).mean()
+    loss = pg + ref.VF_COEF * vl - ent_coef * ent.mean()
+    loss.backward()
+    out["ppo_logits"], out["ppo_values"], out["ppo_actions"] = logits.detach().numpy(), vals.detach().numpy(), acts.numpy()
+    out["ppo_old_logp"], out["ppo_adv"], out["ppo_norm_adv"], out["ppo_ret"] = b_logp.numpy(), b_adv.numpy(), norm_adv.numpy(), b_ret.numpy()
+    out["ppo_scalars"] = np.array([loss.item(), pg.item(), vl.item(), ent.mean().item(),
+                                   ((ratio - 1).abs() > clip_eps).float().mean().item()], np.float32)
+    out["ppo_dlogits"], out["ppo_dvalues"] = logits.grad.numpy(), vals.grad.numpy()
+    out["ppo_coefs"] = np.array([clip_eps, ref.VF_COEF, ent_coef], np.float64)
     out["canon_action"] = np.array([ref.canonicalize_action(a, True) for a in range(5)])
     out["canon_action_t"] = ref.canonicalize_action(torch.arange(5), True).numpy()
     np.savez_compressed(os.path.join(HERE, "mappo_golden.npz"), **out)

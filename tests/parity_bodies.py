@@ -437,10 +437,13 @@ def body_layout_pool(make_env, N=24, T=140, L=7, seed=77, base=0):
     from pacman_marl_2025_b200 import mazeGenerator
     mazes = [mazeGenerator.generateMaze(7000 + s).split("\n") for s in range(L)]
     env = make_env(mazes, N, length=30, auto_reset=True, layout_pool=True, random_seed=seed, env_index_base=base)
+    obs, legal = env.reset()
+    # the seed the kernels hash: the caller's seed, advanced once per FULL reset by the host class (so that successive
+    # rollouts do not replay the same boards) - read it back from the descriptor
+    seed = env.pool_seed()
     ids = np.array([py_pool_layout(seed, base + n, 0, L) for n in range(N)])
     episode = np.zeros(N, np.int64)
     ref = oracle.OracleBatch([mazes[i] for i in ids], N, length=30)
-    obs, legal = env.reset()
     robs, rlegal = ref.reset()
     np.testing.assert_array_equal(env.get_state()["layout_id"], ids)
     np.testing.assert_array_equal(legal, rlegal)

@@ -44,6 +44,9 @@ class CudaEnv:
     def set_draws(self, draws):
         self.draws.copy_(torch.as_tensor(np.asarray(draws, np.int64).reshape(self.N, 4).astype(np.int32)))
 
+    def pool_seed(self):
+        return int(self.env._desc.random_seed)
+
     def set_bits(self, on=True):
         self.env.set_bits_output(on)
 

@@ -1,0 +1,161 @@
+"""SURVEY §8 row f3 as kernels - the PPO minibatch pipeline around the (PyTorch) networks,
+`pacman_mappo_resnet.py:555-600`: uint8 gather + widen, the fused loss + gradient, clip + Adam + EMA over flat
+buffers - against the reference's own formula (tests/golden/mappo_golden.npz, recorded by executing the reference's
+update lines on seeded tensors) and against the same steps written as eager PyTorch ops.  Tolerance 1e-5 relative
+(north_star's fp32 tolerance)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(helpers.GOLDEN, "mappo_golden.npz"))
+
+
+def torch_ppo(logits, vals, acts, old, adv, ret, clip_eps, vf, ec):
+    lg = torch.log_softmax(logits, -1)
+    lps = lg.gather(1, acts[:, None]).squeeze(1)
+    ent = -(lg.exp() * lg).sum(-1)
+    ratio = (lps - old).exp()
+    pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - clip_eps, 1 + clip_eps)).mean()
+    vl = 0.5 * ((vals - ret) ** 2).mean()
+    return pg + vf * vl - ec * ent.mean(), torch.stack([pg, vl, ent.mean(), ((ratio - 1).abs() > clip_eps).float().mean()])
+
+
+def test_fused_ppo_loss_matches_the_references_update_lines():
+    from pacman_marl_2025_b200.mappo_ops import ppo_loss
+    t = lambda k, dt=torch.float32: torch.as_tensor(G[k]).to(dt).cuda()
+    logits, vals = t("ppo_logits").requires_grad_(True), t("ppo_values").requires_grad_(True)
+    clip_eps, vf, ec = (float(x) for x in G["ppo_coefs"])
+    loss, st = ppo_loss(logits, vals, t("ppo_actions", torch.int64), t("ppo_old_logp"), t("ppo_norm_adv"), t("ppo_ret"),
+                        clip_eps, vf, ec)
+    loss.backward()
+    np.testing.assert_allclose(st[:5].cpu().numpy(), G["ppo_scalars"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), G["ppo_dlogits"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(vals.grad.cpu().numpy(), G["ppo_dvalues"], rtol=1e-5, atol=1e-9)
+    assert float(G["ppo_scalars"][4]) > 0.05                     # the fixture really has clipped samples
+
+
+@pytest.mark.parametrize("B,pair", [(8192, True), (8192, False), (1000, False), (66, True), (300000, False)])
+def test_fused_ppo_loss_vs_autograd(B, pair):
+    from pacman_marl_2025_b200.mappo_ops import ppo_loss
+    g = torch.Generator(device="cuda").manual_seed(B)
+    r = lambda *s: torch.randn(*s, generator=g, device="cuda")
+    logits, nv = (r(B, 5) * 2), (B // 2 if pair else B)
+    vals = r(nv)
+    acts = torch.randint(0, 5, (B,), generator=g, device="cuda")
+    old = torch.log_softmax(logits + 0.5 * r(B, 5), -1).gather(1, acts[:, None]).squeeze(1)
+    adv, ret = r(B), r(B)
+    adv[::17] = 0.0
+    la, va = logits.clone().requires_grad_(True), vals.clone().requires_grad_(True)
+    lb, vb = logits.clone().requires_grad_(True), vals.clone().requires_grad_(True)
+    loss, st = ppo_loss(la, va, acts, old, adv, ret, 0.15, 0.5, 0.02)
+    (loss * 3.0).backward()                                       # a non-unit upstream gradient
+    want, wst = torch_ppo(lb, torch.cat([vb, vb]) if pair else vb, acts, old, adv, ret, 0.15, 0.5, 0.02)
+    (want * 3.0).backward()
+    np.testing.assert_allclose(loss.item(), want.item(), rtol=2e-5)
+    np.testing.assert_allclose(st[1:5].cpu().numpy(), wst.detach().cpu().numpy(), rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(la.grad.cpu().numpy(), lb.grad.cpu().numpy(), rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(va.grad.cpu().numpy(), vb.grad.cpu().numpy(), rtol=1e-4, atol=1e-10)
+    # deterministic: the same launch twice gives bit-identical scalars
+    loss2, st2 = ppo_loss(la.detach(), va.detach(), acts, old, adv, ret, 0.15, 0.5, 0.02)
+    assert torch.equal(st2[:5], st[:5])
+
+
+@pytest.mark.parametrize("shape", [(8, 11, 14), (8, 7, 20), (8, 20, 20), (3, 5, 8)])
+def test_gather_rows_is_indexing_plus_float(shape):
+    from pacman_marl_2025_b200.mappo_ops import gather_rows
+    g = torch.Generator(device="cuda").manual_seed(1)
+    src = torch.randint(0, 256, (5000,) + shape, dtype=torch.uint8, device="cuda", generator=g)
+    for n in (1, 31, 4096, 20000):
+        idx = torch.randint(0, 5000, (n,), device="cuda", generator=g)
+        assert torch.equal(gather_rows(src, idx), src[idx].float())
+        assert torch.equal(gather_rows(src, idx, torch.bfloat16), src[idx].to(torch.bfloat16))
+    with pytest.raises(RuntimeError, match="PM_EINVAL"):
+        gather_rows(torch.zeros((10, 7), dtype=torch.uint8, device="cuda"), torch.zeros(3, dtype=torch.int64, device="cuda"))
+
+
+def test_flat_adam_ema_matches_torch_adam_clip_and_ema():
+    """pm_adam_ema == nn.utils.clip_grad_norm_ + torch.optim.Adam(eps=1e-5).step() + ema.mul_(d).add_(p, alpha=1-d)
+    (`pacman_mappo_resnet.py:588-595`), over 30 steps with gradients that do and do not get clipped."""
+    import copy
+    from pacman_marl_2025_b200 import sharding
+    from pacman_marl_2025_b200.mappo_ops import FlatAdamEMA
+    # the bucket holds the SUM over ranks in real use: double one rank's gradient and step with grad_scale = 1/2
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.GELU(), torch.nn.Linear(64, 5)).cuda()
+    ref_net, ref_ema, ema = copy.deepcopy(net), copy.deepcopy(net), copy.deepcopy(net)
+    bucket = sharding.FlatGradBucket(net.parameters())
+    opt = FlatAdamEMA(net, ema, bucket.flat, lr=2e-4, eps=1e-5, ema_decay=0.995, max_grad_norm=0.5)
+    ref_opt = torch.optim.Adam(ref_net.parameters(), lr=2e-4, eps=1e-5)
+    clipped = unclipped = 0
+    for step in range(30):
+        x = torch.randn(256, 37, device="cuda") * (0.05 if step % 3 == 0 else 3.0)
+        bucket.zero_()
+        net(x).square().mean().backward()
+        bucket.flat.mul_(2.0)                                             # "sum over 2 ranks"
+        norm = opt.step(grad_scale=0.5)
+        ref_opt.zero_grad()
+        ref_net(x).square().mean().backward()
+        want_norm = torch.nn.utils.clip_grad_norm_(ref_net.parameters(), 0.5)
+        ref_opt.step()
+        with torch.no_grad():
+            for e, p in zip(ref_ema.parameters(), ref_net.parameters()):
+                e.mul_(0.995).add_(p, alpha=0.005)
+        np.testing.assert_allclose(norm.item(), want_norm.item(), rtol=1e-5)
+        clipped += want_norm.item() > 0.5
+        unclipped += want_norm.item() <= 0.5
+        for a, b in zip(net.parameters(), ref_net.parameters()):
+            np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-5, atol=1e-7, err_msg=f"step {step}")
+    for a, b in zip(ema.parameters(), ref_ema.parameters()):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-5, atol=1e-7)
+    assert clipped > 3 and unclipped > 3
+
+
+def test_trainer_update_fused_pipeline_equals_eager_pipeline():
+    """One PPO update (3 epochs x 4 minibatches) from the same weights, rollout and shuffles: the kernels of row f3
+    (gather + widen, fused loss + gradient, clip + Adam + EMA) leave the same policy, EMA and logged losses as the
+    eager PyTorch formulation of `pacman_mappo_resnet.py:563-600`."""
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    res = []
+    for fused in (True, False):
+        cfg = M.TrainConfig(num_envs=64, num_steps=16, num_minibatches=4, update_epochs=3, total_updates=10, length=12,
+                            seed=21, checkpoint_every=0, fused_pipeline=fused, fast_math=False)
+        tr = M.MAPPOTrainer(cfg, device="cuda:0")
+        torch.manual_seed(77)
+        lv, _ = tr.collect("randomTeam", play_as_red=False)
+        torch.manual_seed(78)
+        losses = tr.update(lv, tr.schedule(0))
+        res.append((torch.cat([p.detach().reshape(-1) for p in tr.agent.parameters()]).cpu(),
+                    torch.cat([p.detach().reshape(-1) for p in tr.ema_agent.parameters()]).cpu(),
+                    {k: float(v) for k, v in losses.items()}))
+    (pa, ea, la), (pb, eb, lb) = res
+    for k in la:
+        np.testing.assert_allclose(la[k], lb[k], rtol=2e-4, atol=1e-6, err_msg=k)
+    # 12 Adam steps of size 2e-4: identical up to fp32 summation order in the losses' gradients
+    assert float((pa - pb).abs().max()) < 2e-5, float((pa - pb).abs().max())
+    assert float((ea - eb).abs().max()) < 2e-6
+
+
+def test_trainer_rollout_against_the_references_cpu_bots():
+    """Curriculum wiring of the host-bot hook: with TrainConfig.reference_root the reference's CPU teams
+    (`pacman_mappo_resnet.py:40-42`) play red through gymPacMan_parallel_env(bot_team=...), each bot asked at its own
+    sub-move on the reference's own GameState.  Needs the reference copy that build() puts in baseline/_ref."""
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.exists(os.path.join(root, "capture.py")):
+        pytest.skip("no copy of the reference in baseline/_ref")
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    cfg = M.TrainConfig(num_envs=3, num_steps=8, num_minibatches=2, update_epochs=1, total_updates=4, length=20, seed=2,
+                        checkpoint_every=0, reference_root=root, easy_until=0, selfplay_after=100)
+    tr = M.MAPPOTrainer(cfg, device="cuda:0")
+    assert M.curriculum_pools(root)[1] == ["MCTSTeam", "heuristicTeam"]
+    lv, stats = tr.collect("heuristicTeam", play_as_red=False)
+    env = tr._host_envs["heuristicTeam"]
+    assert env._bot_team is not None and not isinstance(env.agents[0], int)
+    ro = tr.rollout
+    assert bool(torch.isfinite(ro.reward).all()) and bool(((ro.obs[:, :, :, 1] > 0).sum((-1, -2)) == 1).all())
+    losses = tr.update(lv, tr.schedule(1))
+    assert all(np.isfinite(float(v)) for v in losses.values())

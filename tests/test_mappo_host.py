@@ -80,3 +80,35 @@ def test_action_canonicalisation_and_schedule():
             M.TOTAL_UPDATES, M.LR_START, M.LR_END, M.ENT_COEF_START, M.ENT_COEF_END, M.OPPONENT_POOL_SIZE,
             M.OPPONENT_UPDATE_FREQ, M.SHAPING_SCALE, M.EMA_DECAY) == (
         2048, 512, 0.99, 0.95, 0.15, 0.5, 0.5, 3, 2000, 2e-4, 4e-5, 0.02, 0.004, 80, 15, 0.1, 0.995)
+
+
+def test_critic_written_out_with_bmm_equals_the_module():
+    """MAPPOAgent.attn_impl = "bmm" evaluates the critic's nn.TransformerEncoder layers with explicit ops (same
+    parameters): values and gradients equal nn.TransformerEncoder.forward's."""
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    torch.manual_seed(0)
+    agent = M.MAPPOAgent((8, 11, 14), 5, 2)
+    merged = det_obs(6, 11, 14, 5)
+    outs, grads = {}, {}
+    for impl in ("module", "bmm"):
+        agent.attn_impl = impl
+        agent.zero_grad()
+        v = agent.get_value(merged)
+        v.square().sum().backward()
+        outs[impl] = v.detach().clone()
+        grads[impl] = torch.cat([p.grad.reshape(-1) for n, p in agent.named_parameters() if n.startswith("critic")]).clone()
+    np.testing.assert_allclose(outs["bmm"].numpy(), outs["module"].numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(grads["bmm"].numpy(), grads["module"].numpy(), rtol=1e-4, atol=1e-6)
+    agent.eval()
+    with torch.no_grad():
+        agent.attn_impl = "module"; a = agent.get_value(merged)
+        agent.attn_impl = "bmm"; b = agent.get_value(merged)
+    np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_curriculum_pools_are_the_references_when_its_bots_are_available():
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    assert (M.EASY_TEAMS, M.MEDIUM_TEAMS, M.HARD_TEAMS) == (
+        ["randomTeam"], ["MCTSTeam", "heuristicTeam"], ["baselineTeam", "AstarTeam", "approxQTeam"])   # `:40-42`
+    assert M.curriculum_pools("/some/checkout") == (M.EASY_TEAMS, M.MEDIUM_TEAMS, M.HARD_TEAMS)
+    assert M.curriculum_pools("") == (["randomTeam"], [], ["baselineTeam"])        # what runs inside the step kernel

@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--layout", default="smallCapture")
     ap.add_argument("--pair", type=int, default=1)
     ap.add_argument("--views", type=int, default=1)
+    ap.add_argument("--fused", type=int, default=1, help="row-f3 kernels (gather, fused loss, Adam+EMA) vs eager ops")
+    ap.add_argument("--attn", default="bmm", help="critic attention: bmm (written out) or module (nn.TransformerEncoder)")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -31,7 +33,8 @@ def main():
     from pacman_marl_2025_b200 import pacman_mappo_resnet as M
     lay = os.path.join(os.path.dirname(M.__file__), "layouts", a.layout + ".lay")
     cfg = M.TrainConfig(layout_file=lay, num_envs=a.envs, num_steps=a.steps, amp_bf16=bool(a.amp), checkpoint_every=0,
-                        pair_agents=bool(a.pair), use_views=bool(a.views))
+                        pair_agents=bool(a.pair), use_views=bool(a.views), fused_pipeline=bool(a.fused))
+    M.MAPPOAgent.attn_impl = a.attn
     tr = M.MAPPOTrainer(cfg, device=f"cuda:{local}")
     tr.train_one(0)                                        # warm-up (cuDNN autotune, allocator)
     torch.cuda.synchronize()
@@ -55,7 +58,8 @@ def main():
         print(json.dumps({"metric": "MAPPO SPS (learner-agent samples/s, rollout + GAE + PPO update)", "value": samples / dt,
                           "unit": "samples/s", "n_gpus": world, "config": {"workload": f"{a.layout}, {a.envs} envs/GPU x {a.steps} steps, "
                           f"{cfg.update_epochs} epochs x {cfg.num_minibatches} minibatches, randomTeam opponent", "amp_bf16": bool(a.amp),
-                          "pair_agents": bool(a.pair), "kernel_views": bool(a.views)},
+                          "pair_agents": bool(a.pair), "kernel_views": bool(a.views), "fused_pipeline": bool(a.fused),
+                          "critic_attention": a.attn},
                           "rollout_s": parts["rollout"], "update_s": parts["update"],
                           "env_agent_steps_per_s_in_rollout": 4 * a.envs * a.steps * a.updates * world / parts["rollout"]}), flush=True)
     if world > 1:
