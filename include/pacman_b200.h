@@ -165,7 +165,14 @@ typedef struct pm_step_out {
     uint8_t *view_actor;
     int64_t view_actor_stride;
     uint8_t *view_critic;
-    int32_t view_red, reserved2;
+    int32_t view_red;
+    /* ---- ABI 7: leave what cannot have changed untouched ----
+     * non-zero: the caller guarantees that `obs` is the SAME buffer the previous pm_step / pm_reset / pm_observe of this
+     * batch wrote in full (the host class's persistent observation tensor).  The step then skips the elements of
+     * every observation that cannot differ from what is already there: plane 0 (walls, fixed per board) and, when no
+     * board of the batch has a capsule, planes 2-3 (all zero) - 12.5 % / 37.5 % of the bytes.  An env that moved to
+     * another board inside the launch (layout_pool) is written in full.  The tensors read back are identical.   */
+    int32_t obs_static_valid;
     /* ---- ABI 7: packed observations for a HOST-side consumer ----
      * The eight planes of an observation hold 0/1 except the own cell (1 + numCarrying), so an observation is an
      * 8*H*W-bit string plus one patch.  obs_bits: [dev or mapped pinned host] agent a, env n at

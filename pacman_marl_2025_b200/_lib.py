@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpacman_b200.so")
+# (PM_LIB_PATH: development builds of the same library with other launch-geometry macros, for B200 sweeps)
+LIB_PATH = os.environ.get("PM_LIB_PATH") or os.path.join(_HERE, "libpacman_b200.so")
 
 PM_ERRORS = {-1: "PM_EINVAL (bad argument)", -2: "PM_ELAYOUT (malformed layout text)",
              -3: "PM_ETOOBIG (board larger than 1024 cells or a side > 255)", -4: "PM_ENOGPU"}
@@ -59,7 +60,7 @@ class PmStepOut(C.Structure):
         ("actions_used", C.c_void_p),   # ABI 4
         # ABI 5: learner views
         ("view_actor", C.c_void_p), ("view_actor_stride", C.c_int64), ("view_critic", C.c_void_p),
-        ("view_red", C.c_int32), ("reserved2", C.c_int32),
+        ("view_red", C.c_int32), ("obs_static_valid", C.c_int32),
         # ABI 7: packed observations
         ("obs_bits", C.c_void_p), ("obs_bits_agent_stride", C.c_int64),
     ]

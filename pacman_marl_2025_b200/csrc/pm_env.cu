@@ -39,6 +39,9 @@
 #ifndef PM_E
 #define PM_E 32                                   // envs per CTA (power of two <= PM_THREADS)
 #endif
+#ifndef PM_E_BOTS
+#define PM_E_BOTS PM_E                            // envs per CTA of the variant with the baselineTeam look-ahead (large batches)
+#endif
 #ifndef PM_E_SMALL
 #define PM_E_SMALL 8                              // envs per CTA for batches too small to give every SM work at PM_E
 #endif
@@ -59,7 +62,7 @@ extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToS
 template <int MODE, int BOTS, int VIEWS, int E>
 __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
-    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0);
     const int tid = threadIdx.x;
     const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * E;
 #ifdef PM_TRACE
@@ -77,6 +80,14 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
     for (int i = tid; i < PM_G_NMASKS * P.NCAT; i += PM_THREADS) sm[M.masks + i] = __ldg(P.geom + PM_G_HDR + i);
     if (P.L == 1)
         for (int i = tid; i < P.LS; i += PM_THREADS) sm[M.lay + i] = __ldg(P.layouts + i);
+    if (BOTS && M.dist) {
+        // one board for the whole batch and a table that fits: the baselineTeam look-ahead reads its maze distances
+        // (Distancer.getDistance, distanceCalculator.py:38-62) from shared memory instead of L2
+        const int dw = (P.dist_nmax * P.dist_nmax * 2 + 3) >> 2, nw = (P.HW * 2 + 3) >> 2;
+        const uint32_t *gd = reinterpret_cast<const uint32_t *>(P.dist), *gn = reinterpret_cast<const uint32_t *>(P.node_of_cell);
+        for (int i = tid; i < dw; i += PM_THREADS) sm[M.dist + i] = __ldg(gd + i);
+        for (int i = tid; i < nw; i += PM_THREADS) sm[M.dist + dw + i] = __ldg(gn + i);
+    }
     __syncthreads();
 
     // ---- phase A: rules, one thread per env ----
@@ -196,7 +207,11 @@ template <int MODE, int BOTS, int VIEWS, int E>
 static int launch_env_e(const PmParams &P0, cudaStream_t st) {
     PmParams P = P0;
     set_envs_per_cta(P, E);
-    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS);
+    P.dist_stage_words = 0;
+    if (BOTS && P.L == 1 && P.dist && (((size_t)P.dist | (size_t)P.node_of_cell) & 3) == 0 && ((P.dist_nmax * P.dist_nmax) & 1) == 0 &&
+        pm_dist_stage_words(P.HW, P.dist_nmax) <= PM_DIST_STAGE_MAX_WORDS)
+        P.dist_stage_words = pm_dist_stage_words(P.HW, P.dist_nmax);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0);
     const size_t smem = (size_t)M.total * 4;
     // Per-device cache of the dynamic shared-memory size this kernel instance is configured for.  The launch stays
     // under the lock whenever the attribute may still change, so another host thread can neither launch with a size
@@ -232,7 +247,7 @@ static int launch_env(const PmParams &P, cudaStream_t st) {
         if (sms < 0) return sms;
         small = (P.n_end - P.n_begin) < (int64_t)2 * PM_E * sms;
     }
-    return small ? launch_env_e<MODE, BOTS, VIEWS, PM_E_SMALL>(P, st) : launch_env_e<MODE, BOTS, VIEWS, PM_E>(P, st);
+    return small ? launch_env_e<MODE, BOTS, VIEWS, PM_E_SMALL>(P, st) : launch_env_e<MODE, BOTS, VIEWS, BOTS ? PM_E_BOTS : PM_E>(P, st);
 }
 
 static int set_views(PmParams &P, uint8_t *actor, int64_t stride, uint8_t *critic, int red) {
@@ -296,6 +311,7 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     if (out->obs && ((out->obs_agent_stride & 3) || ((size_t)out->obs & 15))) return PM_EINVAL;
     P.actions = actions; P.act_size = action_itemsize;
     P.obs = out->obs; P.obs_agent_stride = out->obs_agent_stride;
+    P.obs_elide = out->obs_static_valid != 0;
     P.reward = out->reward; P.done = out->done; P.legal = out->legal; P.score_change = out->score_change;
     P.shaping = out->shaping; P.shaped = out->shaped_reward; P.packed = out->packed; P.act_used = out->actions_used;
     if (int rc = set_views(P, out->view_actor, out->view_actor_stride, out->view_critic, out->view_red)) return rc;

@@ -115,6 +115,8 @@ struct PmParams {
     const uint32_t *bot_draws;          // [N][4] externally supplied random.choice indices for the on-device bots
     uint32_t *obs_bits; int64_t obs_bits_stride; int NB;   // packed observations: NB words per observation
     int epc;                            // pm_env_desc.envs_per_cta (0 = auto)
+    int obs_elide;                      // pm_step_out.obs_static_valid: skip the observation elements that cannot have changed
+    int dist_stage_words;               // > 0: the (single) board's distance table + node map are staged in shared memory
 };
 
 #ifndef PM_TMA_STORE
@@ -136,8 +138,13 @@ struct PmParams {
 struct PmSmem {
     int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, stage, total;
     int E1;                             // padded env stride
+    int dist;                           // bots, one board: dist[nmax][nmax] u16 then node_of[HW] i16 (0 = not staged)
 };
-PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots = 4) {
+// words needed to stage one board's maze-distance table + cell->node map (baselineTeam look-ahead)
+PM_HD int pm_dist_stage_words(int HW, int nmax) { return ((nmax * nmax * 2 + 3) >> 2) + ((HW * 2 + 3) >> 2); }
+#define PM_DIST_STAGE_MAX_WORDS 3072    // 12 KB: tinyCapture 7.3 KB, smallCapture 9.6 KB; bloxCapture (72 KB) stays in L2
+
+PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots = 4, int dist_words = 0) {
     const int NW = pm_nw(HW), NCAT = pm_ncat(HW);
     PmSmem m;
     m.E1 = E | 1;
@@ -147,6 +154,8 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     m.masks = o; o += PM_G_NMASKS * NCAT;
     m.lay = o; o += (L == 1) ? LS : 0;
     o = (o + 3) & ~3;
+    m.dist = 0;
+    if (dist_words > 0) { m.dist = o; o += dist_words; o = (o + 3) & ~3; }
     m.blk0 = o;
     // per-block buffer
     m.lid = o; o += E;
@@ -345,8 +354,9 @@ PM_HD void pm_pack_agents(const PmAgents &g, pm_u4 &A, pm_u4 &B) {
 // ============================================================================
 // Per-env constants of a step, and the mutable board counters a sub-move touches.
 struct PmCtx {
-    int W, H, NW, E1, ND, HW;
+    int W, H, NW, E1, ND, HW, NCAT;
     const uint32_t *walls, *dumptab;
+    const uint32_t *halfmask;          // the staged plane masks M6 (blue food half) | M7 (red food half), NCAT words each
     uint32_t teams;
 };
 struct PmBoard {
@@ -435,21 +445,32 @@ PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2,
         int v = -100 * n;
         if (n > 0) {
             int best = 0x7fffffff;
-            const int half = W >> 1;
             const uint16_t *row = D.dist + (size_t)D.node_of[me] * D.nmax;     // distances from my cell
+            // the pellets this team eats: red eats x >= W//2, blue eats x < W//2 - the half-board mask of plane 6 / 7
+            // (bits of the observation string, i.e. shifted by 6*HW / 7*HW) says which cells those are
+            const uint32_t *hm = X.halfmask + (is_red ? 0 : X.NCAT);
+            const int hshift = (is_red ? 6 : 7) * X.HW;
             for (int w = 0; w < X.NW; ++w) {
-                uint32_t bits = fs[w * X.E1];
+                uint32_t bits = fs[w * X.E1] & pm_extract32(hm, 1, X.NCAT, 32 * w + hshift);
+                // four independent (node, distance) look-ups in flight per round instead of one dependent pair
                 while (bits) {
+                    int c[4], d[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
 #if defined(__CUDA_ARCH__)
-                    const int bpos = __ffs((int)bits) - 1;
+                        const int bpos = bits ? __ffs((int)bits) - 1 : -1;
 #else
-                    const int bpos = __builtin_ctz(bits);
+                        const int bpos = bits ? __builtin_ctz(bits) : -1;
 #endif
-                    bits &= bits - 1;
-                    const int c = 32 * w + bpos, x = c % W;
-                    if ((x >= half) != (is_red != 0)) continue;            // red eats x >= W//2, blue eats x < W//2
-                    const int d = (int)row[D.node_of[c]];
-                    best = d < best ? d : best;
+                        bits &= bits - 1;
+                        c[q] = bpos < 0 ? -1 : 32 * w + bpos;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) c[q] = c[q] < 0 ? -1 : (int)D.node_of[c[q]];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) d[q] = c[q] < 0 ? 0x7fffffff : (int)row[c[q]];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) best = d[q] < best ? d[q] : best;
                 }
             }
             v -= best;
@@ -554,8 +575,13 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
     } else if (BOTS && kind >= 2) {
         PmDist D;
         D.nmax = P.dist_nmax;
-        D.dist = P.dist + (size_t)lid * P.dist_nmax * P.dist_nmax;
-        D.node_of = P.node_of_cell + (size_t)lid * X.HW;
+        if (M.dist) {                                  // one board: table + node map staged in shared memory
+            D.dist = reinterpret_cast<const uint16_t *>(sm + M.dist);
+            D.node_of = reinterpret_cast<const int16_t *>(sm + M.dist + ((P.dist_nmax * P.dist_nmax * 2 + 3) >> 2));
+        } else {
+            D.dist = P.dist + (size_t)lid * P.dist_nmax * P.dist_nmax;
+            D.node_of = P.node_of_cell + (size_t)lid * X.HW;
+        }
         const uint32_t rnd = ext_draw ? P.bot_draws[4 * n + A]
                                       : pm_random_u32(P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
         u = pm_baseline_choose<A>(X, D, g, fk, ck, food + (size_t)4 * NW * E1, caps ? caps + (size_t)4 * NW * E1 : nullptr,
@@ -605,8 +631,9 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     const int W = P.W, NW = P.NW, E1 = M.E1;
     const int64_t NP = pm_np(P.N);
     PmCtx X;
-    X.W = W; X.H = P.H; X.NW = NW; X.E1 = E1; X.ND = P.ND; X.HW = P.HW;
+    X.W = W; X.H = P.H; X.NW = NW; X.E1 = E1; X.ND = P.ND; X.HW = P.HW; X.NCAT = P.NCAT;
     X.walls = walls; X.dumptab = P.geom + pm_g_dump_off(P.HW); X.teams = tail[PM_L_TEAMS];
+    X.halfmask = st + M.masks + 2 * P.NCAT;
 
     // ---- load state (128-bit loads, coalesced across the env dimension) ----
     pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
@@ -714,7 +741,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         if (P.layout_pool) {                            // a new maze per episode (gymPacMan.py:98-100)
             lid = pm_pool_layout(P.bot_seed, (unsigned long long)(P.n_base + n), episode, P.L);
             P.layout_id_rw[n] = lid;
-            sm[M.lid + el] = lid;
+            sm[M.lid + el] = lid | 0x80000000u;         // new board: its observations are written in full (obs_static_valid)
             lay = P.layouts + (size_t)lid * P.LS;
             walls = lay + pm_l_walls(P.HW);
             tail = lay + pm_l_tail(P.HW);
@@ -889,12 +916,15 @@ struct PmUnit {
     uint32_t patch;                             // own-cell element | (1+carrying) << 16, or 0xffffffff
     uint32_t p_own2, patch2;                    // critic view: the second learner's own cell (plane 1) and its patch
     int mirror;                                 // canonical red-learner view: mirrored tables and bitsets
+    int fresh;                                  // this env moved to another board inside the launch
 };
 
 template <int MODE>
 PM_HD bool pm_unit_load(const PmParams &P, const uint32_t *sm, const PmSmem &M, int k, int el, PmUnit &U) {
     U.lid = sm[M.lid + el];
     if (U.lid == 0xffffffffu) return false;
+    U.fresh = (int)(U.lid >> 31);
+    U.lid &= 0x7fffffffu;
     if (MODE == PM_MODE_STEP && (k < P.a0 || k >= P.a1)) return false;     // only the agents that moved in this launch
     const int slot = (MODE == PM_MODE_STEP) ? k : 0;
     U.food = sm + M.food + (size_t)slot * P.NW * M.E1 + el;
@@ -924,6 +954,8 @@ template <int MODE>
 PM_HD bool pm_view_unit_load(const PmParams &P, const uint32_t *sm, const PmSmem &M, int v, int el, int mslot0, PmUnit &U) {
     U.lid = sm[M.lid + el];
     if (U.lid == 0xffffffffu) return false;
+    U.fresh = (int)(U.lid >> 31);
+    U.lid &= 0x7fffffffu;
     const int red = P.view_red != 0;
     const int l = v == 2 ? 0 : v;                                // whose snapshot the board comes from
     const int k = red ? 2 * l : 2 * l + 1;                       // agent index of that learner
@@ -1081,15 +1113,22 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
             }
         }
 #else
+        // obs_static_valid: float4s that lie entirely inside plane 0 (walls) or, on capsule-free batches, planes 2-3
+        // already hold their value from the previous full write of this buffer - leave them alone
+        const bool elide = MODE == PM_MODE_STEP && P.obs_elide && !U.fresh;
+        const int s0 = P.HW >> 2;                       // float4 f is static if 4f+3 < HW ...
+        const int s1 = (2 * P.HW + 3) >> 2, s2 = P.has_caps ? 0 : (4 * P.HW) >> 2;       // ... or 2HW <= 4f and 4f+3 < 4HW
         for (int g = 0; g < ngroups; ++g) {
             const int j = 32 * g + lane;
             const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
             const int fbase = 256 * g + lane;
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
+                const int f0 = 256 * g + 32 * r;        // warp-uniform: the whole round may be static
+                if (elide && (f0 + 32 <= s0 || (f0 >= s1 && f0 + 32 <= s2))) continue;
                 const uint32_t w = __shfl_sync(0xffffffffu, word, 4 * r + src);
                 const int f = fbase + 32 * r;
-                if (f < nf4) dst[f] = pm_expand4(lut, (w >> sh) & 15u);
+                if (f < nf4 && !(elide && (f < s0 || (f >= s1 && f < s2)))) dst[f] = pm_expand4(lut, (w >> sh) & 15u);
             }
         }
         if (U.patch != 0xffffffffu) {
@@ -1103,10 +1142,13 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
         for (int g = 0; g < ngroups; ++g) {
             uint32_t words[32];
             for (int L = 0; L < 32; ++L) { const int j = 32 * g + L; words[L] = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u; }
+            const bool elide = MODE == PM_MODE_STEP && P.obs_elide && !U.fresh;
+            const int s0 = P.HW >> 2, s1 = (2 * P.HW + 3) >> 2, s2 = P.has_caps ? 0 : (4 * P.HW) >> 2;
             for (int r = 0; r < 8; ++r)
                 for (int L = 0; L < 32; ++L) {
                     const int f = 256 * g + 32 * r + L;
-                    if (f < nf4) dst[f] = lut[(words[4 * r + (L >> 3)] >> ((L & 7) * 4)) & 15u];
+                    if (f < nf4 && !(elide && (f < s0 || (f >= s1 && f < s2))))
+                        dst[f] = lut[(words[4 * r + (L >> 3)] >> ((L & 7) * 4)) & 15u];
                 }
         }
         if (U.patch != 0xffffffffu) dstf[U.patch & 0xffff] = (float)(U.patch >> 16);

@@ -285,7 +285,8 @@ class gymPacMan_parallel_env:
                  self_play=False, *, num_envs: int = 1, device=None, layouts: Optional[Sequence] = None,
                  shaping_scale: float = 0.1, opponent_seed: int = 0, auto_reset: bool = False,
                  env_index_base: int = 0, opponent_tiebreak: str = "random", layout_ids=None,
-                 bot_team=None, state_factory=None, layout_pool: int = 0, envs_per_cta: int = 0):
+                 bot_team=None, state_factory=None, layout_pool: int = 0, envs_per_cta: int = 0,
+                 elide_static_planes: bool = False):
         if display:
             raise NotImplementedError("display=True (tkinter viewer) is outside the batched GPU path")
         if not torch.cuda.is_available():
@@ -332,6 +333,10 @@ class gymPacMan_parallel_env:
         self._opponent_tiebreak = opponent_tiebreak
         self._opponent_seed = int(opponent_seed)
         self._envs_per_cta = int(envs_per_cta)
+        # the step may leave the observation elements that cannot have changed (walls; capsule planes of capsule-free
+        # batches) as the previous write of the env's own observation tensor left them (pm_step_out.obs_static_valid)
+        self.elide_static_planes = bool(elide_static_planes)
+        self._obs_static_ok = False
         self._submoves_in_step = 0
         # batched extensions: restart finished envs inside the step launch; global index of env 0 when
         # this batch is one shard of a larger one (keys the on-device opponent's random draws)
@@ -488,6 +493,8 @@ class gymPacMan_parallel_env:
             _lib.check(self._L.pm_reset(C.byref(self._desc), mptr, self._obs.data_ptr(), self._obs[0].numel(),
                                         self._legal.data_ptr(), self._stream()), "pm_reset")
         self._version += 1
+        if mask is None:
+            self._obs_static_ok = True                  # every observation of the batch has just been written in full
         return self._obs, self._legal
 
     def step_batched(self, actions: torch.Tensor):
@@ -643,6 +650,7 @@ class gymPacMan_parallel_env:
             if "obs_bits" not in self._host:
                 self._host["obs_bits"] = torch.empty(self._bits.shape, dtype=torch.int32).pin_memory()
             ho.obs_bits, ho.obs_bits_agent_stride = self._host["obs_bits"].data_ptr(), self._host["obs_bits"].stride(0)
+        self._mark_static()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host(C.byref(self._desc), actions_host.data_ptr(), self._act_dev.data_ptr(),
                                             C.byref(self._step_out), C.byref(ho), self._stream()), "pm_step_host")
@@ -679,6 +687,7 @@ class gymPacMan_parallel_env:
             so = self._step_out
             self._pipe_out = _lib.PmStepOut(so.obs, so.obs_agent_stride, None, None, None, None, None, None,
                                             self._rec_dev.data_ptr())
+        self._mark_static()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host_pipelined(C.byref(self._desc), self._pipe, actions_host.data_ptr(),
                                                       self._act_dev.data_ptr(), C.byref(self._pipe_out),
@@ -703,6 +712,7 @@ class gymPacMan_parallel_env:
         if actions_host.numel() != 4 * self.num_envs:
             raise ValueError(f"expected {self.num_envs}x4 actions")
         self._ensure_mapped()
+        self._mark_static()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host_mapped(C.byref(self._desc), actions_host.data_ptr(),
                                                    C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
@@ -862,6 +872,7 @@ class gymPacMan_parallel_env:
         # launch (the kernel reads the pinned action word and writes the pinned record), clone the observation block
         # on the same stream, and only then synchronise: one wait covers both
         self._ensure_mapped()
+        self._mark_static()
         with torch.cuda.device(self.device):
             _lib.check(self._L.pm_step_host_mapped_async(C.byref(self._desc), self._single_act.data_ptr(),
                                                          C.byref(self._mapped_out), self._rec_mapped.data_ptr(),
@@ -913,6 +924,7 @@ class gymPacMan_parallel_env:
         if sub_moves is not None:
             d.agent_begin, d.agent_end = sub_moves
         end = d.agent_end
+        self._mark_static()
         try:
             with torch.cuda.device(self.device):
                 _lib.check(self._L.pm_step(C.byref(d), actions.data_ptr(), actions.element_size(),
@@ -923,6 +935,20 @@ class gymPacMan_parallel_env:
         if end in (0, 4):
             self.steps += 1
         return self._out_dict()
+
+    def _mark_static(self):
+        """Set pm_step_out.obs_static_valid for the coming launch.  Valid while self._obs holds a full write for every
+        env's CURRENT board: a step that skips the fp32 observations while boards may change (layout pool) ends it
+        until the next full reset."""
+        so = self._step_out
+        if so.obs is None and self._pool_mode:
+            self._obs_static_ok = False
+        flag = int(self.elide_static_planes and self._obs_static_ok and so.obs is not None)
+        so.obs_static_valid = flag
+        for name in ("_mapped_out", "_pipe_out"):
+            o = self.__dict__.get(name)
+            if o is not None:
+                o.obs_static_valid = flag
 
     def _out_dict(self):
         out = dict(obs=self._obs, reward=self._reward, done=self._done, legal=self._legal,

@@ -161,11 +161,13 @@ class FlatAdamEMA:
 
     @staticmethod
     def _flatten(params):
-        flat = torch.cat([p.data.reshape(-1) for p in params]).contiguous()
-        o = 0
-        for p in params:
+        """Re-point every parameter at a view of one flat buffer, same aligned layout as sharding.FlatGradBucket."""
+        from .sharding import flat_offsets
+        offs, n = flat_offsets(params)
+        flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+        for p, o in zip(params, offs):
+            flat[o:o + p.numel()].copy_(p.data.reshape(-1))
             p.data = flat[o:o + p.numel()].view_as(p)
-            o += p.numel()
         return flat
 
     def step(self, grad_scale: float = 1.0):

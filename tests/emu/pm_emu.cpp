@@ -22,7 +22,11 @@ static void run(const PmParams &P) {
     bool bots = false;
     for (int i = 0; i < 4; ++i) bots |= MODE == PM_MODE_STEP && ((P.bot_kind >> (4 * i)) & 15) >= 2;   // like the C ABI glue
     const bool views = P.view_actor != nullptr;
-    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L, 4 + (bots ? 1 : 0) + (views ? 2 : 0));
+    // like launch_env_e: one board + a small table -> the bots' distance table is staged in (emulated) shared memory
+    int dsw = 0;
+    if (bots && P.L == 1 && P.dist && ((P.dist_nmax * P.dist_nmax) & 1) == 0 && pm_dist_stage_words(P.HW, P.dist_nmax) <= PM_DIST_STAGE_MAX_WORDS)
+        dsw = pm_dist_stage_words(P.HW, P.dist_nmax);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L, 4 + (bots ? 1 : 0) + (views ? 2 : 0), dsw);
     std::vector<uint32_t> smv((size_t)M.total + 4);
     uint32_t *sm = smv.data();
     const int64_t nblk = (P.n_end - P.n_begin + P.E - 1) / P.E;
@@ -35,6 +39,11 @@ static void run(const PmParams &P) {
         }
         for (int i = 0; i < PM_G_NMASKS * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
         if (P.L == 1) for (int i = 0; i < P.LS; ++i) sm[M.lay + i] = P.layouts[i];
+        if (M.dist) {
+            const int dw = (P.dist_nmax * P.dist_nmax * 2 + 3) >> 2;
+            memcpy(sm + M.dist, P.dist, (size_t)P.dist_nmax * P.dist_nmax * 2);
+            memcpy(sm + M.dist + dw, P.node_of_cell, (size_t)P.HW * 2);
+        }
         for (int el = 0; el < P.E; ++el) {
             if (MODE == PM_MODE_STEP) {
                 if (bots && views) pm_phaseA_step<1, 1>(P, sm, sm, M, el, n0);
@@ -86,6 +95,7 @@ extern "C" int emu_step(const pm_env_desc *d, const void *actions, int itemsize,
     P.view_actor = out->view_actor; P.view_actor_stride = out->view_actor_stride; P.view_critic = out->view_critic;
     P.view_red = out->view_red;
     P.obs_bits = out->obs_bits; P.obs_bits_stride = out->obs_bits_agent_stride;
+    P.obs_elide = out->obs_static_valid != 0;
     run<PM_MODE_STEP>(P);
     return 0;
 }

@@ -85,7 +85,20 @@ class EmuEnv:
             self.desc.bot_first_best = int(bot_first_best)
         self.obs_shape = (8, self.H, self.W)
 
+    def set_elide(self, on=True):
+        """pm_step_out.obs_static_valid: steps write into ONE persistent observation buffer (first filled by reset) and
+        may leave the static planes untouched."""
+        self.elide = bool(on)
+
     def reset(self, mask=None):
+        if getattr(self, "elide", False):
+            if getattr(self, "_obs_persist", None) is None:
+                self._obs_persist = np.full((4, self.N) + self.obs_shape, np.nan, np.float32)
+            obs = self._obs_persist
+            legal = np.zeros((self.N, 4), np.uint8)
+            m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
+            lib().emu_reset(C.byref(self.desc), _p(m), _p(obs), C.c_int64(obs[0].size), _p(legal), self.E, self.KB)
+            return obs.copy(), legal
         obs = np.full((4, self.N) + self.obs_shape, np.nan, np.float32)
         legal = np.zeros((self.N, 4), np.uint8)
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
@@ -134,7 +147,8 @@ class EmuEnv:
 
     def step(self, actions, dtype=np.uint8):
         a = np.ascontiguousarray(np.asarray(actions).reshape(self.N, 4), dtype)
-        o = dict(obs=np.full((4, self.N) + self.obs_shape, np.nan, np.float32), reward=np.zeros((2, self.N)),
+        elide = getattr(self, "elide", False)
+        o = dict(obs=self._obs_persist if elide else np.full((4, self.N) + self.obs_shape, np.nan, np.float32), reward=np.zeros((2, self.N)),
                  done=np.zeros(self.N, np.uint8), legal=np.zeros((self.N, 4), np.uint8),
                  score_change=np.zeros(self.N, np.int32), shaping=np.zeros((4, self.N)),
                  shaped=np.zeros((4, self.N), np.float32))
@@ -152,8 +166,11 @@ class EmuEnv:
             NB = lib().pm_obs_bits_words(self.W, self.H)
             o["obs_bits"] = np.full((4, self.N, NB), 0xEEEEEEEE, np.uint32)
             so.obs_bits, so.obs_bits_agent_stride = o["obs_bits"].ctypes.data, o["obs_bits"][0].size
+        so.obs_static_valid = int(elide)
         rc = lib().emu_step(C.byref(self.desc), _p(a), a.dtype.itemsize, C.byref(so), self.E, self.KB)
         assert rc == 0, rc
+        if elide:
+            o["obs"] = o["obs"].copy()
         return o
 
     def get_state(self):

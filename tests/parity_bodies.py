@@ -478,3 +478,20 @@ def body_layout_pool(make_env, N=24, T=140, L=7, seed=77, base=0):
         np.testing.assert_array_equal(s["layout_id"], ids, err_msg=f"t={t} layout ids")
         np.testing.assert_array_equal(s["episode"], episode)
     assert moved > N                  # envs really changed boards
+
+
+def body_elide_static_planes(make_env, layouts, N=40, T=120, **kw):
+    """pm_step_out.obs_static_valid: with the env's persistent observation buffer the step may skip the elements that
+    cannot have changed (walls; the capsule planes of capsule-free batches).  The tensors read back equal those of an
+    env that writes everything - across restarts, and across moves to another board (layout pool)."""
+    rng = np.random.default_rng(19)
+    full, lean = make_env(layouts, N, length=35, auto_reset=True, **kw), make_env(layouts, N, length=35, auto_reset=True, **kw)
+    lean.set_elide(True)
+    o1, l1 = full.reset()
+    o2, l2 = lean.reset()
+    np.testing.assert_array_equal(o1, o2)
+    for t in range(T):
+        a = biased_actions(rng, N, 0.6, t)
+        x, y = full.step(a), lean.step(a)
+        np.testing.assert_array_equal(x["obs"], y["obs"], err_msg=f"t={t}")
+        np.testing.assert_array_equal(x["reward"], y["reward"])

@@ -47,6 +47,9 @@ class CudaEnv:
     def pool_seed(self):
         return int(self.env._desc.random_seed)
 
+    def set_elide(self, on=True):
+        self.env.elide_static_planes = bool(on)
+
     def set_bits(self, on=True):
         self.env.set_bits_output(on)
 
@@ -910,3 +913,27 @@ def test_random_layout_batched_pool_and_agent_keys():
     # walls of each env's CURRENT board show in plane 0 of its observation
     walls = np.stack([env._layouts[i].walls.array.T for i in s["layout_id"]]).astype(np.float32)
     np.testing.assert_array_equal(o[1][:, 0].cpu().numpy(), walls)
+
+
+def test_cuda_static_plane_elision():
+    """pm_step_out.obs_static_valid through the host class (elide_static_planes): identical tensors, fewer bytes."""
+    from parity_bodies import body_elide_static_planes
+    from pacman_marl_2025_b200 import mazeGenerator
+    body_elide_static_planes(CudaEnv, lay_rows("tinyCapture"), N=700, T=120)
+    body_elide_static_planes(CudaEnv, lay_rows("bloxCapture"), N=300, T=80)
+    body_elide_static_planes(CudaEnv, helpers.load_traj("capsSmall")["layout"], N=200, T=90)
+    body_elide_static_planes(CudaEnv, helpers.load_traj("odd15")["layout"], N=100, T=90)
+    mazes = [mazeGenerator.generateMaze(8000 + s).split("\n") for s in range(9)]
+    body_elide_static_planes(CudaEnv, mazes, N=150, T=90, layout_pool=True, random_seed=3)
+    # the host entries carry the flag too
+    rows = lay_rows("smallCapture")
+    a_env, b_env = CudaEnv(rows, 257, length=40, auto_reset=True).env, CudaEnv(rows, 257, length=40, auto_reset=True).env
+    b_env.elide_static_planes = True
+    a_env.reset_batched(); b_env.reset_batched()
+    rng = np.random.default_rng(1)
+    for t in range(60):
+        a = torch.as_tensor(biased_actions(rng, 257, 0.6, t)).pin_memory()
+        a_env.step_host_mapped(a)
+        (b_env.step_host_mapped, b_env.step_host, lambda x: b_env.step_host_pipelined(x, n_chunks=3))[t % 3](a)
+        assert b_env._step_out.obs_static_valid == 1
+        assert torch.equal(a_env._obs, b_env._obs), t

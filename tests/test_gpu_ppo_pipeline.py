@@ -84,6 +84,8 @@ def test_flat_adam_ema_matches_torch_adam_clip_and_ema():
     import copy
     from pacman_marl_2025_b200 import sharding
     from pacman_marl_2025_b200.mappo_ops import FlatAdamEMA
+    torch.backends.cuda.matmul.allow_tf32 = False       # (a trainer test earlier in the process may have switched TF32 on:
+    torch.backends.cudnn.allow_tf32 = False             #  two copies of a net at different addresses then round differently)
     # the bucket holds the SUM over ranks in real use: double one rank's gradient and step with grad_scale = 1/2
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.GELU(), torch.nn.Linear(64, 5)).cuda()
@@ -121,6 +123,9 @@ def test_trainer_update_fused_pipeline_equals_eager_pipeline():
     eager PyTorch formulation of `pacman_mappo_resnet.py:563-600`."""
     from pacman_marl_2025_b200 import pacman_mappo_resnet as M
     res = []
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
     for fused in (True, False):
         cfg = M.TrainConfig(num_envs=64, num_steps=16, num_minibatches=4, update_epochs=3, total_updates=10, length=12,
                             seed=21, checkpoint_every=0, fused_pipeline=fused, fast_math=False)

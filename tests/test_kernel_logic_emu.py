@@ -154,3 +154,14 @@ def test_emulated_layout_pool_new_maze_every_episode():
     from parity_bodies import body_layout_pool
     body_layout_pool(lambda lays, n, **kw: EmuEnv(lays, n, E=8, KB=1, **kw), N=12, T=100, L=5)
     body_layout_pool(lambda lays, n, **kw: EmuEnv(lays, n, E=4, KB=1, **kw), N=6, T=70, L=3, seed=5, base=1000)
+
+
+def test_emulated_static_plane_elision():
+    from parity_bodies import body_elide_static_planes
+    from pacman_marl_2025_b200 import mazeGenerator
+    mk = lambda lays, n, **kw: EmuEnv(lays, n, E=8, KB=1, **kw)
+    body_elide_static_planes(mk, lay_rows("tinyCapture"), N=20, T=100)                      # no capsules: planes 0, 2, 3 skipped
+    body_elide_static_planes(mk, helpers.load_traj("capsSmall")["layout"], N=12, T=90)      # capsules: plane 0 only
+    body_elide_static_planes(mk, helpers.load_traj("odd15")["layout"], N=12, T=90)          # odd width: ragged float4 edges
+    mazes = [mazeGenerator.generateMaze(8000 + s).split("\n") for s in range(4)]
+    body_elide_static_planes(mk, mazes, N=10, T=90, layout_pool=True, random_seed=3)         # boards change at restarts

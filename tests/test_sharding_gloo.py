@@ -53,7 +53,9 @@ def _worker(rank, world, port, total_envs, q):
         ref.load_state_dict(net.state_dict())
         torch.nn.functional.mse_loss(ref(X), Y).backward()
         want = torch.cat([p.grad.reshape(-1) for p in ref.parameters()])
-        ok_grad = torch.allclose(bucket.flat, want, atol=1e-6)
+        got = torch.cat([p.grad.reshape(-1) for p in net.parameters()])          # views into the (padded) bucket
+        ok_grad = torch.allclose(got, want, atol=1e-6) and bucket.flat.numel() % 64 == 0 and \
+            abs(float(bucket.flat.sum()) - float(got.sum())) < 1e-5                # the padding holds zeros
         views_alias = all(p.grad.data_ptr() >= bucket.flat.data_ptr() for p in net.parameters())
         norm_before = float(torch.linalg.vector_norm(bucket.flat))
         total = float(bucket.clip_grad_norm_(0.01))
