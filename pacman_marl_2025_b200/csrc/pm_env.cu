@@ -62,7 +62,7 @@ extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToS
 template <int MODE, int BOTS, int VIEWS, int E>
 __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
-    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0, VIEWS);
     const int tid = threadIdx.x;
     const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * E;
 #ifdef PM_TRACE
@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
         float4 v = make_float4((tid & 1) ? 1.f : 0.f, (tid & 2) ? 1.f : 0.f, (tid & 4) ? 1.f : 0.f, (tid & 8) ? 1.f : 0.f);
         reinterpret_cast<float4 *>(sm + M.lut)[tid] = v;
     }
+    if (VIEWS)                                          // byte -> eight 0/1 bytes (the uint8 views' expansion table)
+        for (int b = tid; b < 256; b += PM_THREADS) { sm[M.lut8 + 2 * b] = pm_spread4(b & 15u); sm[M.lut8 + 2 * b + 1] = pm_spread4(b >> 4); }
     for (int i = tid; i < PM_G_NMASKS * P.NCAT; i += PM_THREADS) sm[M.masks + i] = __ldg(P.geom + PM_G_HDR + i);
     if (P.L == 1)
         for (int i = tid; i < P.LS; i += PM_THREADS) sm[M.lay + i] = __ldg(P.layouts + i);
@@ -211,7 +213,7 @@ static int launch_env_e(const PmParams &P0, cudaStream_t st) {
     if (BOTS && P.L == 1 && P.dist && (((size_t)P.dist | (size_t)P.node_of_cell) & 3) == 0 && ((P.dist_nmax * P.dist_nmax) & 1) == 0 &&
         pm_dist_stage_words(P.HW, P.dist_nmax) <= PM_DIST_STAGE_MAX_WORDS)
         P.dist_stage_words = pm_dist_stage_words(P.HW, P.dist_nmax);
-    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0, VIEWS);
     const size_t smem = (size_t)M.total * 4;
     // Per-device cache of the dynamic shared-memory size this kernel instance is configured for.  The launch stays
     // under the lock whenever the attribute may still change, so another host thread can neither launch with a size

@@ -139,12 +139,13 @@ struct PmSmem {
     int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, stage, total;
     int E1;                             // padded env stride
     int dist;                           // bots, one board: dist[nmax][nmax] u16 then node_of[HW] i16 (0 = not staged)
+    int lut8;                           // views: 256 x 8 bytes, byte b -> its eight bits as bytes (0 = absent)
 };
 // words needed to stage one board's maze-distance table + cell->node map (baselineTeam look-ahead)
 PM_HD int pm_dist_stage_words(int HW, int nmax) { return ((nmax * nmax * 2 + 3) >> 2) + ((HW * 2 + 3) >> 2); }
 #define PM_DIST_STAGE_MAX_WORDS 3072    // 12 KB: tinyCapture 7.3 KB, smallCapture 9.6 KB; bloxCapture (72 KB) stays in L2
 
-PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots = 4, int dist_words = 0) {
+PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots = 4, int dist_words = 0, int views = 0) {
     const int NW = pm_nw(HW), NCAT = pm_ncat(HW);
     PmSmem m;
     m.E1 = E | 1;
@@ -156,6 +157,8 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     o = (o + 3) & ~3;
     m.dist = 0;
     if (dist_words > 0) { m.dist = o; o += dist_words; o = (o + 3) & ~3; }
+    m.lut8 = 0;
+    if (views) { m.lut8 = o; o += 512; }
     m.blk0 = o;
     // per-block buffer
     m.lid = o; o += E;
@@ -1182,6 +1185,8 @@ PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t
     const int nbytes = 8 * P.HW;                        // bytes per view
     const int nitems = 3 * E * NCAT;
     const uint32_t magic = 0xffffffffu / (uint32_t)NCAT + 1u;      // i / NCAT == (i * magic) >> 32 for i < 2^16
+    uint8_t *const base0 = P.view_actor + (size_t)n0 * nbytes, *const base1 = base0 + P.view_actor_stride;
+    uint8_t *const base2 = P.view_critic + (size_t)n0 * nbytes;
 #if defined(__CUDA_ARCH__)
     const int lanes = 32, first = lane;
 #else
@@ -1196,11 +1201,15 @@ PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t
         const int v = u >> P.lgE, el = u & (E - 1);
         PmUnit U;
         if (!pm_view_unit_load<MODE>(P, sm, M, v, el, mslot0, U)) continue;
-        uint8_t *dstb = (v == 2 ? P.view_critic : P.view_actor + (size_t)v * P.view_actor_stride) + (size_t)(n0 + el) * nbytes;
+        uint8_t *dstb = (v == 2 ? base2 : v == 1 ? base1 : base0) + (uint32_t)el * (uint32_t)nbytes;
         const uint32_t word = pm_cat_word(P, st, M, U, j);
         uint32_t o[8];
+        const unsigned long long *lut8 = reinterpret_cast<const unsigned long long *>(st + M.lut8);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) o[q] = pm_spread4((word >> (4 * q)) & 15u);
+        for (int q = 0; q < 4; ++q) {                   // one 8-byte table entry per byte of the word
+            const unsigned long long e = lut8[(word >> (8 * q)) & 255u];
+            o[2 * q] = (uint32_t)e; o[2 * q + 1] = (uint32_t)(e >> 32);
+        }
         // own-cell values 1 + numCarrying (gymPacMan.py:205); merged view: elementwise max of the two learners' planes
         const uint32_t lo = 32u * (uint32_t)j;
         uint32_t pv = 0, pe = 0xffffffffu;

@@ -26,7 +26,7 @@ static void run(const PmParams &P) {
     int dsw = 0;
     if (bots && P.L == 1 && P.dist && ((P.dist_nmax * P.dist_nmax) & 1) == 0 && pm_dist_stage_words(P.HW, P.dist_nmax) <= PM_DIST_STAGE_MAX_WORDS)
         dsw = pm_dist_stage_words(P.HW, P.dist_nmax);
-    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L, 4 + (bots ? 1 : 0) + (views ? 2 : 0), dsw);
+    const PmSmem M = pm_smem_map(P.HW, P.LS, P.E, P.has_caps, P.L, 4 + (bots ? 1 : 0) + (views ? 2 : 0), dsw, views ? 1 : 0);
     std::vector<uint32_t> smv((size_t)M.total + 4);
     uint32_t *sm = smv.data();
     const int64_t nblk = (P.n_end - P.n_begin + P.E - 1) / P.E;
@@ -37,6 +37,7 @@ static void run(const PmParams &P) {
             float *v = reinterpret_cast<float *>(sm + M.lut) + 4 * t;
             v[0] = (t & 1) ? 1.f : 0.f; v[1] = (t & 2) ? 1.f : 0.f; v[2] = (t & 4) ? 1.f : 0.f; v[3] = (t & 8) ? 1.f : 0.f;
         }
+        if (views) for (int b = 0; b < 256; ++b) { sm[M.lut8 + 2 * b] = pm_spread4(b & 15u); sm[M.lut8 + 2 * b + 1] = pm_spread4(b >> 4); }
         for (int i = 0; i < PM_G_NMASKS * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
         if (P.L == 1) for (int i = 0; i < P.LS; ++i) sm[M.lay + i] = P.layouts[i];
         if (M.dist) {
