@@ -1116,22 +1116,35 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
             }
         }
 #else
-        // obs_static_valid: float4s that lie entirely inside plane 0 (walls) or, on capsule-free batches, planes 2-3
-        // already hold their value from the previous full write of this buffer - leave them alone
-        const bool elide = MODE == PM_MODE_STEP && P.obs_elide && !U.fresh;
-        const int s0 = P.HW >> 2;                       // float4 f is static if 4f+3 < HW ...
-        const int s1 = (2 * P.HW + 3) >> 2, s2 = P.has_caps ? 0 : (4 * P.HW) >> 2;       // ... or 2HW <= 4f and 4f+3 < 4HW
-        for (int g = 0; g < ngroups; ++g) {
-            const int j = 32 * g + lane;
-            const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
-            const int fbase = 256 * g + lane;
+        if (MODE == PM_MODE_STEP && P.obs_elide && !U.fresh) {
+            // obs_static_valid: float4s that lie entirely inside plane 0 (walls) or, on capsule-free batches, planes
+            // 2-3 already hold their value from the previous full write of this buffer - leave them alone
+            const int s0 = P.HW >> 2;                   // float4 f is static if 4f+3 < HW ...
+            const int s1 = (2 * P.HW + 3) >> 2, s2 = P.has_caps ? 0 : (4 * P.HW) >> 2;   // ... or 2HW <= 4f and 4f+3 < 4HW
+            for (int g = 0; g < ngroups; ++g) {
+                const int j = 32 * g + lane;
+                const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
+                const int fbase = 256 * g + lane;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int f0 = 256 * g + 32 * r;        // warp-uniform: the whole round may be static
-                if (elide && (f0 + 32 <= s0 || (f0 >= s1 && f0 + 32 <= s2))) continue;
-                const uint32_t w = __shfl_sync(0xffffffffu, word, 4 * r + src);
-                const int f = fbase + 32 * r;
-                if (f < nf4 && !(elide && (f < s0 || (f >= s1 && f < s2)))) dst[f] = pm_expand4(lut, (w >> sh) & 15u);
+                for (int r = 0; r < 8; ++r) {
+                    const int f0 = 256 * g + 32 * r;    // warp-uniform: the whole round may be static
+                    if (f0 + 32 <= s0 || (f0 >= s1 && f0 + 32 <= s2)) continue;
+                    const uint32_t w = __shfl_sync(0xffffffffu, word, 4 * r + src);
+                    const int f = fbase + 32 * r;
+                    if (f < nf4 && !(f < s0 || (f >= s1 && f < s2))) dst[f] = pm_expand4(lut, (w >> sh) & 15u);
+                }
+            }
+        } else {
+            for (int g = 0; g < ngroups; ++g) {
+                const int j = 32 * g + lane;
+                const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
+                const int fbase = 256 * g + lane;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const uint32_t w = __shfl_sync(0xffffffffu, word, 4 * r + src);
+                    const int f = fbase + 32 * r;
+                    if (f < nf4) dst[f] = pm_expand4(lut, (w >> sh) & 15u);
+                }
             }
         }
         if (U.patch != 0xffffffffu) {

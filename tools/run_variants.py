@@ -36,8 +36,19 @@ VARIANTS = {
     "views+obs": dict(self_play=True, views=False, raw=True),
     "bots": dict(self_play=False, team="baselineTeam", views=None, raw=True),
     "bots+views": dict(self_play=False, team="baselineTeam", views=False, raw=False),
+    "plain-elide": dict(self_play=True, views=None, raw=True, elide=True),     # pm_step_out.obs_static_valid
 }
+def clocks():
+    import subprocess
+    try:
+        return subprocess.check_output(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,clocks_event_reasons.active",
+                                        "--format=csv,noheader,nounits", "-i", "0"], text=True).strip()
+    except Exception:                                   # noqa: BLE001
+        return "n/a"
+
+
 only = [v for v in a.only.split(",") if v]
+print("lib", _lib.LIB_PATH, "| clocks before (sm MHz, mem MHz, W, reasons):", clocks(), flush=True)
 out = {}
 for N in (a.envs, a.small):
     if N <= 0:
@@ -47,7 +58,7 @@ for N in (a.envs, a.small):
         if only and name not in only:
             continue
         env = gymPacMan_parallel_env(layout_file=lay, self_play=v["self_play"], enemieName=v.get("team", "randomTeam"),
-                                     length=300, num_envs=N, auto_reset=True)
+                                     length=300, num_envs=N, auto_reset=True, elide_static_planes=v.get("elide", False))
         env.reset_batched()
         if v["views"] is not None or not v["raw"]:
             env.set_view_outputs(v["views"], raw_obs=v["raw"])
@@ -57,13 +68,16 @@ for N in (a.envs, a.small):
         torch.cuda.synchronize(); e0.record()
         for i in range(a.reps):
             env.step_batched(acts[i % 8])
+        import time as _t
+        t0 = _t.perf_counter()
         e1.record(); torch.cuda.synchronize()
+        drain = (_t.perf_counter() - t0) * 1e6 / a.reps      # ~0 when the host, not the GPU, was the bottleneck
         us = e0.elapsed_time(e1) * 1000 / a.reps
         H, W = env.obs_shape[1:]
         b = (4 * 32 * H * W if v["raw"] else 0) + (3 * 8 * H * W if v["views"] is not None else 0) + 200
         out[f"{name}-{N}"] = {"us": us, "agent_steps_per_s": 4.0 * N / us * 1e6, "bytes_per_env_step": b,
                               "GBps": b * N / us / 1e3}
-        print(f"{a.layout} {name:11s} N={N:6d}  {us:8.1f} us/launch  {4.0 * N / us:8.1f} M agent-steps/s  {b * N / us / 1e3:7.0f} GB/s",
+        print(f"{a.layout} {name:11s} N={N:6d}  {us:8.1f} us/launch  {4.0 * N / us:8.1f} M agent-steps/s  {b * N / us / 1e3:7.0f} GB/s  (drain {drain:.0f} us/launch, clocks {clocks()})",
               flush=True)
         del env
 print(json.dumps(out))
