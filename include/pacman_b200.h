@@ -274,6 +274,17 @@ int pm_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *
 int pm_set_state(const pm_env_desc *d, const int32_t *agents, const uint8_t *food, const uint8_t *caps,
                  const int32_t *misc, pm_stream_t stream);
 
+/* GameState.makeObservation (capture.py:268-292) for every env and every observer - what the tournament loop
+ * (game.py:570-732) hands an agent instead of the full state:
+ *   visible [dev] [N][4] uint8: bit e of visible[n][i] = agent e's configuration survives in agent i's view (own team
+ *           always; an enemy iff a member of i's team stands within SIGHT_RANGE = 5 Manhattan cells of it)
+ *   noisy_distances [dev] [N][4][4] int32: int(manhattanDistance(pos_i, pos_j) + SONAR_NOISE_VALUES[k]), k in 0..12
+ *           (noise -6..+6, capture.py:67-78), i = observer
+ *   draws [dev] [N][4][4] uint32 or NULL: the index k `random.choice(SONAR_NOISE_VALUES)` returned for each distance
+ *           (wraps modulo 13); NULL = hashed from (random_seed, global env index, episode, step, i, j).          */
+int pm_make_observation(const pm_env_desc *d, const uint32_t *draws, uint8_t *visible, int32_t *noisy_distances,
+                        pm_stream_t stream);
+
 /* ---- maze distances ------------------------------------------------------ */
 /* distanceCalculator.computeDistances (distanceCalculator.py:111-150) for L
  * layouts at once.  Node order = walls.asList(False) (x-major, y-minor).

@@ -24,7 +24,7 @@ EXPORTS = [
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
     "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
     "pm_obs_bits_words", "pm_observe_bits",
-    "pm_gather_rows", "pm_ppo_scratch_bytes", "pm_ppo_loss", "pm_adam_scratch_bytes", "pm_adam_ema",
+    "pm_make_observation", "pm_gather_rows", "pm_ppo_scratch_bytes", "pm_ppo_loss", "pm_adam_scratch_bytes", "pm_adam_ema",
 ]
 
 
@@ -138,6 +138,8 @@ def load():
     L.pm_gae.argtypes = [vp, vp, vp, vp, C.c_double, C.c_double, vp, vp, i32, i64, vp]
     L.pm_adv_norm.restype = i32
     L.pm_adv_norm.argtypes = [vp, vp, vp, i64, i32, vp]
+    L.pm_make_observation.restype = i32
+    L.pm_make_observation.argtypes = [C.POINTER(PmEnvDesc), vp, vp, vp, vp]
     L.pm_gather_rows.restype = i32
     L.pm_gather_rows.argtypes = [vp, vp, i64, i32, vp, i32, vp]
     L.pm_ppo_scratch_bytes.restype = C.c_size_t

@@ -477,6 +477,21 @@ extern "C" int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_
     return (int)cudaStreamSynchronize((cudaStream_t)stream);
 }
 
+__global__ void pm_make_observation_kernel(const PmParams P, const uint32_t *draws, uint8_t *visible, int32_t *noisy) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < P.N) pm_make_observation_env(P, n, draws, visible, noisy);
+}
+
+extern "C" int pm_make_observation(const pm_env_desc *d, const uint32_t *draws, uint8_t *visible, int32_t *noisy_distances,
+                                   pm_stream_t stream) {
+    PmParams P;
+    if (int rc = fill_params(d, P)) return rc;
+    if (!visible || !noisy_distances) return PM_EINVAL;
+    const unsigned grid = (unsigned)((P.N + 127) / 128);
+    pm_make_observation_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(P, draws, visible, noisy_distances);
+    return (int)cudaGetLastError();
+}
+
 extern "C" int pm_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc,
                             pm_stream_t stream) {
     PmParams P;

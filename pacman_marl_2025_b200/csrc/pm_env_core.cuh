@@ -1290,6 +1290,45 @@ PM_HD void pm_phaseB_bits(const PmParams &P, const uint32_t *st, const uint32_t 
     }
 }
 
+// ============================================================================
+// GameState.makeObservation (capture.py:268-292): what agent `index` may know - SURVEY row f4
+// ============================================================================
+#define PM_SIGHT_RANGE 5            // capture.py:69, Manhattan
+#define PM_SONAR_NOISE_RANGE 13     // capture.py:67; SONAR_NOISE_VALUES[k] = k - 6
+// For env n and every observer i: visible[n][i] = bitmask over the four agents whose configuration survives (own
+// team always; an enemy iff some member of i's team stands within SIGHT_RANGE of it), and
+// noisy[n][i][j] = int(manhattan(pos_i, pos_j) + SONAR_NOISE_VALUES[k]) with k = random.choice's index: taken from
+// draws[n][i][j] when given (wraps modulo 13), else hashed from (seed, global env, step, i, j).
+PM_HD void pm_make_observation_env(const PmParams &P, int64_t n, const uint32_t *draws, uint8_t *visible, int32_t *noisy) {
+    const pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
+    const pm_u4 Mi = reinterpret_cast<const pm_u4 *>(P.state + pm_st_misc(P.N))[n];
+    const uint32_t lid = P.layout_id ? P.layout_id[n] : (P.L == 1 ? 0u : (uint32_t)(n % P.L));
+    const uint32_t teams = (P.layouts + (size_t)lid * P.LS + pm_l_tail(P.HW))[PM_L_TEAMS];
+    const uint32_t a[4] = {A.x, A.y, A.z, A.w};
+    int x[4], y[4];
+    for (int i = 0; i < 4; ++i) { x[i] = a[i] & 0xff; y[i] = (a[i] >> 8) & 0xff; }
+    for (int i = 0; i < 4; ++i) {
+        const int ti = (teams >> i) & 1;
+        uint32_t vis = 0;
+        for (int e = 0; e < 4; ++e) {
+            if ((int)((teams >> e) & 1) == ti) { vis |= 1u << e; continue; }
+            for (int m = 0; m < 4; ++m) {
+                if ((int)((teams >> m) & 1) != ti) continue;
+                const int dx = x[e] - x[m], dy = y[e] - y[m];
+                if ((dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy) <= PM_SIGHT_RANGE) vis |= 1u << e;
+            }
+        }
+        visible[4 * n + i] = (uint8_t)vis;
+        for (int j = 0; j < 4; ++j) {
+            const int dx = x[i] - x[j], dy = y[i] - y[j];
+            const uint32_t k = draws ? draws[16 * n + 4 * i + j] % PM_SONAR_NOISE_RANGE
+                                     : (uint32_t)(((unsigned long long)pm_random_u32(P.bot_seed ^ 0x736f6e6172ull, (unsigned long long)(P.n_base + n),
+                                                                                    Mi.w, Mi.y * 16u + 4u * i + j) * PM_SONAR_NOISE_RANGE) >> 32);
+            noisy[16 * n + 4 * i + j] = (dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy) + (int)k - (PM_SONAR_NOISE_RANGE - 1) / 2;
+        }
+    }
+}
+
 // ---- pm_env_desc -> PmParams (shared by the C ABI glue and the test emulation) ----
 #ifdef PACMAN_B200_H
 static inline int pm_fill_params(const pm_env_desc *d, PmParams &P, int E) {

@@ -271,6 +271,27 @@ class _StateView:
         return self.layout.starts[i]
 
 
+class _PartialStateView(_StateView):
+    """`GameState.makeObservation(index)` (capture.py:268-292): enemies nobody on the observer's team can see have no
+    configuration, and the sonar readings come along."""
+
+    def __init__(self, env, n, visible_mask, distances):
+        super().__init__(env, n)
+        self._visible, self.agentDistances = visible_mask, distances
+
+    def getAgentDistances(self):
+        return self.agentDistances
+
+    def getAgentPosition(self, i):
+        return super().getAgentPosition(i) if (self._visible >> i) & 1 else None
+
+    def getAgentState(self, i):
+        a = super().getAgentState(i)
+        if not (self._visible >> i) & 1:
+            a.configuration = None
+        return a
+
+
 class _GameView:
     def __init__(self, env):
         self.state = _StateView(env, 0)
@@ -752,6 +773,35 @@ class gymPacMan_parallel_env:
             _lib.check(self._L.pm_observe(C.byref(self._desc), out.data_ptr(), out[0].numel(), self._stream()),
                        "pm_observe")
         return out
+
+    # ---- partial observability: GameState.makeObservation (capture.py:268-292) ----
+    def make_observation_batched(self, draws: Optional[torch.Tensor] = None):
+        """What every agent of every env may know of the CURRENT state, as the tournament loop hands it out
+        (`game.py:570-732` -> `capture.py:268-292`): ``visible`` uint8 [N,4] (bit e of ``visible[n, i]``: agent e's
+        configuration survives in agent i's view - own team always, an enemy iff a team-mate of i stands within 5
+        Manhattan cells of it) and ``noisy_distances`` int32 [N,4,4] (row i: agent i's sonar readings).  ``draws``
+        int32 [N,4,4]: the index `random.choice(SONAR_NOISE_VALUES)` returned for every reading (default: hashed
+        in-kernel from the env's seed, env index, episode and step)."""
+        N, dev = self.num_envs, self.device
+        vis = torch.empty((N, 4), dtype=torch.uint8, device=dev)
+        noisy = torch.empty((N, 4, 4), dtype=torch.int32, device=dev)
+        dptr = None
+        if draws is not None:
+            draws = draws.to(device=dev, dtype=torch.int32).contiguous()
+            if draws.numel() != 16 * N:
+                raise ValueError("draws must hold one index per (env, observer, agent)")
+            dptr = draws.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(self._L.pm_make_observation(C.byref(self._desc), dptr, vis.data_ptr(), noisy.data_ptr(),
+                                                   self._stream()), "pm_make_observation")
+        return vis, noisy
+
+    def make_observation(self, index: int, n: int = 0, draws=None):
+        """``env.game.state.makeObservation(index)`` for env ``n``: a GameState-like view in which unseen enemies have no
+        position (``getAgentPosition`` -> None) and ``getAgentDistances()`` returns the noisy readings."""
+        d = None if draws is None else torch.as_tensor(np.asarray(draws, np.int32))
+        vis, noisy = self.make_observation_batched(d)
+        return _PartialStateView(self, n, int(vis[n, index].item()), [int(v) for v in noisy[n, index].tolist()])
 
     def export_state(self) -> Dict[str, np.ndarray]:
         """Unpacked copy of the device state (GameState accessors; one D2H)."""

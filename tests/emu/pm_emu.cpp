@@ -106,6 +106,11 @@ extern "C" int emu_observe_bits(const pm_env_desc *d, uint32_t *bits, int64_t st
     run<PM_MODE_OBSERVE>(P);
     return 0;
 }
+extern "C" int emu_make_observation(const pm_env_desc *d, const uint32_t *draws, uint8_t *visible, int32_t *noisy) {
+    PmParams P; if (int rc = fill(d, P, 64, 4)) return rc;
+    for (int64_t n = 0; n < P.N; ++n) pm_make_observation_env(P, n, draws, visible, noisy);
+    return 0;
+}
 // host mirror of pm_get_state_kernel
 extern "C" int emu_get_state(const pm_env_desc *d, int32_t *agents, uint8_t *food, uint8_t *caps, int32_t *misc) {
     PmParams P; if (int rc = fill(d, P, 64, 4)) return rc;

@@ -85,6 +85,14 @@ class EmuEnv:
             self.desc.bot_first_best = int(bot_first_best)
         self.obs_shape = (8, self.H, self.W)
 
+    def make_observation(self, draws=None):
+        vis = np.zeros((self.N, 4), np.uint8)
+        noisy = np.zeros((self.N, 4, 4), np.int32)
+        d = None if draws is None else np.ascontiguousarray(np.asarray(draws).reshape(self.N, 4, 4), np.uint32)
+        rc = lib().emu_make_observation(C.byref(self.desc), _p(d), _p(vis), _p(noisy))
+        assert rc == 0, rc
+        return vis, noisy
+
     def set_elide(self, on=True):
         """pm_step_out.obs_static_valid: steps write into ONE persistent observation buffer (first filled by reset) and
         may leave the static planes untouched."""

@@ -560,6 +560,105 @@ def gae_fixture():
     np.savez_compressed(os.path.join(HERE, "gae.npz"), **out)
 
 
+def partial_fixture(lay_name, seed, episodes):
+    """GameState.makeObservation (capture.py:268-292) of the live reference at every step of scripted episodes: which
+    configurations survive in each agent's view and the noisy sonar distances, with the index every
+    random.choice(SONAR_NOISE_VALUES) returned (real global MT19937) so that a replay can be fed the same noise."""
+    rows = layout_text(lay_name)
+    env = make_env(rows, length=120)
+    rng = np.random.default_rng(seed)
+    pol = SmartPolicy(env, rng)
+    random.seed(seed)
+    picks = []
+    orig = random.choice
+
+    def choice(seq):
+        i = random.randrange(len(seq))
+        picks.append(i)
+        return seq[i]
+    R = dict(actions=[], ep_start=[], visible=[], noisy=[], draws=[])
+    for ep in range(episodes):
+        pol.new_episode()
+        with _quiet:
+            env.reset()
+        R["ep_start"].append(len(R["actions"]))
+        done = False
+        while not done:
+            acts = pol.act(env)
+            with _quiet:
+                _, _, term, _ = env.step({i: acts[i] for i in range(4)})
+            done = any(term.values())
+            st = env.game.state
+            vis, noisy, draws = [], [], []
+            random.choice = choice
+            try:
+                for i in range(4):
+                    del picks[:]
+                    o = st.makeObservation(i)
+                    assert len(picks) == 4 and list(capture.SONAR_NOISE_VALUES) == [k - 6 for k in range(13)]
+                    vis.append(sum(1 << e for e in range(4) if o.data.agentStates[e].configuration is not None))
+                    noisy.append(list(o.getAgentDistances()))
+                    draws.append(list(picks))
+            finally:
+                random.choice = orig
+            R["actions"].append(acts); R["visible"].append(vis); R["noisy"].append(noisy); R["draws"].append(draws)
+    np.savez_compressed(os.path.join(HERE, f"partial_{lay_name}.npz"), layout=np.array(rows), length=np.int32(120),
+                        actions=np.array(R["actions"], np.uint8), ep_start=np.array(R["ep_start"], np.int32),
+                        visible=np.array(R["visible"], np.uint8), noisy=np.array(R["noisy"], np.int32),
+                        draws=np.array(R["draws"], np.uint32))
+    v = np.array(R["visible"])
+    print(f"partial_{lay_name}: {len(R['actions'])} steps, hidden enemies in {int((v != 15).sum())} of {v.size} views", file=sys.stderr)
+
+
+def replay_fixture():
+    """A whole game played by the reference's own tournament loop (`Game.run`, game.py:570-732: baselineTeam red vs
+    randomTeam blue, partial observations, global RNG) and recorded the way `capture.runGames(record=True)` does
+    (`capture.py:988-996`: pickle of layout / agents / moveHistory / length / team names), plus the state after every
+    move obtained with `capture.replayGame`'s own loop (`capture.py:952-968`)."""
+    import pickle
+    import game as ref_game
+    import textDisplay
+    random.seed(77)
+    rows = layout_text("smallCapture")
+    lay = ref_layout.Layout(list(rows))
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        with _quiet:
+            red = capture.loadAgents(True, os.path.join(REF, "agents", "baselineTeam"), None, "")
+            blue = capture.loadAgents(False, os.path.join(REF, "agents", "randomTeam"), None, "")
+    finally:
+        os.chdir(cwd)
+    agents = [red[0], blue[0], red[1], blue[1]]
+    length = 400
+    rules = capture.CaptureRules()
+    with _quiet:
+        g = rules.newGame(lay, agents, textDisplay.NullGraphics(), length, True, False)
+        g.run()
+    comp = {"layout": lay, "agents": [ref_game.Agent() for a in agents], "actions": g.moveHistory, "length": length,
+            "redTeamName": "baselineTeam", "blueTeamName": "randomTeam"}
+    with open(os.path.join(HERE, "replay_smallCapture.pkl"), "wb") as f:
+        f.write(pickle.dumps(comp))
+    # the states capture.replayGame walks through
+    with _quiet:
+        g2 = capture.CaptureRules().newGame(lay, agents, textDisplay.NullGraphics(), length, False, False)
+    state = g2.state
+    pos, misc, food, score = [], [], [], []
+    for action in g.moveHistory:
+        state = state.generateSuccessor(*action)
+        d = state.data
+        pos.append([[int(a.configuration.pos[0]), int(a.configuration.pos[1])] for a in d.agentStates])
+        misc.append([[DIR_ID[a.configuration.direction], int(a.isPacman), a.scaredTimer, a.numCarrying, a.numReturned]
+                     for a in d.agentStates])
+        food.append(grid_bits(d.food))
+        score.append(int(d.score))
+    assert score[-1] == g.state.data.score
+    np.savez_compressed(os.path.join(HERE, "replay_smallCapture_states.npz"), pos=np.array(pos, np.int16),
+                        misc=np.array(misc, np.int16), food=np.array(food), score=np.array(score, np.int32),
+                        moves=np.array([[i, DIR_ID[a]] for i, a in g.moveHistory], np.int16))
+    print(f"replay_smallCapture: {len(g.moveHistory)} moves, final score {score[-1]}", file=sys.stderr)
+
+
 def main():
     only = set(sys.argv[1:])
     want = lambda k: not only or k in only
@@ -615,6 +714,13 @@ def main():
         cov["rng_baselineTeam_capsSmall"] = record("rng_baselineTeam_capsSmall", "capsSmall", "global_rng", episodes=2,
                                                     seed=1, enemie="baselineTeam", real_rng=True, full_obs_steps=8, length=150)
         digests["coverage"] = cov
+
+    if want("partial"):
+        partial_fixture("smallCapture", seed=41, episodes=2)
+        partial_fixture("tinyCapture", seed=42, episodes=2)
+
+    if want("replay"):
+        replay_fixture()
 
     if want("survey"):
         digests["survey_traj_sha256"] = {l: survey_digest(l) for l in ("tinyCapture", "smallCapture", "bloxCapture")}

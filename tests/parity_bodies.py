@@ -495,3 +495,36 @@ def body_elide_static_planes(make_env, layouts, N=40, T=120, **kw):
         x, y = full.step(a), lean.step(a)
         np.testing.assert_array_equal(x["obs"], y["obs"], err_msg=f"t={t}")
         np.testing.assert_array_equal(x["reward"], y["reward"])
+
+
+def body_make_observation(make_env, name):
+    """GameState.makeObservation (capture.py:268-292) vs a fixture recorded from the live reference: visibility masks
+    and - fed the recorded random.choice indices - the noisy sonar distances, after every step of the episodes."""
+    z = np.load(os.path.join(helpers.GOLDEN, f"partial_{name}.npz"))
+    rows = [str(r) for r in z["layout"]]
+    N = 3
+    env = make_env(rows, N, length=int(z["length"]))
+    starts = list(z["ep_start"]) + [len(z["actions"])]
+    hidden = 0
+    for ep in range(len(z["ep_start"])):
+        env.reset()
+        for t in range(starts[ep], starts[ep + 1]):
+            env.step(np.tile(z["actions"][t], (N, 1)))
+            vis, noisy = env.make_observation(np.tile(z["draws"][t][None], (N, 1, 1)))
+            np.testing.assert_array_equal(vis[1], z["visible"][t], err_msg=f"t={t} visibility")
+            np.testing.assert_array_equal(noisy[1], z["noisy"][t], err_msg=f"t={t} noisy distances")
+            hidden += int((z["visible"][t] != 15).sum())
+            # without draws: hashed noise stays inside the sonar range of the true distance
+            v2, n2 = env.make_observation()
+            true = noisy[1] - (z["draws"][t].astype(np.int64) - 6)
+            assert (np.abs(n2[1] - true) <= 6).all() and (v2 == vis).all()
+    assert hidden > 100
+
+
+def check_replay_move(z, k, st, n=0):
+    """state after recorded move k == the state capture.replayGame reaches (fixture from the live reference)."""
+    np.testing.assert_array_equal(st["agents"][n][:, 0:2], z["pos"][k], err_msg=f"move {k}: positions")
+    np.testing.assert_array_equal(st["agents"][n][:, 2:7], z["misc"][k], err_msg=f"move {k}: dir/isPacman/scared/carrying/returned")
+    W_H = st["food"].shape[1]
+    np.testing.assert_array_equal(st["food"][n], helpers.unpack_cells(z["food"][k], W_H), err_msg=f"move {k}: food")
+    assert int(st["score"][n]) == int(z["score"][k]), f"move {k}: score"

@@ -50,6 +50,11 @@ class CudaEnv:
     def set_elide(self, on=True):
         self.env.elide_static_planes = bool(on)
 
+    def make_observation(self, draws=None):
+        d = None if draws is None else torch.as_tensor(np.asarray(draws).astype(np.int32))
+        vis, noisy = self.env.make_observation_batched(d)
+        return vis.cpu().numpy(), noisy.cpu().numpy()
+
     def set_bits(self, on=True):
         self.env.set_bits_output(on)
 
@@ -937,3 +942,46 @@ def test_cuda_static_plane_elision():
         (b_env.step_host_mapped, b_env.step_host, lambda x: b_env.step_host_pipelined(x, n_chunks=3))[t % 3](a)
         assert b_env._step_out.obs_static_valid == 1
         assert torch.equal(a_env._obs, b_env._obs), t
+
+
+@pytest.mark.parametrize("name", ["smallCapture", "tinyCapture"])
+def test_cuda_make_observation_matches_reference(name):
+    """SURVEY row f4, partial observability: pm_make_observation vs GameState.makeObservation of the live reference."""
+    from parity_bodies import body_make_observation
+    body_make_observation(CudaEnv, name)
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    env = gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, name + ".lay"), self_play=True)
+    env.reset()
+    o = env.make_observation(0)                                  # start of a game: the enemies are far away
+    assert o.getAgentPosition(0) is not None and o.getAgentPosition(2) is not None
+    assert o.getAgentPosition(1) is None and o.getAgentState(3).configuration is None
+    assert len(o.getAgentDistances()) == 4
+
+
+def test_cuda_replay_of_a_reference_game_and_recorder_round_trip(tmp_path):
+    """capture.replayGame on the GPU env: the reference's recorded game (tests/golden/replay_smallCapture.pkl) move by
+    move, for a batch of copies; then a game played on the GPU env is recorded, saved in the same format and replayed
+    to the same final state."""
+    from pacman_marl_2025_b200 import replay as R
+    from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
+    from parity_bodies import check_replay_move
+    rp = R.load_replay(os.path.join(helpers.GOLDEN, "replay_smallCapture.pkl"))
+    z = np.load(os.path.join(helpers.GOLDEN, "replay_smallCapture_states.npz"))
+    seen = []
+    env = R.replay_game(rp, num_envs=5, on_move=lambda k, i, a, e: (check_replay_move(z, k, e.export_state(), n=3), seen.append(k)))
+    assert len(seen) == len(rp["actions"]) == 132 and env.game.state.data.score == int(z["score"][-1]) == 14
+    # record a GPU game (baselineTeam vs random blue), write it, replay it
+    g = gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, "tinyCapture.lay"), self_play=False, enemieName="baselineTeam",
+                               length=60, num_envs=4, opponent_seed=9)
+    g.reset_batched()
+    rec = R.Recorder(g, n=2)
+    gen = torch.Generator().manual_seed(3)
+    for t in range(61):
+        rec.after_step(g.step_batched(torch.randint(0, 5, (4, 4), generator=gen)))
+    final = g.export_state()
+    path = str(tmp_path / "replay-0")
+    rec.save(path, redTeamName="baselineTeam", blueTeamName="caller")
+    e2 = R.replay_game(R.load_replay(path))
+    s2 = e2.export_state()
+    for k in ("agents", "food", "caps", "score"):
+        np.testing.assert_array_equal(s2[k][0], final[k][2], err_msg=k)

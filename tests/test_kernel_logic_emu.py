@@ -165,3 +165,33 @@ def test_emulated_static_plane_elision():
     body_elide_static_planes(mk, helpers.load_traj("odd15")["layout"], N=12, T=90)          # odd width: ragged float4 edges
     mazes = [mazeGenerator.generateMaze(8000 + s).split("\n") for s in range(4)]
     body_elide_static_planes(mk, mazes, N=10, T=90, layout_pool=True, random_seed=3)         # boards change at restarts
+
+
+@pytest.mark.parametrize("name", ["smallCapture", "tinyCapture"])
+def test_emulated_make_observation_matches_reference(name):
+    from parity_bodies import body_make_observation
+    body_make_observation(lambda r, n, **kw: EmuEnv(r, n, E=2, KB=1, **kw), name)
+
+
+def test_replay_file_of_the_reference_loads_and_replays_move_by_move():
+    """SURVEY row f4, record / replay: a game played by the reference's tournament loop (Game.run) and pickled the way
+    capture.runGames(record=True) does is read WITHOUT the reference's classes and replayed one sub-move per launch;
+    the state after every move equals the one capture.replayGame walks through."""
+    import os
+    from pacman_marl_2025_b200 import replay as R
+    from parity_bodies import check_replay_move
+    rp = R.load_replay(os.path.join(helpers.GOLDEN, "replay_smallCapture.pkl"))
+    z = np.load(os.path.join(helpers.GOLDEN, "replay_smallCapture_states.npz"))
+    assert rp["layout_rows"] == lay_rows("smallCapture") and rp["length"] == 400 and rp["redTeamName"] == "baselineTeam"
+    assert [list(m) for m in rp["actions"]] == z["moves"].tolist()
+    env = EmuEnv(rp["layout_rows"], 2, length=10 ** 9, reward_forLegalAction=False, defenceReward=False, E=2, KB=1)
+    env.reset()
+    a = np.zeros((2, 4), np.uint8)
+    for k, (idx, act) in enumerate(rp["actions"]):
+        a[:, idx] = act
+        env.set_agents(idx, idx + 1)
+        env.step(a)
+        check_replay_move(z, k, env.get_state(), n=1)
+    # and our own writer round-trips through the same loader
+    again = R.load_replay(R.save_replay(None, rp["layout_rows"], rp["actions"], rp["length"], "a", "b"))
+    assert again["actions"] == rp["actions"] and again["layout_rows"] == rp["layout_rows"] and again["blueTeamName"] == "b"
