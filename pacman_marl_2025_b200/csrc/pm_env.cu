@@ -77,8 +77,6 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
         float4 v = make_float4((tid & 1) ? 1.f : 0.f, (tid & 2) ? 1.f : 0.f, (tid & 4) ? 1.f : 0.f, (tid & 8) ? 1.f : 0.f);
         reinterpret_cast<float4 *>(sm + M.lut)[tid] = v;
     }
-    if (VIEWS)                                          // byte -> eight 0/1 bytes (the uint8 views' expansion table)
-        for (int b = tid; b < 256; b += PM_THREADS) { sm[M.lut8 + 2 * b] = pm_spread4(b & 15u); sm[M.lut8 + 2 * b + 1] = pm_spread4(b >> 4); }
     for (int i = tid; i < PM_G_NMASKS * P.NCAT; i += PM_THREADS) sm[M.masks + i] = __ldg(P.geom + PM_G_HDR + i);
     if (P.L == 1)
         for (int i = tid; i < P.LS; i += PM_THREADS) sm[M.lay + i] = __ldg(P.layouts + i);

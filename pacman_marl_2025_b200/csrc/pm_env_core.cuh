@@ -158,7 +158,7 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     m.dist = 0;
     if (dist_words > 0) { m.dist = o; o += dist_words; o = (o + 3) & ~3; }
     m.lut8 = 0;
-    if (views) { m.lut8 = o; o += 512; }
+    (void)views;
     m.blk0 = o;
     // per-block buffer
     m.lid = o; o += E;
@@ -505,14 +505,17 @@ template <int A>
 PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAgents &g, const uint32_t *fk, const uint32_t *ck,
                              uint32_t *fs, uint32_t *cs, const PmBoard &b, int legal, int kind, uint32_t rnd,
                              bool first_best, bool rnd_is_index) {
-    const int order[5] = {0, 2, 1, 3, 4};              // Actions.getPossibleActions: N, S, E, W, Stop (game.py:295-299)
+    // Actions.getPossibleActions: N, S, E, W, Stop (game.py:295-299) = gym ints 0, 2, 1, 3, 4, one nibble each
+    const uint32_t order = 0x43120u;
     const int is_red = (X.teams >> A) & 1;
     const bool go_home = (is_red ? b.bf : b.rf) <= 0;  // foodLeft <= 0: walk towards self.start (:79-90)
     const int start_c = g.sy[A] * X.W + g.sx[A];
     int vals[5], bestv = -0x7fffffff, home_a = 4, home_d = 9999;
-#pragma unroll
+    // NOT unrolled: one copy of the look-ahead sub-move per agent instead of five keeps the kernel's code (and the
+    // rules warp's instruction fetch) 2.5x smaller; vals[] lives in local memory
+#pragma unroll 1
     for (int k = 0; k < 5; ++k) {
-        const int u = order[k];
+        const int u = (int)((order >> (4 * k)) & 15u);
         vals[k] = -0x7fffffff;
         if (!((legal >> u) & 1)) continue;
         for (int w = 0; w < X.NW; ++w) fs[w * X.E1] = fk[w * X.E1];
@@ -531,11 +534,13 @@ PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAgents &g,
     if (go_home) return home_a;
     int nb = 0;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) nb += (vals[k] == bestv && ((legal >> order[k]) & 1)) ? 1 : 0;
+    for (int k = 0; k < 5; ++k) nb += (vals[k] == bestv && ((legal >> ((order >> (4 * k)) & 15u)) & 1)) ? 1 : 0;
     int pick = first_best ? 0 : rnd_is_index ? (int)(rnd % (unsigned)nb) : (int)(((unsigned long long)rnd * (unsigned)nb) >> 32);
 #pragma unroll
-    for (int k = 0; k < 5; ++k)
-        if (vals[k] == bestv && ((legal >> order[k]) & 1)) { if (pick == 0) return order[k]; --pick; }
+    for (int k = 0; k < 5; ++k) {
+        const int u = (int)((order >> (4 * k)) & 15u);
+        if (vals[k] == bestv && ((legal >> u) & 1)) { if (pick == 0) return u; --pick; }
+    }
     return 4;
 }
 
@@ -1119,8 +1124,9 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
         if (MODE == PM_MODE_STEP && P.obs_elide && !U.fresh) {
             // obs_static_valid: float4s that lie entirely inside plane 0 (walls) or, on capsule-free batches, planes
             // 2-3 already hold their value from the previous full write of this buffer - leave them alone
-            const int s0 = P.HW >> 2;                   // float4 f is static if 4f+3 < HW ...
-            const int s1 = (2 * P.HW + 3) >> 2, s2 = P.has_caps ? 0 : (4 * P.HW) >> 2;   // ... or 2HW <= 4f and 4f+3 < 4HW
+            // (ranges rounded inwards to whole 128-byte lines: a half-written 32-byte sector costs a read-modify-write)
+            const int s0 = (P.HW >> 2) & ~7;            // float4 f is static if 4f+3 < HW ...
+            const int s1 = (((2 * P.HW + 3) >> 2) + 7) & ~7, s2 = P.has_caps ? 0 : ((4 * P.HW) >> 2) & ~7;   // ... or 2HW <= 4f, 4f+3 < 4HW
             for (int g = 0; g < ngroups; ++g) {
                 const int j = 32 * g + lane;
                 const uint32_t word = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u;
@@ -1159,7 +1165,7 @@ PM_HD void pm_phaseB(const PmParams &P, const uint32_t *st, const uint32_t *sm, 
             uint32_t words[32];
             for (int L = 0; L < 32; ++L) { const int j = 32 * g + L; words[L] = (j < NCAT) ? pm_cat_word(P, st, M, U, j) : 0u; }
             const bool elide = MODE == PM_MODE_STEP && P.obs_elide && !U.fresh;
-            const int s0 = P.HW >> 2, s1 = (2 * P.HW + 3) >> 2, s2 = P.has_caps ? 0 : (4 * P.HW) >> 2;
+            const int s0 = (P.HW >> 2) & ~7, s1 = (((2 * P.HW + 3) >> 2) + 7) & ~7, s2 = P.has_caps ? 0 : ((4 * P.HW) >> 2) & ~7;
             for (int r = 0; r < 8; ++r)
                 for (int L = 0; L < 32; ++L) {
                     const int f = 256 * g + 32 * r + L;
@@ -1217,12 +1223,9 @@ PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t
         uint8_t *dstb = (v == 2 ? base2 : v == 1 ? base1 : base0) + (uint32_t)el * (uint32_t)nbytes;
         const uint32_t word = pm_cat_word(P, st, M, U, j);
         uint32_t o[8];
-        const unsigned long long *lut8 = reinterpret_cast<const unsigned long long *>(st + M.lut8);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {                   // one 8-byte table entry per byte of the word
-            const unsigned long long e = lut8[(word >> (8 * q)) & 255u];
-            o[2 * q] = (uint32_t)e; o[2 * q + 1] = (uint32_t)(e >> 32);
-        }
+        for (int q = 0; q < 8; ++q) o[q] = pm_spread4((word >> (4 * q)) & 15u);     // (a 256 x 8-byte shared-memory table
+                                                                                    //  was measured 5 % slower on B200)
         // own-cell values 1 + numCarrying (gymPacMan.py:205); merged view: elementwise max of the two learners' planes
         const uint32_t lo = 32u * (uint32_t)j;
         uint32_t pv = 0, pe = 0xffffffffu;

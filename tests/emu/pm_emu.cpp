@@ -37,7 +37,6 @@ static void run(const PmParams &P) {
             float *v = reinterpret_cast<float *>(sm + M.lut) + 4 * t;
             v[0] = (t & 1) ? 1.f : 0.f; v[1] = (t & 2) ? 1.f : 0.f; v[2] = (t & 4) ? 1.f : 0.f; v[3] = (t & 8) ? 1.f : 0.f;
         }
-        if (views) for (int b = 0; b < 256; ++b) { sm[M.lut8 + 2 * b] = pm_spread4(b & 15u); sm[M.lut8 + 2 * b + 1] = pm_spread4(b >> 4); }
         for (int i = 0; i < PM_G_NMASKS * P.NCAT; ++i) sm[M.masks + i] = P.geom[PM_G_HDR + i];
         if (P.L == 1) for (int i = 0; i < P.LS; ++i) sm[M.lay + i] = P.layouts[i];
         if (M.dist) {

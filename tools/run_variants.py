@@ -29,7 +29,8 @@ ap.add_argument("--warm", type=int, default=5)
 ap.add_argument("--only", default="")
 ap.add_argument("--small", type=int, default=1024)
 a = ap.parse_args()
-lay = os.path.join(os.path.dirname(_lib.LIB_PATH), "layouts", a.layout + ".lay")
+lay = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pacman_marl_2025_b200", "layouts", a.layout + ".lay")
+assert os.path.exists(lay), lay
 VARIANTS = {
     "plain": dict(self_play=True, views=None, raw=True),
     "views": dict(self_play=False, team="randomTeam", views=False, raw=False),

@@ -5,7 +5,7 @@ from pacman_marl_2025_b200 import _lib
 from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
 N = 65536
 for lay in ("tinyCapture", "bloxCapture"):
-    env = gymPacMan_parallel_env(layout_file=os.path.join(os.path.dirname(_lib.LIB_PATH), "layouts", lay + ".lay"),
+    env = gymPacMan_parallel_env(layout_file=os.path.join(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pacman_marl_2025_b200"), "layouts", lay + ".lay"),
                                  self_play=False, enemieName="baselineTeam", length=300, num_envs=N, auto_reset=True)
     acts = torch.randint(0, 5, (8, N, 4), dtype=torch.uint8).cuda()
     for raw in (True, False):

@@ -7,7 +7,7 @@ from pacman_marl_2025_b200 import _lib
 from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
 lay = sys.argv[1] if len(sys.argv) > 1 else "tinyCapture"
 N = 65536
-env = gymPacMan_parallel_env(layout_file=os.path.join(os.path.dirname(_lib.LIB_PATH), "layouts", lay + ".lay"),
+env = gymPacMan_parallel_env(layout_file=os.path.join(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pacman_marl_2025_b200"), "layouts", lay + ".lay"),
                              self_play=True, length=300, num_envs=N, auto_reset=True)
 acts = torch.randint(0, 5, (8, N, 4), dtype=torch.uint8).cuda()
 L = _lib.load()
