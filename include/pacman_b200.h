@@ -91,8 +91,9 @@ typedef struct pm_env_desc {
        reward / done / score_change / shaping describe the terminal step; obs / legal and the
        stored state are those of the fresh episode.                                         */
     int32_t auto_reset;
-    /* ---- ABI 7 ---- envs per CTA of the env kernels: 0 = chosen from the batch size (32, or 8 for batches that
-       would leave SMs idle), 8 or 32 = forced (launch geometry only; results never depend on it)            */
+    /* ---- ABI 7 ---- envs per CTA of the env kernels: 0 = chosen from the batch size (the large-batch geometry, or 8
+       for batches that would leave SMs idle); 8 = force the small CTAs, 32 = force the large-batch geometry (32 envs
+       per CTA, 64 for the launches bound by the rules phase).  Launch geometry only; results never depend on it.  */
     int32_t envs_per_cta;
     int64_t env_index_base;       /* global index of env 0 of this batch (rank offset when the batch is a
                                      shard): keys the in-kernel random draws, so trajectories do not

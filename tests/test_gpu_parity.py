@@ -952,10 +952,14 @@ def test_cuda_make_observation_matches_reference(name):
     from pacman_marl_2025_b200.gymPacMan import gymPacMan_parallel_env
     env = gymPacMan_parallel_env(layout_file=os.path.join(LAYDIR, name + ".lay"), self_play=True)
     env.reset()
-    o = env.make_observation(0)                                  # start of a game: the enemies are far away
-    assert o.getAgentPosition(0) is not None and o.getAgentPosition(2) is not None
-    assert o.getAgentPosition(1) is None and o.getAgentState(3).configuration is None
-    assert len(o.getAgentDistances()) == 4
+    o = env.make_observation(0)
+    pos = [env.game.state.getAgentPosition(i) for i in range(4)]
+    assert o.getAgentPosition(0) == pos[0] and o.getAgentPosition(2) == pos[2]
+    for e in (1, 3):                                             # an enemy shows iff a red agent stands within 5 cells of it
+        seen = any(abs(pos[e][0] - pos[m][0]) + abs(pos[e][1] - pos[m][1]) <= 5 for m in (0, 2))
+        assert (o.getAgentPosition(e) == pos[e]) if seen else (o.getAgentPosition(e) is None and o.getAgentState(e).configuration is None)
+    assert len(o.getAgentDistances()) == 4 and all(abs(d - (abs(pos[0][0] - p[0]) + abs(pos[0][1] - p[1]))) <= 6
+                                                    for d, p in zip(o.getAgentDistances(), pos))
 
 
 def test_cuda_replay_of_a_reference_game_and_recorder_round_trip(tmp_path):
