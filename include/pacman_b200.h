@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PM_ABI_VERSION 7
+#define PM_ABI_VERSION 8
 
 /* argument errors */
 #define PM_EINVAL   (-1)  /* null pointer / bad size                                   */
@@ -210,6 +210,26 @@ int pm_reset(const pm_env_desc *d, const uint8_t *mask, float *obs, int64_t obs_
  * illegal move (-> Stop, no legal-action bonus).                             */
 int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
             pm_stream_t stream);
+
+/* ---- ABI 8: a run of steps whose actions are already resident ----
+ * `for t in range(n_steps): env.step(actions[t])` (gymPacMan.py:143-193 driven by a policy that does not look at the
+ * observations: the self-play random-action loop of BASELINE config 2, scripted opponents, a recorded move list) as
+ * n_steps launches of the same kernel on `stream` that OVERLAP: launch t+1 is a programmatic dependent launch
+ * (sm_90+: cudaLaunchAttributeProgrammaticStreamSerialization), so its CTAs take the SM slots launch t frees in its
+ * tail and run their rules phase under launch t's last stores instead of after them.  Envs are independent, so the
+ * only ordering that matters is per env tile: every CTA publishes a counter when it is done and the CTA of the next
+ * launch that owns the same envs (same grid, same tile) waits for it (acquire / release at GPU scope) before it reads
+ * the state or writes the outputs.  Results are identical to n_steps calls of pm_step.
+ *   actions  [dev] step t reads the [N][4] block at actions + t*actions_step_stride elements (stride 0 = the same
+ *            block every step); ALL of it must be valid before the call
+ *   outs     n_outs descriptors; step t writes outs[t % n_outs] (1 = the same buffers every step, n_steps = a
+ *            rollout buffer with one slot per step)
+ *   scratch  [dev] pm_chain_scratch_bytes(N) bytes, 4-byte aligned, owned by the caller; contents irrelevant
+ * Whole steps of the whole batch only (agent_begin/agent_end and env_begin/env_count must be 0).  Work queued on
+ * `stream` after the call is ordered after the last step as usual.                                              */
+size_t pm_chain_scratch_bytes(int64_t n_envs);
+int pm_step_chain(const pm_env_desc *d, const void *actions, int action_itemsize, int64_t actions_step_stride,
+                  int n_steps, const pm_step_out *outs, int n_outs, void *scratch, pm_stream_t stream);
 
 /* get_Observation(agentIndex) on the CURRENT state (gymPacMan.py:195-229) for
  * all four agents of every env. */

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("PM_LIB_PATH") or os.path.join(_HERE, "libpacman_b200.
 PM_ERRORS = {-1: "PM_EINVAL (bad argument)", -2: "PM_ELAYOUT (malformed layout text)",
              -3: "PM_ETOOBIG (board larger than 1024 cells or a side > 255)", -4: "PM_ENOGPU"}
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 EXPORTS = [
     "pm_abi_version", "pm_geom_words", "pm_layout_words", "pm_state_bytes", "pm_pack_geom", "pm_pack_layout",
@@ -24,6 +24,7 @@ EXPORTS = [
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
     "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
     "pm_obs_bits_words", "pm_observe_bits",
+    "pm_chain_scratch_bytes", "pm_step_chain",
     "pm_make_observation", "pm_gather_rows", "pm_ppo_scratch_bytes", "pm_ppo_loss", "pm_adam_scratch_bytes", "pm_adam_ema",
 ]
 
@@ -110,6 +111,10 @@ def load():
     L.pm_reset.argtypes = [C.POINTER(PmEnvDesc), vp, vp, i64, vp, vp]
     L.pm_step.restype = i32
     L.pm_step.argtypes = [C.POINTER(PmEnvDesc), vp, i32, C.POINTER(PmStepOut), vp]
+    L.pm_chain_scratch_bytes.restype = C.c_size_t
+    L.pm_chain_scratch_bytes.argtypes = [i64]
+    L.pm_step_chain.restype = i32
+    L.pm_step_chain.argtypes = [C.POINTER(PmEnvDesc), vp, i32, i64, i32, C.POINTER(PmStepOut), i32, vp, vp]
     L.pm_observe.restype = i32
     L.pm_observe.argtypes = [C.POINTER(PmEnvDesc), vp, i64, vp]
     L.pm_observe_bits.restype = i32

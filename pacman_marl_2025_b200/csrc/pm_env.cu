@@ -65,6 +65,10 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
     const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0, VIEWS);
     const int tid = threadIdx.x;
     const int64_t n0 = P.n_begin + (int64_t)blockIdx.x * E;
+    // pm_step_chain: the next launch of the run may take the SM slots this launch no longer needs as soon as every CTA
+    // of this one has started (programmatic dependent launch); what orders the two is the per-tile counter below
+    const bool chained = MODE == PM_MODE_STEP && P.chain_flags != nullptr;
+    if (chained) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef PM_TRACE
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) {
         unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -87,6 +91,21 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
         const uint32_t *gd = reinterpret_cast<const uint32_t *>(P.dist), *gn = reinterpret_cast<const uint32_t *>(P.node_of_cell);
         for (int i = tid; i < dw; i += PM_THREADS) sm[M.dist + i] = __ldg(gd + i);
         for (int i = tid; i < nw; i += PM_THREADS) sm[M.dist + dw + i] = __ldg(gn + i);
+    }
+    if (chained && P.chain_k > 0 && tid == 0) {
+        // Launch k of a chain started before launch k-1 finished.  This CTA's envs, observation rows and output records
+        // were last touched by the CTA with the same index of launch k-1: wait until that CTA has published k
+        // (release / acquire at GPU scope; the barrier below extends the ordering to the whole CTA).  Launch k-1's CTAs
+        // are all resident or finished before any CTA of launch k is scheduled, so the wait always ends.
+        const uint32_t *f = P.chain_flags + blockIdx.x;
+        uint32_t v = 0;
+        for (unsigned spin = 0;; ++spin) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v == P.chain_k) break;
+            if (spin > (1u << 24)) __trap();            // (seconds: the chain was mis-used; fail instead of hanging the GPU)
+            __nanosleep(100);
+        }
+        __threadfence();
     }
     __syncthreads();
 
@@ -111,6 +130,14 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
     __syncthreads();
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) pm_trace_buf[4 * blockIdx.x + 3] = pm_gtime();
 #endif
+    if (chained) {
+        // every store of this CTA (state, observations, records) happens-before the counter the next launch polls
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.chain_flags + blockIdx.x), "r"(P.chain_k + 1u) : "memory");
+        }
+    }
 }
 
 // ---- state export / import (GameState accessors; tests, checkpoints) ---------
@@ -233,6 +260,16 @@ static int launch_env_e(const PmParams &P0, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         configured[dev] = smem;
     }
+    if (MODE == PM_MODE_STEP && P.chain_flags && P.chain_k > 0) {
+        // launch k > 0 of a chain: allowed to start while the previous launch of the stream (launch k-1) is still running
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(PM_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, pm_env_kernel<MODE, BOTS, VIEWS, E>, P);
+    }
     pm_env_kernel<MODE, BOTS, VIEWS, E><<<grid, PM_THREADS, smem, st>>>(P);
     return (int)cudaGetLastError();
 }
@@ -314,10 +351,11 @@ extern "C" int pm_observe_views(const pm_env_desc *d, int view_red, uint8_t *vie
     return launch_env<PM_MODE_OBSERVE, 0, 1>(P, (cudaStream_t)stream);
 }
 
-extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
-                       pm_stream_t stream) {
+static int step_impl(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
+                     pm_stream_t stream, uint32_t *chain_flags, uint32_t chain_k) {
     PmParams P;
     if (int rc = fill_params(d, P)) return rc;
+    P.chain_flags = chain_flags; P.chain_k = chain_k;
     if (!actions || !out || (action_itemsize != 1 && action_itemsize != 8)) return PM_EINVAL;
     if (out->obs && ((out->obs_agent_stride & 3) || ((size_t)out->obs & 15))) return PM_EINVAL;
     P.actions = actions; P.act_size = action_itemsize;
@@ -329,8 +367,42 @@ extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_ite
     if (P.view_actor && (P.a0 != 0 || P.a1 != 4)) return PM_EINVAL;                    // views need both learners' snapshots
     if (int rc = set_bits(P, out->obs_bits, out->obs_bits_agent_stride)) return rc;
     const bool bots = has_lookahead_bots(P), views = P.view_actor != nullptr;
+    // steps with the baselineTeam look-ahead are bound by their rules phase and run as ONE wave of 64-env CTAs: there
+    // is no store-only tail for the next launch to hide under, and sharing the SMs between two steps costs more than
+    // it returns (B200, tinyCapture 65,536 envs: 142 us per step alone, 198 us overlapped) - a chain of such steps is
+    // issued as ordinary launches
+    if (bots) P.chain_flags = nullptr;
     if (bots) return views ? launch_env<PM_MODE_STEP, 1, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 1, 0>(P, (cudaStream_t)stream);
     return views ? launch_env<PM_MODE_STEP, 0, 1>(P, (cudaStream_t)stream) : launch_env<PM_MODE_STEP, 0, 0>(P, (cudaStream_t)stream);
+}
+
+extern "C" int pm_step(const pm_env_desc *d, const void *actions, int action_itemsize, const pm_step_out *out,
+                       pm_stream_t stream) {
+    return step_impl(d, actions, action_itemsize, out, stream, nullptr, 0);
+}
+
+// ---- a run of steps whose actions are already resident ------------------------------
+extern "C" size_t pm_chain_scratch_bytes(int64_t n_envs) {
+    return n_envs > 0 ? (size_t)((n_envs + PM_E_SMALL - 1) / PM_E_SMALL) * sizeof(uint32_t) : 0;   // one counter per CTA
+}
+
+extern "C" int pm_step_chain(const pm_env_desc *d, const void *actions, int action_itemsize, int64_t actions_step_stride,
+                             int n_steps, const pm_step_out *outs, int n_outs, void *scratch, pm_stream_t stream) {
+    if (!d || !actions || !outs || n_steps < 1 || n_outs < 1 || !scratch || ((size_t)scratch & 3) || actions_step_stride < 0)
+        return PM_EINVAL;
+    if (action_itemsize != 1 && action_itemsize != 8) return PM_EINVAL;
+    if (d->agent_begin || d->agent_end || d->env_begin || d->env_count) return PM_EINVAL;     // whole steps of the whole batch
+    // the counters start at 0; launch 0 is an ordinary (fully stream-ordered) launch, so everything queued before the
+    // chain - this memset included - is complete before any launch of the chain reads or writes
+    cudaError_t e = cudaMemsetAsync(scratch, 0, pm_chain_scratch_bytes(d->n_envs), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    const char *a = (const char *)actions;
+    for (int k = 0; k < n_steps; ++k) {
+        const int rc = step_impl(d, a + (size_t)k * (size_t)actions_step_stride * (size_t)action_itemsize, action_itemsize,
+                                 outs + (k % n_outs), stream, (uint32_t *)scratch, (uint32_t)k);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 // ---- host-buffer step ------------------------------------------------------

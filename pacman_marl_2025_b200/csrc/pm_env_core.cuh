@@ -117,6 +117,9 @@ struct PmParams {
     int epc;                            // pm_env_desc.envs_per_cta (0 = auto)
     int obs_elide;                      // pm_step_out.obs_static_valid: skip the observation elements that cannot have changed
     int dist_stage_words;               // > 0: the (single) board's distance table + node map are staged in shared memory
+    // ABI 8 (pm_step_chain): launch `chain_k` of a run of chained step launches; chain_flags[cta] = number of launches
+    // of the run that have finished this CTA's env tile (see pm_env.cu)
+    uint32_t *chain_flags; uint32_t chain_k;
 };
 
 #ifndef PM_TMA_STORE

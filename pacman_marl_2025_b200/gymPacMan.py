@@ -530,6 +530,59 @@ class gymPacMan_parallel_env:
             raise ValueError(f"expected {self.num_envs}x4 actions, got {tuple(actions.shape)}")
         return self._launch_step(actions)
 
+    def step_chain(self, actions: torch.Tensor, collect: bool = False):
+        """``for t in range(T): step_batched(actions[t])`` as ONE call (pm_step_chain): T launches that overlap, each
+        env tile of step t+1 starting as soon as the same tile of step t is done.  For loops whose actions do not depend
+        on the observations (random-action self-play, scripted policies, recorded move lists).  actions: [T, N, 4]
+        uint8 / int64 on the env's device.  Returns the dict of the LAST step; with ``collect`` the per-step small
+        outputs are kept as well: ``reward`` [T,2,N], ``done`` [T,N], ``legal`` [T,N,4], ``score_change`` [T,N],
+        ``shaped_reward`` [T,4,N], ``actions_used`` [T,N,4] (observations are always the last step's)."""
+        if actions.device != self.device:
+            actions = actions.to(self.device)
+        if actions.dtype not in (torch.uint8, torch.int64):
+            actions = actions.to(torch.int64)
+        actions = actions.contiguous()
+        N = self.num_envs
+        if actions.dim() != 3 or tuple(actions.shape[1:]) != (N, 4):
+            raise ValueError(f"expected [T, {N}, 4] actions, got {tuple(actions.shape)}")
+        if self._bot_team is not None:
+            raise ValueError("host-side bots decide from the live state: use step()")
+        T = int(actions.shape[0])
+        if getattr(self, "_chain_scratch", None) is None or self._chain_scratch.device != self.device:
+            self._chain_scratch = torch.empty(max(4, int(self._L.pm_chain_scratch_bytes(N))), dtype=torch.uint8,
+                                              device=self.device)
+        self._mark_static()
+        if collect:
+            dev = self.device
+            coll = dict(reward=torch.empty((T, 2, N), dtype=torch.float64, device=dev),
+                        done=torch.empty((T, N), dtype=torch.uint8, device=dev),
+                        legal=torch.empty((T, N, 4), dtype=torch.uint8, device=dev),
+                        score_change=torch.empty((T, N), dtype=torch.int32, device=dev),
+                        shaped_reward=torch.empty((T, 4, N), dtype=torch.float32, device=dev),
+                        actions_used=torch.empty((T, N, 4), dtype=torch.uint8, device=dev))
+            outs = (_lib.PmStepOut * T)()
+            for t in range(T):
+                C.memmove(C.byref(outs[t]), C.byref(self._step_out), C.sizeof(_lib.PmStepOut))
+                o = outs[t]
+                o.reward, o.done, o.legal = coll["reward"][t].data_ptr(), coll["done"][t].data_ptr(), coll["legal"][t].data_ptr()
+                o.score_change, o.shaped_reward = coll["score_change"][t].data_ptr(), coll["shaped_reward"][t].data_ptr()
+                o.actions_used = coll["actions_used"][t].data_ptr()
+            n_outs = T
+        else:
+            outs, n_outs = (_lib.PmStepOut * 1)(), 1
+            C.memmove(C.byref(outs[0]), C.byref(self._step_out), C.sizeof(_lib.PmStepOut))
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_step_chain(C.byref(self._desc), actions.data_ptr(), actions.element_size(), 4 * N, T,
+                                             outs, n_outs, self._chain_scratch.data_ptr(), self._stream()), "pm_step_chain")
+        self._version += 1
+        self.steps += T
+        out = self._out_dict()
+        if collect:
+            # the env's own small-output buffers were not written by this call: hand back the last step's slices
+            out.update({k: v[-1] for k, v in coll.items()})
+            out["collected"] = coll
+        return out
+
     # ---- learner views: the trainer's network inputs written by the encoder (pm_step_out.view_*) ----
     def set_view_outputs(self, red: Optional[bool], actor: Optional[torch.Tensor] = None,
                          critic: Optional[torch.Tensor] = None, raw_obs: bool = True):

@@ -94,7 +94,9 @@ def replay_game(replay: Dict, num_envs: int = 1, device=None, on_move=None):
                                  num_envs=num_envs, device=device, reward_forLegalAction=False, defenceReward=False)
     env.reset_batched()
     a = torch.zeros((num_envs, 4), dtype=torch.uint8, device=env.device)
-    expect = 0
+    # CaptureRules.newGame draws the first mover (capture.py:372-374: `starter = random.randint(0,1)`), so a recorded
+    # game may open with agent 1; after that the turn order is cyclic (game.py:700-708)
+    expect = replay["actions"][0][0] if replay["actions"] else 0
     for k, (idx, act) in enumerate(replay["actions"]):
         if idx != expect:
             raise ValueError(f"move {k}: agent {idx} moves out of turn (expected agent {expect})")

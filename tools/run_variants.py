@@ -28,6 +28,7 @@ ap.add_argument("--reps", type=int, default=50)
 ap.add_argument("--warm", type=int, default=5)
 ap.add_argument("--only", default="")
 ap.add_argument("--small", type=int, default=1024)
+ap.add_argument("--chain", type=int, default=0, help="> 0: also time the same steps as pm_step_chain runs of this length")
 a = ap.parse_args()
 lay = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "pacman_marl_2025_b200", "layouts", a.layout + ".lay")
 assert os.path.exists(lay), lay
@@ -80,5 +81,18 @@ for N in (a.envs, a.small):
                               "GBps": b * N / us / 1e3}
         print(f"{a.layout} {name:11s} N={N:6d}  {us:8.1f} us/launch  {4.0 * N / us:8.1f} M agent-steps/s  {b * N / us / 1e3:7.0f} GB/s  (drain {drain:.0f} us/launch, clocks {clocks()})",
               flush=True)
+        if a.chain > 0:
+            T = a.chain
+            ca = torch.randint(0, 5, (T, N, 4), dtype=torch.uint8).cuda()
+            env.step_chain(ca)
+            torch.cuda.synchronize(); e0.record()
+            reps = max(1, a.reps // T)
+            for i in range(reps):
+                env.step_chain(ca)
+            e1.record(); torch.cuda.synchronize()
+            usc = e0.elapsed_time(e1) * 1000 / (reps * T)
+            out[f"{name}-{N}"]["chain_us"] = usc
+            print(f"{a.layout} {name:11s} N={N:6d}  {usc:8.1f} us/step in chains of {T}  {4.0 * N / usc:8.1f} M agent-steps/s  {b * N / usc / 1e3:7.0f} GB/s",
+                  flush=True)
         del env
 print(json.dumps(out))
