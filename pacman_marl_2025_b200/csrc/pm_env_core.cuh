@@ -251,35 +251,28 @@ PM_HD void pm_mirror_bits(const uint32_t *src, uint32_t *dst, int st, int W, int
     }
 }
 
-// Agents of one env, unpacked into registers (all loops over agents unroll).
-struct PmAgents {
-    int x[4], y[4], dir[4], pac[4], scared[4], carry[4], ret[4];
-    int sx[4], sy[4];
-};
+// Agents of one env in registers, in the state blob's own packing (pm_format.h):
+//   a[i] = x | y<<8 | dir<<16 | isPacman<<19 | scaredTimer<<20        b[i] = numCarrying | numReturned<<16
+// Every array index in this file is a compile-time constant (loops over agents unroll), so the eight words stay in
+// registers.  The agent that MOVES is a run-time index - the four sub-moves of a step, and the look-ahead of the
+// on-device bots, share one copy of the rules code instead of one per agent (the per-agent template instantiations
+// this replaces were 7 100 SASS instructions = 113 KB for the rules phase, and the warp that runs it spent 40 % of
+// its time waiting for instruction fetches) - and is read / written through pm_sel4 / pm_put4.
+struct PmAg { uint32_t a[4], b[4]; };
 
-PM_HD void pm_home(PmAgents &g, int i) {        // configuration = start (capture.py:691-693 etc.)
-    g.pac[i] = 0; g.x[i] = g.sx[i]; g.y[i] = g.sy[i]; g.dir[i] = 4; g.scared[i] = 0;
+PM_HD uint32_t pm_sel4(const uint32_t (&v)[4], int i) { return (i & 2) ? ((i & 1) ? v[3] : v[2]) : ((i & 1) ? v[1] : v[0]); }
+PM_HD void pm_put4(uint32_t (&v)[4], int i, uint32_t x) {
+    v[0] = i == 0 ? x : v[0]; v[1] = i == 1 ? x : v[1]; v[2] = i == 2 ? x : v[2]; v[3] = i == 3 ? x : v[3];
 }
-
-// One pacman/ghost pair on the same cell (capture.py:682-701 and :708-727): an
-// unscared ghost kills the pacman (dump, respawn), a scared ghost is sent home.
-// `pacman` and `ghost` are compile-time after unrolling, so PmAgents stays in registers.
-PM_HD uint32_t pm_collide(PmAgents &g, const int pacman, const int ghost, int W, int H, int ND, const uint32_t *dumptab,
-                          const uint32_t *walls, uint32_t *fk, const uint32_t *ck, int E1) {
-    uint32_t added = 0;
-    if (g.scared[ghost] <= 0) {
-        if (g.carry[pacman] > 0) {
-            const uint32_t c01 = (uint32_t)(g.y[0] * W + g.x[0]) | (uint32_t)(g.y[1] * W + g.x[1]) << 16;
-            const uint32_t c23 = (uint32_t)(g.y[2] * W + g.x[2]) | (uint32_t)(g.y[3] * W + g.x[3]) << 16;
-            added = pm_dump(W, H, ND, dumptab, walls, fk, ck, E1, g.x[pacman], g.y[pacman], g.carry[pacman], c01, c23);
-            g.carry[pacman] = 0;
-        }
-        pm_home(g, pacman);
-    } else {
-        pm_home(g, ghost);
-    }
-    return added;
-}
+PM_HD int pm_ax(uint32_t a) { return (int)(a & 0xff); }
+PM_HD int pm_ay(uint32_t a) { return (int)((a >> 8) & 0xff); }
+PM_HD int pm_adir(uint32_t a) { return (int)((a >> 16) & 7); }
+PM_HD int pm_apac(uint32_t a) { return (int)((a >> 19) & 1); }
+PM_HD int pm_ascared(uint32_t a) { return (int)(a >> 20); }
+PM_HD int pm_acell(uint32_t a, int W) { return pm_ay(a) * W + pm_ax(a); }
+PM_HD int pm_bcarry(uint32_t b) { return (int)(b & 0xffff); }
+// configuration = start, not a pacman, heading Stop, not scared (capture.py:691-693 etc.)
+PM_HD uint32_t pm_home_word(const uint32_t *tail, int i) { return (tail[PM_L_START + i] & 0xffffu) | 4u << 16; }
 
 PM_HD int pm_legal_mask(const uint32_t *walls, int W, int c) {   // game.py:335-350, bit = gym action int
     return (pm_bit(walls, c + W) ? 0 : 1) | (pm_bit(walls, c + 1) ? 0 : 2) | (pm_bit(walls, c - W) ? 0 : 4) |
@@ -315,44 +308,31 @@ PM_HD int pm_random_legal(int legal, uint32_t draw, bool is_index) {
     return 4;
 }
 
-// heuristic shaping (pacman_mappo_resnet.py:251-264); L1 distance is flip-invariant
-PM_HD double pm_shaping(int px, int py, int pcarry, int nx, int ny) {
+// heuristic shaping (pacman_mappo_resnet.py:251-264); L1 distance is flip-invariant.  A turn only records WHICH of
+// the formula's cases applies (case | carrying << 2); the fp64 value is formed where it is consumed.
+#define PM_SHAPE_NONE 0xffffffffu      // agent has not moved in this step yet: 0.0
+PM_HD uint32_t pm_shaping_code(int px, int py, int pcarry, int nx, int ny) {
     int dx = px - nx, dy = py - ny;
     const int dist = (dx < 0 ? -dx : dx) + (dy < 0 ? -dy : dy);
+    return (uint32_t)(dist >= 2 ? 2 : dist) | (uint32_t)pcarry << 2;
+}
+PM_HD double pm_shaping_value(uint32_t code) {
+    if (code == PM_SHAPE_NONE) return 0.0;
     const double living = -0.15;
-    if (dist >= 2) return pm_dadd(pm_dadd(living, -0.4), -pm_dmul(0.15, (double)pcarry));
-    if (dist == 0) return pm_dadd(living, -0.05);
+    const int cls = (int)(code & 3);
+    if (cls == 2) return pm_dadd(pm_dadd(living, -0.4), -pm_dmul(0.15, (double)(code >> 2)));
+    if (cls == 0) return pm_dadd(living, -0.05);
     return living;
 }
 
-PM_HD void pm_store_snapshot(uint32_t *sm, const PmSmem &M, const PmParams &P, int k, int el, const PmAgents &g) {
+PM_HD void pm_store_snapshot(uint32_t *sm, const PmSmem &M, const PmParams &P, int k, int el, const PmAg &g) {
     const int HW = P.HW, W = P.W;
-    const int me = k, ally = k ^ 2, e1 = k ^ 1, e2 = k ^ 3;       // gym teams by index parity, gymPacMan.py:210
-    const uint32_t own = (uint32_t)(HW + g.y[me] * W + g.x[me]);
-    sm[M.posA + k * M.E1 + el] = own | (uint32_t)(4 * HW + g.y[ally] * W + g.x[ally]) << 16;
-    sm[M.posB + k * M.E1 + el] = (uint32_t)(5 * HW + g.y[e1] * W + g.x[e1]) | (uint32_t)(5 * HW + g.y[e2] * W + g.x[e2]) << 16;
-    sm[M.patch + k * M.E1 + el] = g.carry[me] > 0 ? (own | (uint32_t)(1 + g.carry[me]) << 16) : 0xffffffffu;
-}
-
-PM_HD void pm_unpack_agents(PmAgents &g, const pm_u4 &A, const pm_u4 &B, const uint32_t *tail) {
-    const uint32_t a[4] = {A.x, A.y, A.z, A.w}, b[4] = {B.x, B.y, B.z, B.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        g.x[i] = a[i] & 0xff; g.y[i] = (a[i] >> 8) & 0xff; g.dir[i] = (a[i] >> 16) & 7;
-        g.pac[i] = (a[i] >> 19) & 1; g.scared[i] = (a[i] >> 20) & 0xff;
-        g.carry[i] = b[i] & 0xffff; g.ret[i] = b[i] >> 16;
-        g.sx[i] = tail[PM_L_START + i] & 0xff; g.sy[i] = (tail[PM_L_START + i] >> 8) & 0xff;
-    }
-}
-PM_HD void pm_pack_agents(const PmAgents &g, pm_u4 &A, pm_u4 &B) {
-    uint32_t a[4], b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        a[i] = pm_agA_pack(g.x[i], g.y[i], g.dir[i], g.pac[i], g.scared[i]);
-        b[i] = (uint32_t)g.carry[i] | (uint32_t)g.ret[i] << 16;
-    }
-    A.x = a[0]; A.y = a[1]; A.z = a[2]; A.w = a[3];
-    B.x = b[0]; B.y = b[1]; B.z = b[2]; B.w = b[3];
+    // gym teams by index parity, gymPacMan.py:210: me = k, ally = k ^ 2, enemies k ^ 1 and k ^ 3
+    const uint32_t me = pm_sel4(g.a, k), carry = (uint32_t)pm_bcarry(pm_sel4(g.b, k));
+    const uint32_t own = (uint32_t)(HW + pm_acell(me, W));
+    sm[M.posA + k * M.E1 + el] = own | (uint32_t)(4 * HW + pm_acell(pm_sel4(g.a, k ^ 2), W)) << 16;
+    sm[M.posB + k * M.E1 + el] = (uint32_t)(5 * HW + pm_acell(pm_sel4(g.a, k ^ 1), W)) | (uint32_t)(5 * HW + pm_acell(pm_sel4(g.a, k ^ 3), W)) << 16;
+    sm[M.patch + k * M.E1 + el] = carry > 0 ? (own | (1u + carry) << 16) : 0xffffffffu;
 }
 
 // ============================================================================
@@ -362,6 +342,7 @@ PM_HD void pm_pack_agents(const PmAgents &g, pm_u4 &A, pm_u4 &B) {
 struct PmCtx {
     int W, H, NW, E1, ND, HW, NCAT;
     const uint32_t *walls, *dumptab;
+    const uint32_t *tail;              // the board's 8 tail words: start[4] | teams | ... (pm_format.h)
     const uint32_t *halfmask;          // the staged plane masks M6 (blue food half) | M7 (red food half), NCAT words each
     uint32_t teams;
 };
@@ -370,63 +351,88 @@ struct PmBoard {
     bool food_dirty, caps_dirty;
 };
 
+// One pacman/ghost pair on the same cell (capture.py:682-701 and :708-727): an
+// unscared ghost kills the pacman (dump, respawn), a scared ghost is sent home.
+PM_HD uint32_t pm_collide(const PmCtx &X, PmAg &g, int pacman, int ghost, uint32_t *fk, const uint32_t *ck) {
+    uint32_t added = 0;
+    if (pm_ascared(pm_sel4(g.a, ghost)) <= 0) {
+        const uint32_t ap = pm_sel4(g.a, pacman), bp = pm_sel4(g.b, pacman);
+        if (pm_bcarry(bp) > 0) {
+            const int W = X.W;
+            const uint32_t c01 = (uint32_t)pm_acell(g.a[0], W) | (uint32_t)pm_acell(g.a[1], W) << 16;
+            const uint32_t c23 = (uint32_t)pm_acell(g.a[2], W) | (uint32_t)pm_acell(g.a[3], W) << 16;
+            added = pm_dump(W, X.H, X.ND, X.dumptab, X.walls, fk, ck, X.E1, pm_ax(ap), pm_ay(ap), pm_bcarry(bp), c01, c23);
+            pm_put4(g.b, pacman, bp & 0xffff0000u);
+        }
+        pm_put4(g.a, pacman, pm_home_word(X.tail, pacman));
+    } else {
+        pm_put4(g.a, ghost, pm_home_word(X.tail, ghost));
+    }
+    return added;
+}
+
 // GameState.generateSuccessor for agent A playing the (already legalised) gym action u:
 // AgentRules.applyAction + consume + checkDeath + decrementTimer (capture.py:107-123, 468-728)
 // on agents `g` and the bitsets fk / ck (word stride X.E1).  Returns the score change.
-template <int A>
-PM_HD int pm_submove(const PmCtx &X, PmAgents &g, uint32_t *fk, uint32_t *ck, PmBoard &b, int u) {
+PM_HD int pm_submove(const PmCtx &X, PmAg &g, uint32_t *fk, uint32_t *ck, PmBoard &b, const int A, int u) {
     const int W = X.W, E1 = X.E1;
     const uint32_t teams = X.teams;
     // ---- AgentRules.applyAction (capture.py:468-517) ----
+    uint32_t aA = pm_sel4(g.a, A), bA = pm_sel4(g.b, A);
     const int dx = (u == 1) - (u == 3), dy = (u == 0) - (u == 2);
-    g.x[A] += dx; g.y[A] += dy;
-    const int c = g.y[A] * W + g.x[A];
-    if (u != 4) g.dir[A] = u;                          // Stop keeps the heading, game.py:115-117
+    const int x = pm_ax(aA) + dx, y = pm_ay(aA) + dy;
+    const int c = y * W + x;
+    const int dir = (u != 4) ? u : pm_adir(aA);        // Stop keeps the heading, game.py:115-117
     const int is_red = (teams >> A) & 1;
-    g.pac[A] = is_red ^ (2 * g.x[A] < W ? 1 : 0);
-    int pacflag = g.pac[A];
+    const int pac = is_red ^ (2 * x < W ? 1 : 0);
+    aA = pm_agA_pack(x, y, dir, pac, pm_ascared(aA));
+    pm_put4(g.a, A, aA);
+    const uint32_t posA = aA & 0xffffu;
+    int pacflag = pac;
     int sc = 0;
-    if (g.carry[A] > 0 && !g.pac[A]) {
-        sc = is_red ? g.carry[A] : -g.carry[A];
-        g.ret[A] += g.carry[A];
-        g.carry[A] = 0;
-        pacflag = g.pac[3];                            // the rebinding quirk: capture.py:505 -> :514
+    if (pm_bcarry(bA) > 0 && !pac) {
+        const int carry = pm_bcarry(bA);
+        sc = is_red ? carry : -carry;
+        pm_put4(g.b, A, (bA & 0xffff0000u) + ((uint32_t)carry << 16));     // numReturned += numCarrying; numCarrying = 0
+        pacflag = pm_apac(g.a[3]);                     // the rebinding quirk: capture.py:505 -> :514
     }
     if (pacflag) {                                     // AgentRules.consume (capture.py:519-560)
         if (pm_sbit(fk, E1, c)) {
             bool given = false;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (!given && (int)((teams >> i) & 1) == is_red && g.x[i] == g.x[A] && g.y[i] == g.y[A]) { g.carry[i] += 1; given = true; }
+                if (!given && (int)((teams >> i) & 1) == is_red && (g.a[i] & 0xffffu) == posA) { g.b[i] += 1; given = true; }
             fk[(c >> 5) * E1] &= ~(1u << (c & 31));
             b.food_dirty = true;
-            if (g.x[A] < (W >> 1)) --b.rf; else --b.bf;
+            if (x < (W >> 1)) --b.rf; else --b.bf;
         }
-        if (ck && pm_sbit(ck, E1, c) && (is_red ? (2 * g.x[A] > W) : (2 * g.x[A] <= W))) {
+        if (ck && pm_sbit(ck, E1, c) && (is_red ? (2 * x > W) : (2 * x <= W))) {
             ck[(c >> 5) * E1] &= ~(1u << (c & 31));
             b.caps_dirty = true;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) if ((int)((teams >> i) & 1) != is_red) g.scared[i] = PM_SCARED_TIME;
+            for (int i = 0; i < 4; ++i)
+                if ((int)((teams >> i) & 1) != is_red) g.a[i] = (g.a[i] & 0x000fffffu) | (uint32_t)PM_SCARED_TIME << 20;
         }
     }
     // ---- AgentRules.checkDeath (capture.py:670-728) ----
     // The branch (mover is pacman / ghost) is chosen once; enemies are then
     // visited in index order against live positions and timers.
-    const bool mover_is_pac = g.pac[A] != 0;
-#pragma unroll
+#pragma unroll 1
     for (int e = 0; e < 4; ++e) {
         if (e == A) continue;
         if ((int)((teams >> e) & 1) == is_red) continue;
-        if (g.x[e] != g.x[A] || g.y[e] != g.y[A]) continue;
+        const uint32_t ae = pm_sel4(g.a, e);
+        if ((ae & 0xffffu) != (pm_sel4(g.a, A) & 0xffffu)) continue;
         uint32_t added = 0;
-        if (mover_is_pac) {
-            if (!g.pac[e]) added = pm_collide(g, A, e, W, X.H, X.ND, X.dumptab, X.walls, fk, ck, E1);   // A = pacman, e = ghost
+        if (pac) {
+            if (!pm_apac(ae)) added = pm_collide(X, g, A, e, fk, ck);      // A = pacman, e = ghost
         } else {
-            if (g.pac[e]) added = pm_collide(g, e, A, W, X.H, X.ND, X.dumptab, X.walls, fk, ck, E1);    // e = pacman, A = ghost
+            if (pm_apac(ae)) added = pm_collide(X, g, e, A, fk, ck);       // e = pacman, A = ghost
         }
         if (added) { b.rf += (int)(added & 0xffff); b.bf += (int)(added >> 16); b.food_dirty = true; }
     }
-    g.scared[A] = g.scared[A] > 0 ? g.scared[A] - 1 : 0;      // decrementTimer, capture.py:562-567
+    aA = pm_sel4(g.a, A);                              // decrementTimer, capture.py:562-567
+    if (pm_ascared(aA) > 0) pm_put4(g.a, A, aA - (1u << 20));
     return sc;
 }
 
@@ -441,11 +447,11 @@ PM_HD int pm_maze_dist(const PmDist &D, int ca, int cb) {
 }
 
 // Q(s, a) of ReflexCaptureAgent.evaluate for the successor state (g2, fs): integer features x integer weights.
-template <int A>
-PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2, const uint32_t *fs, const PmBoard &b2,
-                            int kind, int u, int dir_before) {
+PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAg &g2, const uint32_t *fs, const PmBoard &b2,
+                            const int A, int kind, int u, int dir_before) {
     const int W = X.W, is_red = (X.teams >> A) & 1;
-    const int me = g2.y[A] * W + g2.x[A];
+    const uint32_t aA = pm_sel4(g2.a, A);
+    const int me = pm_acell(aA, W);
     if (kind == 2) {                                   // OffensiveReflexAgent.getFeatures / getWeights (:132-150)
         const int n = is_red ? b2.bf : b2.rf;          // len(self.getFood(successor).asList()): the half this team eats
         int v = -100 * n;
@@ -484,12 +490,12 @@ PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2,
         return v;
     }
     // DefensiveReflexAgent.getFeatures / getWeights (:159-187)
-    int v = g2.pac[A] ? 0 : 100;                       // onDefense
+    int v = pm_apac(aA) ? 0 : 100;                     // onDefense
     int ninv = 0, best = 0;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-        if ((int)((X.teams >> o) & 1) == is_red || !g2.pac[o]) continue;
-        const int d = pm_maze_dist(D, me, g2.y[o] * W + g2.x[o]);
+        if ((int)((X.teams >> o) & 1) == is_red || !pm_apac(g2.a[o])) continue;
+        const int d = pm_maze_dist(D, me, pm_acell(g2.a[o], W));
         if (ninv == 0 || d < best) best = d;
         ++ninv;
     }
@@ -503,46 +509,48 @@ PM_HD int pm_baseline_value(const PmCtx &X, const PmDist &D, const PmAgents &g2,
 
 // ReflexCaptureAgent.chooseAction (:65-92): evaluate every legal action on a scratch copy of the
 // state, keep the best set, break ties with `rnd` (random.choice) or take the first (test hook).
-// fs / cs: scratch bitsets (slot 4).  Returns the gym action; *best_mask = the best set.
-template <int A>
-PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAgents &g, const uint32_t *fk, const uint32_t *ck,
-                             uint32_t *fs, uint32_t *cs, const PmBoard &b, int legal, int kind, uint32_t rnd,
+// fs / cs: scratch bitsets (slot 4).  Returns the gym action.
+PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAg &g, const uint32_t *fk, const uint32_t *ck,
+                             uint32_t *fs, uint32_t *cs, const PmBoard &b, const int A, int legal, int kind, uint32_t rnd,
                              bool first_best, bool rnd_is_index) {
     // Actions.getPossibleActions: N, S, E, W, Stop (game.py:295-299) = gym ints 0, 2, 1, 3, 4, one nibble each
     const uint32_t order = 0x43120u;
     const int is_red = (X.teams >> A) & 1;
     const bool go_home = (is_red ? b.bf : b.rf) <= 0;  // foodLeft <= 0: walk towards self.start (:79-90)
-    const int start_c = g.sy[A] * X.W + g.sx[A];
-    int vals[5], bestv = -0x7fffffff, home_a = 4, home_d = 9999;
-    // NOT unrolled: one copy of the look-ahead sub-move per agent instead of five keeps the kernel's code (and the
-    // rules warp's instruction fetch) 2.5x smaller; vals[] lives in local memory
+    const uint32_t st = X.tail[PM_L_START + A];
+    const int start_c = (int)((st >> 8) & 0xff) * X.W + (int)(st & 0xff);
+    const int dir_before = pm_adir(pm_sel4(g.a, A));
+    int bestv = -0x7fffffff, home_a = 4, home_d = 9999;
+    // the values of the (up to five) candidates: 5 x 12 bits would not hold them, so two passes over the best set use
+    // a bitmask of the candidates that reached the best value so far instead of an array (no local memory)
+    uint32_t best_set = 0;
 #pragma unroll 1
     for (int k = 0; k < 5; ++k) {
         const int u = (int)((order >> (4 * k)) & 15u);
-        vals[k] = -0x7fffffff;
         if (!((legal >> u) & 1)) continue;
         for (int w = 0; w < X.NW; ++w) fs[w * X.E1] = fk[w * X.E1];
         if (ck) for (int w = 0; w < X.NW; ++w) cs[w * X.E1] = ck[w * X.E1];
-        PmAgents g2 = g;
+        PmAg g2 = g;
         PmBoard b2 = b;
-        pm_submove<A>(X, g2, fs, ck ? cs : nullptr, b2, u);
+        pm_submove(X, g2, fs, ck ? cs : nullptr, b2, A, u);
         if (go_home) {
-            const int d = pm_maze_dist(D, start_c, g2.y[A] * X.W + g2.x[A]);
+            const int d = pm_maze_dist(D, start_c, pm_acell(pm_sel4(g2.a, A), X.W));
             if (d < home_d) { home_d = d; home_a = u; }
         } else {
-            vals[k] = pm_baseline_value<A>(X, D, g2, fs, b2, kind, u, g.dir[A]);
-            bestv = vals[k] > bestv ? vals[k] : bestv;
+            const int v = pm_baseline_value(X, D, g2, fs, b2, A, kind, u, dir_before);
+            if (v > bestv) { bestv = v; best_set = 1u << k; }
+            else if (v == bestv) best_set |= 1u << k;
         }
     }
     if (go_home) return home_a;
     int nb = 0;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) nb += (vals[k] == bestv && ((legal >> ((order >> (4 * k)) & 15u)) & 1)) ? 1 : 0;
+    for (int k = 0; k < 5; ++k) nb += (int)((best_set >> k) & 1u);
     int pick = first_best ? 0 : rnd_is_index ? (int)(rnd % (unsigned)nb) : (int)(((unsigned long long)rnd * (unsigned)nb) >> 32);
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const int u = (int)((order >> (4 * k)) & 15u);
-        if (vals[k] == bestv && ((legal >> u) & 1)) { if (pick == 0) return u; --pick; }
+        if ((best_set >> k) & 1u) { if (pick == 0) return u; --pick; }
     }
     return 4;
 }
@@ -551,16 +559,17 @@ PM_HD int pm_baseline_choose(const PmCtx &X, const PmDist &D, const PmAgents &g,
 struct PmStepAcc {
     PmBoard b;
     int score, sc_total, red_sc, blue_sc;
-    double red_r, blue_r, shap[4];
+    double red_r, blue_r;
+    uint32_t shcode[4];                // pm_shaping_code of each agent's turn
     uint32_t snap[4];
     uint32_t act_used;                 // the action each agent actually played, one byte per agent
 };
 
 // One turn of gymPacMan.step's loop for agent A (gymPacMan.py:149-167): pick the action (caller's,
 // random legal, or baselineTeam), get_reward bookkeeping, the sub-move, the observation snapshot.
-template <int A, int BOTS, int VIEWS>
+template <int BOTS, int VIEWS>
 PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const PmSmem &M, int el, int64_t n, uint32_t lid,
-                         PmAgents &g, uint32_t *food, uint32_t *caps, PmStepAcc &S, uint32_t act4, int steps,
+                         PmAg &g, uint32_t *food, uint32_t *caps, PmStepAcc &S, const int A, uint32_t act4, int steps,
                          uint32_t episode) {
     const int NW = X.NW, E1 = X.E1, W = X.W;
     uint32_t *fk = food + (size_t)A * NW * E1;
@@ -573,9 +582,9 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
     const bool gym_red = (A & 1) == 0;
     const int o1 = gym_red ? 1 : 0, o2 = o1 + 2;
     const int mine_before = gym_red ? S.b.rf : S.b.bf, theirs_before = gym_red ? S.b.bf : S.b.rf;
-    const int pb1 = g.pac[o1], pb2 = g.pac[o2];
+    const int pb1 = pm_apac(gym_red ? g.a[1] : g.a[0]), pb2 = pm_apac(gym_red ? g.a[3] : g.a[2]);
 
-    const int legal = pm_legal_mask(X.walls, W, g.y[A] * W + g.x[A]);
+    const int legal = pm_legal_mask(X.walls, W, pm_acell(pm_sel4(g.a, A), W));
     int u = (act4 >> (8 * A)) & 0xff;
     const int kind = (P.bot_kind >> (4 * A)) & 15;
     const bool ext_draw = P.bot_draws != nullptr;
@@ -595,14 +604,14 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
         }
         const uint32_t rnd = ext_draw ? P.bot_draws[4 * n + A]
                                       : pm_random_u32(P.bot_seed, (unsigned long long)(P.n_base + n), episode, (unsigned)steps * 4u + A);
-        u = pm_baseline_choose<A>(X, D, g, fk, ck, food + (size_t)4 * NW * E1, caps ? caps + (size_t)4 * NW * E1 : nullptr,
-                                  S.b, legal, kind, rnd, P.bot_first_best != 0, ext_draw);
+        u = pm_baseline_choose(X, D, g, fk, ck, food + (size_t)4 * NW * E1, caps ? caps + (size_t)4 * NW * E1 : nullptr,
+                               S.b, A, legal, kind, rnd, P.bot_first_best != 0, ext_draw);
     }
     const bool req_legal = u <= 4 && ((legal >> u) & 1);
     if (!req_legal) u = 4;                             // illegal -> Stop, capture.py:472-475
     S.act_used |= (uint32_t)u << (8 * A);
 
-    const int sc = pm_submove<A>(X, g, fk, ck, S.b, u);
+    const int sc = pm_submove(X, g, fk, ck, S.b, A, u);
     S.score += sc;
     S.sc_total += sc;
     if (gym_red) S.red_sc += sc; else S.blue_sc -= sc;
@@ -612,9 +621,10 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
     const int mine_after = gym_red ? S.b.rf : S.b.bf, theirs_after = gym_red ? S.b.bf : S.b.rf;
     if (mine_before < mine_after) r = pm_dadd(r, 1.0);
     if (theirs_before > theirs_after) r = pm_dadd(r, 0.1);
-    if (P.defence) {
-        if (pb1 && !g.pac[o1] && g.x[o1] == g.sx[o1] && g.y[o1] == g.sy[o1]) r = pm_dadd(r, 0.25);
-        if (pb2 && !g.pac[o2] && g.x[o2] == g.sx[o2] && g.y[o2] == g.sy[o2]) r = pm_dadd(r, 0.25);
+    if (P.defence) {                                   // an enemy pacman is back on its start cell as a ghost
+        const uint32_t a1 = gym_red ? g.a[1] : g.a[0], a2 = gym_red ? g.a[3] : g.a[2];
+        if (pb1 && !pm_apac(a1) && (a1 & 0xffffu) == (X.tail[PM_L_START + o1] & 0xffffu)) r = pm_dadd(r, 0.25);
+        if (pb2 && !pm_apac(a2) && (a2 & 0xffffu) == (X.tail[PM_L_START + o2] & 0xffffu)) r = pm_dadd(r, 0.25);
     }
     if (P.reward_legal && req_legal) r = pm_dadd(r, 0.01);
     if (gym_red) S.red_r = r; else S.blue_r = r;
@@ -626,8 +636,9 @@ PM_HD void pm_agent_turn(const PmParams &P, const PmCtx &X, uint32_t *sm, const 
         pm_mirror_bits(fk, food + (size_t)ms * NW * E1, E1, W, X.H, NW);
         if (ck) pm_mirror_bits(ck, caps + (size_t)ms * NW * E1, E1, W, X.H, NW);
     }
-    S.shap[A] = pm_shaping((int)(S.snap[A] & 0xff), (int)((S.snap[A] >> 8) & 0xff), (int)(S.snap[A] >> 16), g.x[A], g.y[A]);
-    S.snap[A] = (uint32_t)g.x[A] | (uint32_t)g.y[A] << 8 | (uint32_t)g.carry[A] << 16;
+    const uint32_t prev = pm_sel4(S.snap, A), aA = pm_sel4(g.a, A);
+    pm_put4(S.shcode, A, pm_shaping_code((int)(prev & 0xff), (int)((prev >> 8) & 0xff), (int)(prev >> 16), pm_ax(aA), pm_ay(aA)));
+    pm_put4(S.snap, A, (aA & 0xffffu) | (uint32_t)pm_bcarry(pm_sel4(g.b, A)) << 16);
 }
 
 template <int BOTS, int VIEWS>
@@ -643,7 +654,7 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     const int64_t NP = pm_np(P.N);
     PmCtx X;
     X.W = W; X.H = P.H; X.NW = NW; X.E1 = E1; X.ND = P.ND; X.HW = P.HW; X.NCAT = P.NCAT;
-    X.walls = walls; X.dumptab = P.geom + pm_g_dump_off(P.HW); X.teams = tail[PM_L_TEAMS];
+    X.walls = walls; X.dumptab = P.geom + pm_g_dump_off(P.HW); X.tail = tail; X.teams = tail[PM_L_TEAMS];
     X.halfmask = st + M.masks + 2 * P.NCAT;
 
     // ---- load state (128-bit loads, coalesced across the env dimension) ----
@@ -660,8 +671,9 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     for (int w = 0; w < NW; ++w) food[(s0 * NW + w) * E1] = gfood[(size_t)w * NP + n];
     if (caps) for (int w = 0; w < NW; ++w) caps[(s0 * NW + w) * E1] = gcaps[(size_t)w * NP + n];
 
-    PmAgents g;
-    pm_unpack_agents(g, A, B, tail);
+    PmAg g;
+    g.a[0] = A.x; g.a[1] = A.y; g.a[2] = A.z; g.a[3] = A.w;
+    g.b[0] = B.x; g.b[1] = B.y; g.b[2] = B.z; g.b[3] = B.w;
     int steps = (int)Mi.y;
     uint32_t episode = Mi.w;                                      // restarts of this env (keys the random draws)
     PmStepAcc S;
@@ -672,13 +684,12 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     S.snap[0] = Sn.x; S.snap[1] = Sn.y; S.snap[2] = Sn.z; S.snap[3] = Sn.w;
     pm_u4 *gacc = reinterpret_cast<pm_u4 *>(P.state + pm_st_acc(P.N, P.HW));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) S.shap[i] = 0.0;
+    for (int i = 0; i < 4; ++i) S.shcode[i] = PM_SHAPE_NONE;
     if (P.a0 > 0) {                                    // continue a step that earlier launches started
-        const pm_u4 c0 = gacc[n], c1 = gacc[NP + n], c2 = gacc[2 * NP + n], c3 = gacc[3 * NP + n];
+        const pm_u4 c0 = gacc[n], c1 = gacc[NP + n], c2 = gacc[2 * NP + n];
         S.red_r = pm_dfrom(c0.x, c0.y); S.blue_r = pm_dfrom(c0.z, c0.w);
         S.sc_total = (int)c1.x; S.red_sc = (int)c1.y; S.blue_sc = (int)c1.z; S.act_used = c1.w;
-        S.shap[0] = pm_dfrom(c2.x, c2.y); S.shap[1] = pm_dfrom(c2.z, c2.w);
-        S.shap[2] = pm_dfrom(c3.x, c3.y); S.shap[3] = pm_dfrom(c3.z, c3.w);
+        S.shcode[0] = c2.x; S.shcode[1] = c2.y; S.shcode[2] = c2.z; S.shcode[3] = c2.w;
     }
 
     uint32_t act4;
@@ -690,25 +701,22 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         for (int i = 0; i < 4; ++i) { long long v = a8[i]; act4 |= (uint32_t)((v < 0 || v > 4) ? 255 : (int)v) << (8 * i); }
     }
 
-    if (P.a0 <= 0 && 0 < P.a1) pm_agent_turn<0, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    if (P.a0 <= 1 && 1 < P.a1) pm_agent_turn<1, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    if (P.a0 <= 2 && 2 < P.a1) pm_agent_turn<2, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
-    if (P.a0 <= 3 && 3 < P.a1) pm_agent_turn<3, BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, act4, steps, episode);
+    // the (up to) four ordered sub-moves of the step: ONE copy of the turn's code, the mover is a run-time index
+#pragma unroll 1
+    for (int k = P.a0; k < P.a1; ++k) pm_agent_turn<BOTS, VIEWS>(P, X, sm, M, el, n, lid, g, food, caps, S, k, act4, steps, episode);
 
     if (P.a1 < 4) {
         // ---- the step continues in a later launch (a CPU bot decides the next sub-move from the state as it is
         // now, gymPacMan.py:157): park the accumulators and the state; no epilogue, no step outputs ----
-        pm_u4 c0, c1, c2, c3;
+        pm_u4 c0, c1, c2;
         uint64_t u;
         u = pm_dbits(S.red_r); c0.x = (uint32_t)u; c0.y = (uint32_t)(u >> 32);
         u = pm_dbits(S.blue_r); c0.z = (uint32_t)u; c0.w = (uint32_t)(u >> 32);
         c1.x = (uint32_t)S.sc_total; c1.y = (uint32_t)S.red_sc; c1.z = (uint32_t)S.blue_sc; c1.w = S.act_used;
-        u = pm_dbits(S.shap[0]); c2.x = (uint32_t)u; c2.y = (uint32_t)(u >> 32);
-        u = pm_dbits(S.shap[1]); c2.z = (uint32_t)u; c2.w = (uint32_t)(u >> 32);
-        u = pm_dbits(S.shap[2]); c3.x = (uint32_t)u; c3.y = (uint32_t)(u >> 32);
-        u = pm_dbits(S.shap[3]); c3.z = (uint32_t)u; c3.w = (uint32_t)(u >> 32);
-        gacc[n] = c0; gacc[NP + n] = c1; gacc[2 * NP + n] = c2; gacc[3 * NP + n] = c3;
-        pm_pack_agents(g, A, B);
+        c2.x = S.shcode[0]; c2.y = S.shcode[1]; c2.z = S.shcode[2]; c2.w = S.shcode[3];
+        gacc[n] = c0; gacc[NP + n] = c1; gacc[2 * NP + n] = c2;
+        A.x = g.a[0]; A.y = g.a[1]; A.z = g.a[2]; A.w = g.a[3];
+        B.x = g.b[0]; B.y = g.b[1]; B.z = g.b[2]; B.w = g.b[3];
         reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
         reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
         Sn.x = S.snap[0]; Sn.y = S.snap[1]; Sn.z = S.snap[2]; Sn.w = S.snap[3];
@@ -727,14 +735,13 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     double red_r = S.red_r, blue_r = S.blue_r;
     bool food_dirty = S.b.food_dirty, caps_dirty = S.b.caps_dirty;
     uint32_t *snap = S.snap;
-    const double *shap = S.shap;
 
     // ---- step epilogue (gymPacMan.py:171-193) ----
     blue_r = pm_dadd(blue_r, (double)(S.blue_sc > 0 ? S.blue_sc : 0));
     red_r = pm_dadd(red_r, (double)(S.red_sc > 0 ? S.red_sc : 0));
     bool term = false;
-    if (bf == 0 && g.carry[0] == 0 && g.carry[2] == 0) term = true;      // check_termination, :261-270
-    if (rf == 0 && g.carry[1] == 0 && g.carry[3] == 0) term = true;
+    if (bf == 0 && pm_bcarry(g.b[0]) == 0 && pm_bcarry(g.b[2]) == 0) term = true;      // check_termination, :261-270
+    if (rf == 0 && pm_bcarry(g.b[1]) == 0 && pm_bcarry(g.b[3]) == 0) term = true;
     if (steps >= P.length) term = true;
     if (term) {
         const double bonus = pm_dadd(20.0, pm_dmul(1.0 / 5, (double)(score < 0 ? -score : score)));
@@ -760,9 +767,8 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t s0 = tail[PM_L_START + i];
-            g.sx[i] = s0 & 0xff; g.sy[i] = (s0 >> 8) & 0xff;
-            g.x[i] = g.sx[i]; g.y[i] = g.sy[i]; g.dir[i] = 4; g.pac[i] = (s0 >> 16) & 1; g.scared[i] = 0;
-            g.carry[i] = 0; g.ret[i] = 0;
+            g.a[i] = pm_agA_pack((int)(s0 & 0xff), (int)((s0 >> 8) & 0xff), 4, (int)((s0 >> 16) & 1), 0);
+            g.b[i] = 0;
             snap[i] = s0 & 0xffff;
         }
         score = 0; steps = 0;
@@ -795,15 +801,16 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
     uint32_t lm = 0;
     if (P.legal || P.packed) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, g.y[i] * W + g.x[i]) << (8 * i);
+        for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, pm_acell(g.a[i], W)) << (8 * i);
         if (P.legal) reinterpret_cast<uint32_t *>(P.legal)[n] = lm;
     }
     float shaped[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const double team = (i & 1) ? blue_r : red_r;          // sum over both learners = 2 * team reward
-        shaped[i] = (float)pm_dadd(pm_dadd(team, team), pm_dmul(P.shaping_scale, shap[i]));
-        if (P.shaping) P.shaping[(size_t)i * P.N + n] = shap[i];
+        const double shap = pm_shaping_value(S.shcode[i]);
+        shaped[i] = (float)pm_dadd(pm_dadd(team, team), pm_dmul(P.shaping_scale, shap));
+        if (P.shaping) P.shaping[(size_t)i * P.N + n] = shap;
         if (P.shaped) P.shaped[(size_t)i * P.N + n] = shaped[i];
     }
     if (P.act_used) reinterpret_cast<uint32_t *>(P.act_used)[n] = S.act_used;
@@ -817,7 +824,8 @@ PM_HD void pm_phaseA_step(const PmParams &P, const uint32_t *st, uint32_t *sm, c
         rec[0] = r0; rec[1] = r1; rec[2] = r2;
     }
     // ---- state write-back ----
-    pm_pack_agents(g, A, B);
+    A.x = g.a[0]; A.y = g.a[1]; A.z = g.a[2]; A.w = g.a[3];
+    B.x = g.b[0]; B.y = g.b[1]; B.z = g.b[2]; B.w = g.b[3];
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agA(P.N))[n] = A;
     reinterpret_cast<pm_u4 *>(P.state + pm_st_agB(P.N))[n] = B;
     Sn.x = snap[0]; Sn.y = snap[1]; Sn.z = snap[2]; Sn.w = snap[3];
@@ -854,7 +862,7 @@ PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm,
     uint32_t *gcaps = reinterpret_cast<uint32_t *>(P.state + pm_st_caps(P.N, P.HW));
     uint32_t *food = sm + M.food + el;
     uint32_t *caps = P.has_caps ? sm + M.caps + el : nullptr;
-    PmAgents g;
+    PmAg g;
     if (MODE == PM_MODE_RESET) {
         // CaptureRules.newGame -> GameState.initialize (capture.py:369-382,311-323; game.py:490-508)
         pm_u4 A, B, S, Mi;
@@ -880,13 +888,15 @@ PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm,
             gcaps[(size_t)w * NP + n] = cp;
             if (caps) caps[w * E1] = cp;
         }
-        pm_unpack_agents(g, A, B, tail);
+        g.a[0] = A.x; g.a[1] = A.y; g.a[2] = A.z; g.a[3] = A.w;
+        g.b[0] = B.x; g.b[1] = B.y; g.b[2] = B.z; g.b[3] = B.w;
     } else {
         pm_u4 A = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agA(P.N))[n];
         pm_u4 B = reinterpret_cast<const pm_u4 *>(P.state + pm_st_agB(P.N))[n];
         for (int w = 0; w < NW; ++w) food[w * E1] = gfood[(size_t)w * NP + n];
         if (caps) for (int w = 0; w < NW; ++w) caps[w * E1] = gcaps[(size_t)w * NP + n];
-        pm_unpack_agents(g, A, B, tail);
+        g.a[0] = A.x; g.a[1] = A.y; g.a[2] = A.z; g.a[3] = A.w;
+        g.b[0] = B.x; g.b[1] = B.y; g.b[2] = B.z; g.b[3] = B.w;
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) pm_store_snapshot(sm, M, P, k, el, g);
@@ -900,7 +910,7 @@ PM_HD void pm_phaseA_static(const PmParams &P, const uint32_t *st, uint32_t *sm,
         const uint32_t *walls = lay + pm_l_walls(P.HW);
         uint32_t lm = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, g.y[i] * W + g.x[i]) << (8 * i);
+        for (int i = 0; i < 4; ++i) lm |= (uint32_t)pm_legal_mask(walls, W, pm_acell(g.a[i], W)) << (8 * i);
         reinterpret_cast<uint32_t *>(P.legal)[n] = lm;
     }
 }
