@@ -355,6 +355,18 @@ int pm_adam_ema(float *params, const float *grads, float *exp_avg, float *exp_av
                 double lr, double beta1, double beta2, double eps, double max_grad_norm, double grad_scale,
                 double ema_decay, float *grad_norm_out, void *scratch, pm_stream_t stream);
 
+/* ---- ABI 8: the critic's attention core ----
+ * softmax(Q K^T / sqrt(8)) V of nn.MultiheadAttention inside the reference's centralised critic
+ * (nn.TransformerEncoder(d_model 32, nhead 4) over one token per board cell, pacman_mappo_resnet.py:131-136,
+ * 168-176) and its gradient, for heads of dimension 8 and S <= 1024 tokens, plain fp32.  Layouts are
+ * nn.MultiheadAttention's (batch_first = False):
+ *   qkv [dev] [S][B][3E] = in_proj(x), E = 8*n_heads (q | k | v along the last axis)
+ *   out [dev] [S][B][E]  concatenated heads (input of out_proj);  lse [dev] [B][n_heads][S] log-sum-exp per row
+ *   (forward: may be NULL when no backward pass follows);  dout like out, dqkv like qkv.  16-byte aligned. */
+int pm_attn_fwd(const float *qkv, float *out, float *lse, int S, int64_t B, int n_heads, pm_stream_t stream);
+int pm_attn_bwd(const float *qkv, const float *out, const float *dout, const float *lse, float *dqkv, int S, int64_t B,
+                int n_heads, pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ EXPORTS = [
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
     "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
     "pm_obs_bits_words", "pm_observe_bits",
-    "pm_chain_scratch_bytes", "pm_step_chain",
+    "pm_chain_scratch_bytes", "pm_step_chain", "pm_attn_fwd", "pm_attn_bwd",
     "pm_make_observation", "pm_gather_rows", "pm_ppo_scratch_bytes", "pm_ppo_loss", "pm_adam_scratch_bytes", "pm_adam_ema",
 ]
 
@@ -153,6 +153,10 @@ def load():
     L.pm_adam_scratch_bytes.restype = C.c_size_t
     L.pm_adam_ema.restype = i32
     L.pm_adam_ema.argtypes = [vp, vp, vp, vp, vp, i64, i64] + [C.c_double] * 7 + [vp, vp, vp]
+    L.pm_attn_fwd.restype = i32
+    L.pm_attn_fwd.argtypes = [vp, vp, vp, i32, i64, i32, vp]
+    L.pm_attn_bwd.restype = i32
+    L.pm_attn_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, vp]
     if L.pm_abi_version() != ABI_VERSION:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L

@@ -137,6 +137,50 @@ def ppo_loss(logits, values, actions, old_logp, norm_adv, returns, clip_eps, vf_
     return _PPOLoss.apply(logits, values, actions, old_logp, norm_adv, returns, clip_eps, vf_coef, ent_coef)
 
 
+class _Attention8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, n_heads):
+        L = _lib.load()
+        dev = qkv.device
+        x = qkv.contiguous().float()
+        S, B, E3 = x.shape
+        out = torch.empty((S, B, E3 // 3), dtype=torch.float32, device=dev)
+        need_grad = qkv.requires_grad
+        lse = torch.empty((B, n_heads, S), dtype=torch.float32, device=dev) if need_grad else None
+        with torch.cuda.device(dev):
+            _lib.check(L.pm_attn_fwd(x.data_ptr(), out.data_ptr(), lse.data_ptr() if need_grad else None, S, B, n_heads,
+                                     _stream(dev)), "pm_attn_fwd")
+        if need_grad:
+            ctx.save_for_backward(x, out, lse)
+        ctx.n_heads, ctx.in_dtype = n_heads, qkv.dtype
+        return out.to(qkv.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, out, lse = ctx.saved_tensors
+        L = _lib.load()
+        dev = x.device
+        S, B, _ = x.shape
+        g = g.contiguous().float()
+        dqkv = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            _lib.check(L.pm_attn_bwd(x.data_ptr(), out.data_ptr(), g.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), S, B,
+                                     ctx.n_heads, _stream(dev)), "pm_attn_bwd")
+        return dqkv.to(ctx.in_dtype), None
+
+
+def attention_hd8(qkv: torch.Tensor, n_heads: int) -> torch.Tensor:
+    """The attention core of ``nn.MultiheadAttention`` for heads of dimension 8 (the reference critic's
+    ``nn.TransformerEncoder(d_model 32, nhead 4)``, `pacman_mappo_resnet.py:131-136`): ``qkv`` [S, B, 3E] =
+    ``in_proj(x)`` -> concatenated heads [S, B, E] = softmax(q k^T / sqrt(8)) v, differentiable (kernels pm_attn_fwd /
+    pm_attn_bwd, plain fp32).  No [B*heads, S, S] tensor is ever materialised."""
+    if not qkv.is_cuda:
+        raise RuntimeError("attention_hd8 expects CUDA tensors; there is no CPU fallback")
+    if qkv.dim() != 3 or qkv.shape[2] != 24 * n_heads or qkv.shape[0] > 1024:
+        raise ValueError("attention_hd8: qkv must be [S <= 1024, B, 3 * 8 * n_heads]")
+    return _Attention8.apply(qkv, n_heads)
+
+
 class FlatAdamEMA:
     """``clip_grad_norm_`` + ``Adam.step`` + the EMA copy of the policy (`pacman_mappo_resnet.py:588-595`) as two
     kernels over flat buffers.  The module's parameters (and the EMA module's) are re-pointed to views of one flat

@@ -153,20 +153,28 @@ class MAPPOAgent(nn.Module):
     #             With 4 heads of dimension 8 over H*W tokens, PyTorch's fused fp32 attention kernels
     #             (mem-efficient fmha) spend 22 ms per layer on a 4 096-sample minibatch, most of a PPO update;
     #             batched TF32 GEMMs + one softmax do the same arithmetic in a fraction of that.
-    #   "auto"    "bmm" in fp32 / TF32, "module" under bf16 autocast (there PyTorch's flash kernel wins: B200, 4 096-sample
-    #             minibatch, fwd+bwd of the whole critic: fp32 36.7 ms module vs 27.8 ms bmm; bf16 14.4 ms vs 29.5 ms)
+    #   "kernel"  the same layer with the attention core (softmax(q k^T / sqrt(8)) v and its gradient) in the library's
+    #             own kernels (mappo_ops.attention_hd8: one CTA per (sample, head), K / V in shared memory, plain
+    #             fp32, nothing S x S materialised)
+    #   "auto"    "module" under bf16 autocast (PyTorch's bf16 flash kernel), otherwise "kernel" when the heads have
+    #             dimension 8, else "bmm".  B200, smallCapture, 4 096-sample minibatch, fwd+bwd of the whole critic:
+    #             fp32 36.5 ms module / 27.9 ms bmm / 16.1 ms kernel; bf16 autocast 14.5 / 29.6 / 15.2 ms
     attn_impl = "auto"
 
-    def _encoder_layer_bmm(self, layer, x):
+    def _encoder_layer_bmm(self, layer, x, kernel=False):
         """One nn.TransformerEncoderLayer (norm_first=False, relu, dropout 0) on x [S, B, E] with explicit ops."""
         sa = layer.self_attn
         S, B, E = x.shape
         h = sa.num_heads
         hd = E // h
         qkv = nn.functional.linear(x, sa.in_proj_weight, sa.in_proj_bias)             # [S, B, 3E]
-        q, k, v = (t.reshape(S, B * h, hd).transpose(0, 1) for t in qkv.chunk(3, dim=-1))   # [B*h, S, hd]
-        p = torch.softmax(torch.bmm(q * (1.0 / math.sqrt(hd)), k.transpose(1, 2)), dim=-1)
-        o = torch.bmm(p, v).transpose(0, 1).reshape(S, B, E)
+        if kernel:
+            from .mappo_ops import attention_hd8
+            o = attention_hd8(qkv, h)
+        else:
+            q, k, v = (t.reshape(S, B * h, hd).transpose(0, 1) for t in qkv.chunk(3, dim=-1))   # [B*h, S, hd]
+            p = torch.softmax(torch.bmm(q * (1.0 / math.sqrt(hd)), k.transpose(1, 2)), dim=-1)
+            o = torch.bmm(p, v).transpose(0, 1).reshape(S, B, E)
         x = layer.norm1(x + sa.out_proj(o))
         return layer.norm2(x + layer.linear2(nn.functional.relu(layer.linear1(x))))
 
@@ -175,10 +183,16 @@ class MAPPOAgent(nn.Module):
         x = x.flatten(2).permute(2, 0, 1)                                  # [H*W tokens, B, d]
         impl = self.attn_impl
         if impl == "auto":
-            impl = "module" if torch.is_autocast_enabled("cuda") else "bmm"
-        if impl == "bmm":
+            sa = self.critic_transformer.layers[0].self_attn
+            if torch.is_autocast_enabled("cuda"):
+                impl = "module"
+            elif x.is_cuda and sa.embed_dim // sa.num_heads == 8 and x.shape[0] <= 1024:
+                impl = "kernel"
+            else:
+                impl = "bmm"
+        if impl in ("bmm", "kernel"):
             for layer in self.critic_transformer.layers:
-                x = self._encoder_layer_bmm(layer, x)
+                x = self._encoder_layer_bmm(layer, x, kernel=impl == "kernel")
         else:
             x = self.critic_transformer(x)
         return self.critic_head(x.mean(dim=0))

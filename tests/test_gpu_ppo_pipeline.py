@@ -164,3 +164,53 @@ def test_trainer_rollout_against_the_references_cpu_bots():
     assert bool(torch.isfinite(ro.reward).all()) and bool(((ro.obs[:, :, :, 1] > 0).sum((-1, -2)) == 1).all())
     losses = tr.update(lv, tr.schedule(1))
     assert all(np.isfinite(float(v)) for v in losses.values())
+
+
+@pytest.mark.parametrize("S,B,h", [(154, 64, 4), (140, 33, 4), (1, 5, 2), (400, 7, 4), (1024, 2, 1), (33, 1, 8)])
+def test_attention_kernels_match_multihead_attention_math(S, B, h):
+    """pm_attn_fwd / pm_attn_bwd == softmax(q k^T / sqrt(8)) v of nn.MultiheadAttention (the reference critic's
+    nn.TransformerEncoder, `pacman_mappo_resnet.py:131-136`), forward and gradient, against an fp64 evaluation of the
+    same formula; 1e-5 relative (of the tensor's scale)."""
+    from pacman_marl_2025_b200.mappo_ops import attention_hd8
+    g = torch.Generator(device="cuda").manual_seed(S * 131 + B)
+    E = 8 * h
+    qkv = (torch.randn((S, B, 3 * E), generator=g, device="cuda") * 1.7).requires_grad_(True)
+    dout = torch.randn((S, B, E), generator=g, device="cuda")
+    out = attention_hd8(qkv, h)
+    out.backward(dout)
+
+    x = qkv.detach().double().requires_grad_(True)
+    q, k, v = (t.reshape(S, B * h, 8).transpose(0, 1) for t in x.chunk(3, dim=-1))
+    p = torch.softmax(torch.bmm(q / np.sqrt(8.0), k.transpose(1, 2)), dim=-1)
+    ref = torch.bmm(p, v).transpose(0, 1).reshape(S, B, E)
+    ref.backward(dout.double())
+    tol = lambda t: 1e-5 * float(t.abs().max())
+    assert float((out.double() - ref).abs().max()) <= tol(ref)
+    assert float((qkv.grad.double() - x.grad).abs().max()) <= tol(x.grad)
+
+
+def test_critic_with_attention_kernel_equals_the_module_path():
+    """MAPPOAgent.get_value with attn_impl 'kernel' == nn.TransformerEncoder.forward (the reference's call) in fp32:
+    values and every parameter gradient."""
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(5)
+        agent = M.MAPPOAgent((8, 11, 14), 5, 2).cuda()
+        x = (torch.rand(96, 8, 11, 14, device="cuda") < 0.2).float()
+        res = {}
+        for impl in ("module", "kernel"):
+            agent.attn_impl = impl
+            agent.zero_grad(set_to_none=True)
+            v = agent.get_value(x)
+            (v * torch.linspace(-1, 1, 96, device="cuda")).sum().backward()
+            res[impl] = (v.detach().clone(), {n: p.grad.clone() for n, p in agent.named_parameters() if p.grad is not None})
+        np.testing.assert_allclose(res["kernel"][0].cpu().numpy(), res["module"][0].cpu().numpy(), rtol=2e-4, atol=2e-5)
+        assert res["kernel"][1].keys() == res["module"][1].keys() and len(res["kernel"][1]) > 10
+        for n, gm in res["module"][1].items():
+            gk = res["kernel"][1][n]
+            assert float((gk - gm).abs().max()) <= 2e-4 * float(gm.abs().max()) + 1e-6, n
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        M.MAPPOAgent.attn_impl = "auto"

@@ -10,7 +10,7 @@ for (H, W), B in (((11, 14), 4096), ((7, 20), 4096), ((20, 20), 1024)):
     agent = M.MAPPOAgent((8, H, W), 5, 2).cuda()
     x = (torch.rand(B, 8, H, W, device="cuda") < 0.2).float()
     for amp in (False, True):
-        for impl in ("module", "bmm"):
+        for impl in ("module", "bmm", "kernel"):
             agent.attn_impl = impl
             def it():
                 agent.zero_grad(set_to_none=True)

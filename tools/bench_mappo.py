@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--pair", type=int, default=1)
     ap.add_argument("--views", type=int, default=1)
     ap.add_argument("--fused", type=int, default=1, help="row-f3 kernels (gather, fused loss, Adam+EMA) vs eager ops")
-    ap.add_argument("--attn", default="bmm", help="critic attention: bmm (written out) or module (nn.TransformerEncoder)")
+    ap.add_argument("--attn", default="bmm", help="critic attention: auto, kernel (pm_attn), bmm (written out) or module (nn.TransformerEncoder)")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
