@@ -528,6 +528,17 @@ def main():
 
         KE = min(K, 200)
         e2e_ms, e2e_wall_ms = e2e_loop(host_step, KE)
+        # the same traffic as chained runs: the actions of CHAIN steps are in pinned host memory before the call, the
+        # per-step records are in pinned host memory when it returns (one synchronise per run instead of one per step)
+        acts_host_chain = acts.cpu().pin_memory()
+        env.step_chain_host_mapped(acts_host_chain)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, KE // CHAIN)):
+            env.step_chain_host_mapped(acts_host_chain)
+        e2e_chain_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        e2e_chain_steps = max(1, KE // CHAIN) * CHAIN
+        barrier()
         # the unpipelined entry (pm_step_host: one launch, six separate copies) for comparison
         plain_ms, _ = e2e_loop(lambda a: env.step_host(a), 50)
         e2e_plain = 4.0 * N * 50 * world / (plain_ms * 1e-3)
@@ -586,6 +597,11 @@ def main():
                         "observations stay in HBM for a policy net on the same GPU.  e2e_bits / e2e_views / e2e_obs are the "
                         "same call with the observations ALSO delivered to the host in three formats",
                 "unpipelined_pm_step_host_agent_steps_per_s": e2e_plain},
+        "e2e_chain": {"value": rate(e2e_chain_ms, e2e_chain_steps), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                      "d2h_bytes_per_step": d2h, "steps": e2e_chain_steps,
+                      "note": f"pm_step_chain_host_mapped: runs of {CHAIN} steps, every step reads its actions from and writes "
+                              "its records to pinned host memory across PCIe; host wall clock around host-synchronous calls "
+                              "(one synchronise per run).  For loops whose actions do not depend on the observations"},
         "e2e_bits": {"value": rate(bits_ms, KB), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                      "d2h_bytes_per_step": d2h + 4 * N * NB * 4, "steps": KB,
                      "zero_copy_agent_steps_per_s": rate(bits_mapped_ms, KB), "memcpy_agent_steps_per_s": rate(bits_copy_ms, KB),

@@ -231,6 +231,14 @@ size_t pm_chain_scratch_bytes(int64_t n_envs);
 int pm_step_chain(const pm_env_desc *d, const void *actions, int action_itemsize, int64_t actions_step_stride,
                   int n_steps, const pm_step_out *outs, int n_outs, void *scratch, pm_stream_t stream);
 
+/* pm_step_chain with HOST buffers and no copy engine (see pm_step_host_mapped): step t reads its actions from
+ * actions_pinned[t] ([n_steps][N][4] uint8) and writes its records to records_pinned[t] ([n_steps][N]
+ * pm_host_record), both page-locked, straight across PCIe from inside the kernel.  out_dev->packed is ignored;
+ * the other non-NULL members of out_dev stay in device memory and are written by every step.  Asynchronous: the
+ * records are complete once the caller has synchronised `stream`.                                             */
+int pm_step_chain_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, int n_steps, const pm_step_out *out_dev,
+                              struct pm_host_record *records_pinned, void *scratch, pm_stream_t stream);
+
 /* get_Observation(agentIndex) on the CURRENT state (gymPacMan.py:195-229) for
  * all four agents of every env. */
 int pm_observe(const pm_env_desc *d, float *obs, int64_t obs_agent_stride, pm_stream_t stream);

@@ -24,7 +24,7 @@ EXPORTS = [
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
     "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
     "pm_obs_bits_words", "pm_observe_bits",
-    "pm_chain_scratch_bytes", "pm_step_chain", "pm_attn_fwd", "pm_attn_bwd",
+    "pm_chain_scratch_bytes", "pm_step_chain", "pm_step_chain_host_mapped", "pm_attn_fwd", "pm_attn_bwd",
     "pm_make_observation", "pm_gather_rows", "pm_ppo_scratch_bytes", "pm_ppo_loss", "pm_adam_scratch_bytes", "pm_adam_ema",
 ]
 
@@ -115,6 +115,8 @@ def load():
     L.pm_chain_scratch_bytes.argtypes = [i64]
     L.pm_step_chain.restype = i32
     L.pm_step_chain.argtypes = [C.POINTER(PmEnvDesc), vp, i32, i64, i32, C.POINTER(PmStepOut), i32, vp, vp]
+    L.pm_step_chain_host_mapped.restype = i32
+    L.pm_step_chain_host_mapped.argtypes = [C.POINTER(PmEnvDesc), vp, i32, C.POINTER(PmStepOut), vp, vp, vp]
     L.pm_observe.restype = i32
     L.pm_observe.argtypes = [C.POINTER(PmEnvDesc), vp, i64, vp]
     L.pm_observe_bits.restype = i32

@@ -20,6 +20,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <new>
 
 #include "../../include/pacman_b200.h"
 #include "pm_env_core.cuh"
@@ -122,7 +123,11 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
         for (int t = tid; t < 3 * E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
     // ---- phase B: observations, one warp per (env, agent) ----
     if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
-    // ---- phase B': learner views, one warp per (env, view) ----
+    // ---- phase B': learner views: one record per (env, view) unit, then one (unit, word) item per lane ----
+    if (VIEWS && P.view_actor != nullptr) {
+        for (int u = tid; u < 3 * E; u += PM_THREADS) pm_views_prep<MODE>(P, sm, M, u, 4 + BOTS);
+        __syncthreads();
+    }
     if (VIEWS && P.view_actor != nullptr) pm_phaseB_views<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0, 4 + BOTS);
     // ---- phase B'': packed observations for a host-side consumer ----
     if (P.obs_bits != nullptr) pm_phaseB_bits<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
@@ -550,6 +555,26 @@ extern "C" int pm_step_host_mapped_async(const pm_env_desc *d, const uint8_t *ac
             cudaGetLastError();
     }
     return pm_step(d, a_dev, 1, &o, stream);
+}
+
+// ---- a run of steps fed from / delivered to pinned host memory ----------------------------------------
+extern "C" int pm_step_chain_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, int n_steps, const pm_step_out *od,
+                                         pm_host_record *records_pinned, void *scratch, pm_stream_t stream) {
+    if (!d || !actions_pinned || !od || !records_pinned || n_steps < 1 || n_steps > 65536) return PM_EINVAL;
+    void *a_dev = nullptr, *r_dev = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&a_dev, (void *)actions_pinned, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return PM_EINVAL; }        // not pinned / not mapped
+    e = cudaHostGetDevicePointer(&r_dev, (void *)records_pinned, 0);
+    if (e != cudaSuccess) { cudaGetLastError(); return PM_EINVAL; }
+    pm_step_out *outs = new (std::nothrow) pm_step_out[n_steps];
+    if (!outs) return PM_EINVAL;
+    for (int t = 0; t < n_steps; ++t) {
+        outs[t] = *od;
+        outs[t].packed = (pm_host_record *)r_dev + (size_t)t * (size_t)d->n_envs;
+    }
+    const int rc = pm_step_chain(d, a_dev, 1, 4 * d->n_envs, n_steps, outs, n_steps, scratch, stream);
+    delete[] outs;
+    return rc;
 }
 
 extern "C" int pm_step_host_mapped(const pm_env_desc *d, const uint8_t *actions_pinned, const pm_step_out *od,

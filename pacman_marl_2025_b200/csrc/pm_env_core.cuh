@@ -142,8 +142,9 @@ struct PmSmem {
     int lut, masks, lay, blk0, blk_words, lid, posA, posB, patch, rec, food, caps, stage, total;
     int E1;                             // padded env stride
     int dist;                           // bots, one board: dist[nmax][nmax] u16 then node_of[HW] i16 (0 = not staged)
-    int lut8;                           // views: 256 x 8 bytes, byte b -> its eight bits as bytes (0 = absent)
+    int vrec;                           // views: 3E unit records of PM_VREC_WORDS words (pm_views_prep)
 };
+#define PM_VREC_WORDS 8
 // words needed to stage one board's maze-distance table + cell->node map (baselineTeam look-ahead)
 PM_HD int pm_dist_stage_words(int HW, int nmax) { return ((nmax * nmax * 2 + 3) >> 2) + ((HW * 2 + 3) >> 2); }
 #define PM_DIST_STAGE_MAX_WORDS 3072    // 12 KB: tinyCapture 7.3 KB, smallCapture 9.6 KB; bloxCapture (72 KB) stays in L2
@@ -160,8 +161,6 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     o = (o + 3) & ~3;
     m.dist = 0;
     if (dist_words > 0) { m.dist = o; o += dist_words; o = (o + 3) & ~3; }
-    m.lut8 = 0;
-    (void)views;
     m.blk0 = o;
     // per-block buffer
     m.lid = o; o += E;
@@ -170,6 +169,7 @@ PM_HD PmSmem pm_smem_map(int HW, int LS, int E, int has_caps, int L, int nslots 
     m.patch = o; o += 4 * m.E1;
     o = (o + 3) & ~3;
     m.rec = o; o += 12 * E;             // pm_host_record staging: 12 words per env, written out coalesced
+    m.vrec = o; o += views ? 3 * E * PM_VREC_WORDS : 0;
     m.food = o; o += nslots * NW * m.E1;   // slots 0-3: per-agent snapshots; slot 4 (bots): look-ahead scratch
     m.caps = o; o += has_caps ? nslots * NW * m.E1 : 0;
     o = (o + 3) & ~3;
@@ -1210,9 +1210,31 @@ PM_HD uint32_t pm_spread4(uint32_t nib) { return (nib * 0x00204081u) & 0x0101010
 // 256-bit store (two 128-bit / four 64-bit stores when the view's row pitch is not 32- / 16-byte aligned); the
 // lanes of a warp cover a contiguous 1 KB run.  No shuffles, no second pass for the own-cell values: the lane that
 // owns the word holding the patched element substitutes the byte before storing.
+// Unit records: everything an item of the views encoder needs to know about its (env, view) unit, worked out ONCE per
+// unit by pm_views_prep (3E threads after the rules phase) instead of once per word: which snapshot slot, the (mirrored)
+// bit positions of the agents and the own-cell patches.  PM_VREC_WORDS words per unit:
+//   [0] word offset of the unit's food bitset relative to M.food (0xFFFFFFFF: env not in this launch)
+//   [1] layout id | mirror << 31      [2] p_own | p_ally << 16      [3] p_e1 | p_e2 << 16      [4] p_own2 | 0xFFFF << 16
+//   [5] patch      [6] patch2         (16-bit positions: 0xFFFF = none)
+template <int MODE>
+PM_HD void pm_views_prep(const PmParams &P, uint32_t *sm, const PmSmem &M, int u, int mslot0) {
+    const int v = u >> P.lgE, el = u & (P.E - 1);
+    uint32_t *r = sm + M.vrec + u * PM_VREC_WORDS;
+    PmUnit U;
+    if (!pm_view_unit_load<MODE>(P, sm, M, v, el, mslot0, U)) { r[0] = 0xffffffffu; return; }
+    r[0] = (uint32_t)(U.food - (sm + M.food));
+    r[1] = U.lid | (uint32_t)U.mirror << 31;
+    r[2] = (U.p_own & 0xffffu) | U.p_ally << 16;
+    r[3] = (U.p_e1 & 0xffffu) | U.p_e2 << 16;
+    r[4] = (U.p_own2 & 0xffffu) | 0xffff0000u;
+    r[5] = U.patch; r[6] = U.patch2; r[7] = 0;
+}
+PM_HD uint32_t pm_pos16(uint32_t p) { return p == 0xffffu ? 0xffffffffu : p; }
+
 template <int MODE>
 PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t *sm, const PmSmem &M, int warp, int nwarps,
                            int lane, int64_t n0, int mslot0) {
+    (void)mslot0;
     const int NCAT = P.NCAT, E = P.E;
     const int nbytes = 8 * P.HW;                        // bytes per view
     const int nitems = 3 * E * NCAT;
@@ -1231,8 +1253,16 @@ PM_HD void pm_phaseB_views(const PmParams &P, const uint32_t *st, const uint32_t
 #endif
         const int u = (int)(((unsigned long long)(uint32_t)i * magic) >> 32), j = i - u * NCAT;
         const int v = u >> P.lgE, el = u & (E - 1);
+        const pm_u4 r0 = reinterpret_cast<const pm_u4 *>(sm + M.vrec)[2 * u], r1 = reinterpret_cast<const pm_u4 *>(sm + M.vrec)[2 * u + 1];
+        if (r0.x == 0xffffffffu) continue;
         PmUnit U;
-        if (!pm_view_unit_load<MODE>(P, sm, M, v, el, mslot0, U)) continue;
+        U.food = sm + M.food + r0.x;
+        U.caps = P.has_caps ? sm + M.caps + r0.x : nullptr;
+        U.lid = r0.y & 0x7fffffffu; U.mirror = (int)(r0.y >> 31); U.fresh = 0;
+        U.p_own = pm_pos16(r0.z & 0xffffu); U.p_ally = pm_pos16(r0.z >> 16);
+        U.p_e1 = pm_pos16(r0.w & 0xffffu); U.p_e2 = pm_pos16(r0.w >> 16);
+        U.p_own2 = pm_pos16(r1.x & 0xffffu);
+        U.patch = r1.y; U.patch2 = r1.z;
         uint8_t *dstb = (v == 2 ? base2 : v == 1 ? base1 : base0) + (uint32_t)el * (uint32_t)nbytes;
         const uint32_t word = pm_cat_word(P, st, M, U, j);
         uint32_t o[8];

@@ -548,7 +548,7 @@ class gymPacMan_parallel_env:
         if self._bot_team is not None:
             raise ValueError("host-side bots decide from the live state: use step()")
         T = int(actions.shape[0])
-        if getattr(self, "_chain_scratch", None) is None or self._chain_scratch.device != self.device:
+        if getattr(self, "_chain_scratch", None) is None:
             self._chain_scratch = torch.empty(max(4, int(self._L.pm_chain_scratch_bytes(N))), dtype=torch.uint8,
                                               device=self.device)
         self._mark_static()
@@ -794,6 +794,40 @@ class gymPacMan_parallel_env:
         self._version += 1
         self.steps += 1
         return self._rec_mapped_views
+
+    def step_chain_host_mapped(self, actions_host: torch.Tensor, records: Optional[torch.Tensor] = None, sync: bool = True):
+        """``for t: step_host_mapped(actions_host[t])`` as one chained run (``pm_step_chain_host_mapped``): the T
+        launches overlap, each reading its [N,4] actions from the pinned ``actions_host`` [T,N,4] and writing its
+        records into the pinned ``records`` [T,N,48] (allocated and cached when not given) across PCIe.  Returns the
+        per-step views (``reward`` [T,N,2], ``shaped_reward`` [T,N,4], ``score_change`` [T,N], ``legal`` [T,N,4],
+        ``done`` [T,N]) after a stream synchronise (``sync=False``: the caller synchronises)."""
+        N = self.num_envs
+        if (actions_host.device.type != "cpu" or actions_host.dtype != torch.uint8 or not actions_host.is_contiguous()
+                or not actions_host.is_pinned() or actions_host.dim() != 3 or tuple(actions_host.shape[1:]) != (N, 4)):
+            raise ValueError(f"actions_host must be a contiguous, pinned CPU uint8 [T, {N}, 4] tensor")
+        T = int(actions_host.shape[0])
+        if records is None:
+            records = getattr(self, "_rec_chain", None)
+            if records is None or records.shape[0] < T:
+                records = self._rec_chain = torch.zeros((T, N, 48), dtype=torch.uint8).pin_memory()
+            records = records[:T]
+        elif not records.is_pinned() or records.dtype != torch.uint8 or tuple(records.shape) != (T, N, 48):
+            raise ValueError(f"records must be a pinned uint8 [T, {N}, 48] tensor")
+        self._ensure_mapped()
+        self._mark_static()
+        if getattr(self, "_chain_scratch", None) is None:
+            self._chain_scratch = torch.empty(max(4, int(self._L.pm_chain_scratch_bytes(N))), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.pm_step_chain_host_mapped(C.byref(self._desc), actions_host.data_ptr(), T,
+                                                         C.byref(self._mapped_out), records.data_ptr(),
+                                                         self._chain_scratch.data_ptr(), self._stream()),
+                       "pm_step_chain_host_mapped")
+            if sync:
+                torch.cuda.current_stream(self.device).synchronize()
+        self._version += 1
+        self.steps += T
+        r = records.view(T * N, 48)
+        return {k: v.view((T, N) + tuple(v.shape[1:])) for k, v in self._record_views(r).items()}
 
     def _ensure_mapped(self):
         """Pinned record buffer + the pm_step_out the zero-copy entry uses (observations / views / packed bits as the

@@ -59,6 +59,8 @@ static void run(const PmParams &P) {
             for (int w = 0; w < EMU_THREADS / 32; ++w)
                 for (int lane = 0; lane < 32; ++lane) pm_phaseB<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0);
         if (views)
+            for (int u = 0; u < 3 * P.E; ++u) pm_views_prep<MODE>(P, sm, M, u, 4 + (bots ? 1 : 0));
+        if (views)
             for (int w = 0; w < EMU_THREADS / 32; ++w)
                 for (int lane = 0; lane < 32; ++lane)
                     pm_phaseB_views<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0, 4 + (bots ? 1 : 0));

@@ -124,6 +124,27 @@ def test_chain_with_layout_pool():
     assert torch.equal(a._obs, b._obs) and torch.equal(a._state, b._state) and torch.equal(a._layout_id, b._layout_id)
 
 
+def test_chain_with_pinned_host_actions_and_records():
+    """pm_step_chain_host_mapped: the per-step records in pinned host memory == step_host_mapped called T times"""
+    N, T = 16384, 40
+    a, b = make("tinyCapture", N, length=25), make("tinyCapture", N, length=25)
+    a.reset_batched(); b.reset_batched()
+    rng = np.random.default_rng(21)
+    acts = torch.from_numpy(np.stack([biased_actions(rng, N, 0.6, t) for t in range(T)])).pin_memory()
+    seq = []
+    for t in range(T):
+        r = a.step_host_mapped(acts[t])
+        seq.append({k: v.clone() for k, v in r.items()})
+    got = b.step_chain_host_mapped(acts)
+    for k in ("reward", "shaped_reward", "score_change", "legal", "done"):
+        want = torch.stack([s[k] for s in seq])
+        assert torch.equal(got[k], want), k
+    assert int(got["done"].sum()) >= N
+    assert torch.equal(a._obs, b._obs) and torch.equal(a._state, b._state)
+    with pytest.raises(ValueError):
+        b.step_chain_host_mapped(torch.zeros((2, N, 4), dtype=torch.uint8))          # pageable
+
+
 def test_chain_argument_errors():
     e = make("tinyCapture", 64)
     e.reset_batched()

@@ -11,9 +11,8 @@ for V in plain views views+obs bots bots+views; do
   tail -2 gpurun_out/ncu_${V}_$TAG.log
   if [ -f gpurun_out/prof_${V}_$TAG.ncu-rep ]; then
     ncu -i gpurun_out/prof_${V}_$TAG.ncu-rep --page raw --csv > gpurun_out/ncu_raw_${V}_$TAG.csv 2>/dev/null
-    ncu -i gpurun_out/prof_${V}_$TAG.ncu-rep --page source --csv > gpurun_out/ncu_source_${V}_$TAG.csv 2>/dev/null
     ncu -i gpurun_out/prof_${V}_$TAG.ncu-rep --page details > gpurun_out/ncu_details_${V}_$TAG.txt 2>/dev/null
-    [ "$V" != "bots" ] && [ "$V" != "views" ] && rm -f gpurun_out/prof_${V}_$TAG.ncu-rep
+    true || rm -f gpurun_out/prof_${V}_$TAG.ncu-rep
   fi
 done
 ls -la gpurun_out | tail -30; du -sh gpurun_out
