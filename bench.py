@@ -363,28 +363,61 @@ def other_kernels(torch, device, N, peak):
     return out
 
 
+def mappo_one(torch, device, layout, amp):
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    cfg = M.TrainConfig(layout_file=layout_path(layout), num_envs=1024, num_steps=32, amp_bf16=amp, checkpoint_every=0)
+    tr = M.MAPPOTrainer(cfg, device=device)
+    tr.train_one(0)                                     # eager warm-up (cuDNN autotune, allocator)
+    tr.train_one(1)                                     # the rollout steps are captured into CUDA graphs here
+    recs = [tr.train_one(2), tr.train_one(3)]
+    best = max(recs, key=lambda r: r["sps"])
+    del tr
+    torch.cuda.empty_cache()
+    return {"samples_per_s": best["sps"], "seconds_per_update": best["seconds"]}
+
+
 def mappo_sps(torch, device, world=1):
     """BASELINE's second metric, MAPPO SPS (config 5): learner-agent samples per second of rollout + GAE + PPO update
     on smallCapture, whole job (every rank runs the same trainer on its env shard; one flat-bucket NCCL gradient
-    all-reduce per optimizer step).  Short run: 1 warm-up update + 2 timed.  Two arithmetic modes, labelled: the
+    all-reduce per optimizer step).  Short run: 2 warm-up updates (eager, then graph capture) + 2 timed.  Two arithmetic modes, labelled: the
     reference's nets are fp32; `fp32_tf32` keeps fp32 storage with TF32 tensor-core matmuls (narrower than fp32
     inside the matmul), `bf16_autocast` is narrower still."""
-    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
     out = {}
     for name, amp in (("fp32_tf32", False), ("bf16_autocast", True)):
-        cfg = M.TrainConfig(layout_file=layout_path("smallCapture"), num_envs=1024, num_steps=32, amp_bf16=amp,
-                            checkpoint_every=0)
-        tr = M.MAPPOTrainer(cfg, device=device)
-        tr.train_one(0)
-        recs = [tr.train_one(1), tr.train_one(2)]
-        best = max(recs, key=lambda r: r["sps"])
-        out[name] = {"samples_per_s": best["sps"], "seconds_per_update": best["seconds"]}
-        del tr
-        torch.cuda.empty_cache()
+        out[name] = mappo_one(torch, device, "smallCapture", amp)
     out["config"] = (f"smallCapture, 1024 envs/GPU x 32 steps x 2 learners per update, 3 epochs x 8 minibatches, randomTeam "
                      f"opponent, {world} GPU(s), NCCL gradient all-reduce per optimizer step" )
-    out["reference"] = "no figure: the reference publishes none and its trainer (1 env, CPU env loop) is bound by the env: ~350 env-steps/s/core"
+    out["reference"] = "timed at --gpus 1 (also.mappo.reference): the unmodified reference trainer on the same box"
     return out
+
+
+def python_reference_mappo(num_steps=512, updates=1, timeout=240):
+    """MAPPO SPS of the unmodified reference trainer on this box (its nets on this box's GPU, its env on one host core):
+    baseline/ref_mappo_driver.py runs `pacman_mappo_resnet.train()` with NUM_STEPS / TOTAL_UPDATES shortened."""
+    import shutil
+    import tempfile
+    if not os.path.exists(os.path.join(REF_ROOT, "pacman_mappo_resnet.py")):
+        return {"unavailable": "baseline/_ref is not populated (run __graft_entry__.build() where /root/reference is mounted)"}
+    tmp = tempfile.mkdtemp(prefix="refmappo_")
+    try:
+        for d in ("layouts", "agents"):
+            os.symlink(os.path.join(REF_ROOT, d), os.path.join(tmp, d))
+        env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+        for k in ("OMP_NUM_THREADS", "RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "baseline", "ref_mappo_driver.py"), REF_ROOT, str(num_steps), str(updates)],
+                           cwd=tmp, env=env, capture_output=True, text=True, timeout=timeout)
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+        if p.returncode != 0 or not line:
+            return {"unavailable": (p.stderr or p.stdout).strip().splitlines()[-1][:200] if (p.stderr or p.stdout).strip() else f"rc {p.returncode}"}
+        d = json.loads(line[-1])
+        return {"samples_per_s": d["samples"] / d["seconds"], "seconds": d["seconds"], "samples": d["samples"],
+                "nets_on": d["device"], "how": f"unmodified pacman_mappo_resnet.train(): 1 env on one host core (bloxCapture, hard-coded `:341-359`), "
+                f"NUM_STEPS shortened to {num_steps}, {d['updates']} updates, no evaluation; includes process start-up of the two envs"}
+    except Exception as e:                              # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 CHAIN = 50      # steps per pm_step_chain call in the timed loops
@@ -486,6 +519,17 @@ def main():
         loop_ms = max_over_ranks(ev0.elapsed_time(ev1))
         chain_ms = time_chained(torch, env, acts, min(K, 200))        # this rank, for the roofline
 
+        # a write-only reference point measured in the same run: the copy peak in MEASURED_PEAKS.json is read + write
+        # traffic, this kernel only writes, and write-only streams run higher on this part
+        fill = torch.empty(1 << 31, dtype=torch.uint8, device=device)
+        fill.zero_(); torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(5):
+            fill.zero_()
+        ev1.record(); torch.cuda.synchronize()
+        memset_gbps = 5 * fill.numel() / (ev0.elapsed_time(ev1) * 1e-3) / 1e9
+        del fill
+
         # ---- (1b) the same K steps as separate pm_step launches (what a loop with a policy between the steps sees) ----
         barrier()
         ev0.record()
@@ -583,6 +627,10 @@ def main():
                      "how": f"average launch duration inside pm_step_chain runs of {CHAIN} steps: one CUDA-event pair around "
                             "the run on the launching stream / steps (consecutive launches overlap, so no event can sit "
                             "between them)",
+                     "write_only_reference": {"memset_GBps": memset_gbps, "frac_of_memset": achieved / memset_gbps,
+                                              "note": "peak is the measured COPY bandwidth (read + write); this kernel only "
+                                                      "writes. A 2 GiB cudaMemset timed in this run is the write-only reference "
+                                                      "point: a frac slightly above 1.0 of the copy peak is below it"},
                      "separate_launches": {"kernel_ms": kern_ms, "achieved": achieved_sep, "frac": achieved_sep / peak,
                                            "how": "one CUDA-event pair around every pm_step launch; this is the duration ncu "
                                                   "reports for a launch (profiles/: serialised, nothing to overlap with)"}},
@@ -653,6 +701,10 @@ def main():
         v1, _, _ = oracle_rate(args.layout, 4096, 4, 1, args.length, nthreads=1)
         line["cpu_baseline"]["one_core_value"] = v1
         line["cpu_baseline"]["python_reference"] = python_reference_rate(args.layout, seconds=3.0)
+        if "mappo" in also:
+            # the reference's own train() is hard-wired to bloxCapture: time it, and this trainer on the same board
+            also["mappo"]["reference"] = python_reference_mappo()
+            also["mappo"]["bloxCapture_fp32_tf32"] = mappo_one(torch, device, "bloxCapture", False)
         # the same layout at 4x the batch: the fixed cost of a launch (the store-free rules phase at its start) weighs less
         e4, a4, one4 = measure_layout(torch, gymPacMan_parallel_env, args.layout, 4 * N, 0, 5, args.length, device, pool=2)
         km, _ = time_launches(torch, lambda i: e4.step_batched(a4[i % 2]), 30)

@@ -70,6 +70,27 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
     // of this one has started (programmatic dependent launch); what orders the two is the per-tile counter below
     const bool chained = MODE == PM_MODE_STEP && P.chain_flags != nullptr;
     if (chained) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (chained && P.chain_k > 0) {
+        // Launch k of a chain started before launch k-1 finished.  This CTA's envs, observation rows and output records
+        // were last touched by the CTA with the same index of launch k-1: wait until that CTA has published k
+        // (release / acquire at GPU scope; the barrier extends the ordering to the whole CTA).  Launch k-1's CTAs
+        // are all resident or finished before any CTA of launch k is scheduled, so the wait always ends.
+        if (tid == 0) {
+            const uint32_t *f = P.chain_flags + blockIdx.x;
+            uint32_t v = 0;
+            for (unsigned spin = 0;; ++spin) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v == P.chain_k) break;
+                if (spin > (1u << 24)) __trap();        // (seconds: the chain was mis-used; fail instead of hanging the GPU)
+                __nanosleep(100);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+    // the rules threads' state loads go out first, so that they are in flight under the table staging below
+    PmFetch F;
+    if (MODE == PM_MODE_STEP && tid < E) pm_phaseA_fetch(P, sm, M, tid, n0, F);
 #ifdef PM_TRACE
     if (MODE == PM_MODE_STEP && tid == 0 && pm_trace_buf) {
         unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -93,26 +114,11 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
         for (int i = tid; i < dw; i += PM_THREADS) sm[M.dist + i] = __ldg(gd + i);
         for (int i = tid; i < nw; i += PM_THREADS) sm[M.dist + dw + i] = __ldg(gn + i);
     }
-    if (chained && P.chain_k > 0 && tid == 0) {
-        // Launch k of a chain started before launch k-1 finished.  This CTA's envs, observation rows and output records
-        // were last touched by the CTA with the same index of launch k-1: wait until that CTA has published k
-        // (release / acquire at GPU scope; the barrier below extends the ordering to the whole CTA).  Launch k-1's CTAs
-        // are all resident or finished before any CTA of launch k is scheduled, so the wait always ends.
-        const uint32_t *f = P.chain_flags + blockIdx.x;
-        uint32_t v = 0;
-        for (unsigned spin = 0;; ++spin) {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-            if (v == P.chain_k) break;
-            if (spin > (1u << 24)) __trap();            // (seconds: the chain was mis-used; fail instead of hanging the GPU)
-            __nanosleep(100);
-        }
-        __threadfence();
-    }
     __syncthreads();
 
     // ---- phase A: rules, one thread per env ----
     if (tid < E) {
-        if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS, VIEWS>(P, sm, sm, M, tid, n0);
+        if (MODE == PM_MODE_STEP) pm_phaseA_step<BOTS, VIEWS>(P, sm, sm, M, tid, n0, F);
         else pm_phaseA_static<MODE, VIEWS>(P, sm, sm, M, tid, n0);
     }
     __syncthreads();
@@ -123,11 +129,7 @@ __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE ==
         for (int t = tid; t < 3 * E; t += PM_THREADS) pm_records_out(P, sm, M, t, n0);
     // ---- phase B: observations, one warp per (env, agent) ----
     if (P.obs != nullptr) pm_phaseB<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);
-    // ---- phase B': learner views: one record per (env, view) unit, then one (unit, word) item per lane ----
-    if (VIEWS && P.view_actor != nullptr) {
-        for (int u = tid; u < 3 * E; u += PM_THREADS) pm_views_prep<MODE>(P, sm, M, u, 4 + BOTS);
-        __syncthreads();
-    }
+    // ---- phase B': learner views, one (view, word) item per lane ----
     if (VIEWS && P.view_actor != nullptr) pm_phaseB_views<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0, 4 + BOTS);
     // ---- phase B'': packed observations for a host-side consumer ----
     if (P.obs_bits != nullptr) pm_phaseB_bits<MODE>(P, sm, sm, M, tid >> 5, PM_THREADS / 32, tid & 31, n0);

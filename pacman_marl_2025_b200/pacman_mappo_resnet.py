@@ -223,19 +223,31 @@ class MAPPOAgent(nn.Module):
 
 
 # ---- observation / action views (pacman_mappo_resnet.py:215-238, 267-274) ------------------------------
+_index_cache: Dict[tuple, torch.Tensor] = {}
+
+
+def _index_tensor(name: str, values, device) -> torch.Tensor:
+    """The small constant index tensors of the canonical views, one per device (a fresh torch.tensor(...) per call is a
+    host-to-device copy: slow in the rollout loop and illegal while a CUDA graph is being captured)."""
+    key = (name, str(device))
+    if key not in _index_cache:
+        _index_cache[key] = torch.tensor(values, device=device)
+    return _index_cache[key]
+
+
 def canonicalize_obs(obs: torch.Tensor, is_red_agent: bool) -> torch.Tensor:
     """Red agents see the board mirrored with the capsule (2,3) and food (6,7) plane pairs swapped, so one
     policy serves both sides.  obs [...,8,H,W]."""
     if not is_red_agent:
         return obs
-    return obs.flip(-1).index_select(-3, torch.tensor(_CANON_PLANES, device=obs.device))
+    return obs.flip(-1).index_select(-3, _index_tensor("planes", _CANON_PLANES, obs.device))
 
 
 def canonicalize_action(action, is_red_agent: bool):
     if not is_red_agent:
         return action
     if isinstance(action, torch.Tensor):
-        return torch.tensor(_CANON_ACTION, device=action.device)[action]
+        return _index_tensor("action", _CANON_ACTION, action.device)[action]
     return _CANON_ACTION[int(action)]
 
 
@@ -282,6 +294,9 @@ class TrainConfig:
     fused_pipeline: bool = True       # the minibatch pipeline around the nets as kernels (row f3): uint8 gather + widen,
                                       # fused PPO loss + gradient, clip + Adam + EMA over flat buffers; False = the
                                       # same steps as eager PyTorch ops (kept as the in-repo cross-check)
+    graph_rollout: bool = True        # a rollout step (policy forward, sampling, env step, bookkeeping: ~150 small launches)
+                                      # is captured into a CUDA graph per (opponent, side, t) on its second use and
+                                      # replayed afterwards; host-side bots and False = eager launches
     easy_until: int = 200             # updates <= this: EASY_TEAMS only (`:396-402`)
     selfplay_after: int = 800         # update index after which self-play opponents enter the mix (`:404-438`)
     log_every: int = 1
@@ -356,6 +371,13 @@ class MAPPOTrainer:
         N = cfg.num_envs
         self._ep_return = torch.zeros(N, dtype=torch.float64, device=self.device)
         self._score = torch.zeros(N, dtype=torch.int32, device=self.device)       # running game score per env
+        # persistent rollout scratch (the CUDA graphs of the rollout steps hold on to these addresses)
+        self._stats = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self._all_envs = torch.ones(N, dtype=torch.uint8, device=self.device)
+        self._actions = torch.zeros((N, 4), dtype=torch.int64, device=self.device)
+        self._graphs: Dict[tuple, Dict[int, "torch.cuda.CUDAGraph"]] = {}
+        self._graph_uses: Dict[tuple, int] = {}
+        self._graph_pool = None
 
     # ------------------------------------------------------------------ helpers
     def _autocast(self):
@@ -411,11 +433,19 @@ class MAPPOTrainer:
         elif mode == "Self(Old)":
             self.opponent.load_state_dict(self.opponent_pool[int(self.rng.integers(len(self.opponent_pool)))])
         learner_ids, opp_ids = ([0, 2], [1, 3]) if play_as_red else ([1, 3], [0, 2])
-        obs4, _ = env.reset_batched()
+        # `:457`: every rollout starts from fresh games.  After an env's first rollout the reset is a MASKED reset of all
+        # envs, which advances the per-env episode counters instead of restarting them: the counters key the in-kernel
+        # opponents' draws, so a later rollout does not replay the random choices of an earlier one (the reference's
+        # bots draw from Python's global RNG, which never restarts either)
+        if getattr(env, "_rolled_out", False):
+            obs4, _ = env.reset_batched(self._all_envs)
+        else:
+            obs4, _ = env.reset_batched()
+            env._rolled_out = True
         self._ep_return.zero_()
         self._score.zero_()
-        stats = torch.zeros(4, dtype=torch.float64, device=self.device)      # episodes, return sum, wins, reward sum
-        actions = torch.zeros((N, 4), dtype=torch.int64, device=self.device)
+        stats = self._stats.zero_()                                   # episodes, return sum, wins, reward sum
+        actions = self._actions.zero_()
         team_row = 0 if play_as_red else 1
         shp = self.obs_shape
 
@@ -427,48 +457,87 @@ class MAPPOTrainer:
             env.observe_views(play_as_red, ro.obs[0], ro.merged[0])
         else:
             store_views(0, obs4)
+
+        def step_body(t):
+            """One rollout step (`:470-538`).  No host synchronisation and no per-call allocation of anything that
+            outlives the step, so the whole body can be captured into a CUDA graph."""
+            actor_in, merged = ro.obs[t].view(2 * N, *shp).float(), ro.merged[t].float()
+            with self._autocast():
+                act, logp, value, _ = self.agent.get_action_and_value(actor_in, merged)
+            act = act.view(2, N)
+            ro.action[t] = act
+            ro.logp[t] = logp.float().view(2, N)
+            ro.value[t] = value.float().unsqueeze(0).expand(2, N)
+            env_act = canonicalize_action(act, play_as_red)
+            actions[:, learner_ids[0]] = env_act[0]
+            actions[:, learner_ids[1]] = env_act[1]
+            if selfplay:
+                o_in, o_merged = self._views(env._obs, opp_ids, not play_as_red)
+                with self._autocast():
+                    o_act, _, _, _ = self.opponent.get_action_and_value(o_in, o_merged)
+                o_act = canonicalize_action(o_act.view(2, N), not play_as_red)
+                actions[:, opp_ids[0]] = o_act[0]
+                actions[:, opp_ids[1]] = o_act[1]
+            if use_views:                                         # next step's network inputs land in slot t+1;
+                env.set_view_outputs(play_as_red, ro.obs[t + 1], ro.merged[t + 1], raw_obs=selfplay)   # raw obs only for the opponent net
+            out = env._step_with_host_bots(actions) if env._bot_team is not None else env.step_batched(actions)
+            if not use_views:
+                store_views(t + 1, out["obs"])                    # finished envs already show the new episode
+            ro.reward[t, 0] = out["shaped_reward"][learner_ids[0]]
+            ro.reward[t, 1] = out["shaped_reward"][learner_ids[1]]
+            ro.done[t] = out["done"].to(torch.float32).unsqueeze(0).expand(2, N)
+            # episode bookkeeping (`:516-538`): team_reward = sum over both learners = 2 x team reward
+            team_reward = 2.0 * out["reward"][team_row]
+            self._ep_return.add_(team_reward)
+            db = out["done"].bool()
+            # final score of a finished episode (`:525-531`): the env restarted in-kernel, so the score is
+            # tracked here from the per-step score_change output
+            self._score.add_(out["score_change"])
+            won = (self._score > 0) if play_as_red else (self._score < 0)
+            stats[0] += db.sum()
+            stats[1] += (self._ep_return * db).sum()
+            stats[2] += (db & won).sum()
+            stats[3] += team_reward.sum()
+            self._ep_return.masked_fill_(db, 0.0)
+            self._score.masked_fill_(db, 0)
+
+        # CUDA graphs: a step is ~150 small launches (two network forwards, sampling, the env kernel, bookkeeping) and
+        # the loop is bound by their launch cost, not by the GPU.  The first rollout against an opponent runs eagerly
+        # (cuDNN autotune, lazy initialisation); on the second the T step bodies are captured - one graph per t, because
+        # step t reads slot t and writes slot t + 1 of the rollout buffer - and replayed from then on.
+        key = (id(env), mode if not selfplay else "self", bool(play_as_red), bool(use_views), T)
+        graphs = None
+        if cfg.graph_rollout and env._bot_team is None:
+            self._graph_uses[key] = self._graph_uses.get(key, 0) + 1
+            if self._graph_uses[key] >= 2:
+                graphs = self._graphs.setdefault(key, {})
         try:
             for t in range(T):
-                actor_in, merged = ro.obs[t].view(2 * N, *shp).float(), ro.merged[t].float()
-                with self._autocast():
-                    act, logp, value, _ = self.agent.get_action_and_value(actor_in, merged)
-                act = act.view(2, N)
-                ro.action[t] = act
-                ro.logp[t] = logp.float().view(2, N)
-                ro.value[t] = value.float().unsqueeze(0).expand(2, N)
-                env_act = canonicalize_action(act, play_as_red)
-                actions[:, learner_ids[0]] = env_act[0]
-                actions[:, learner_ids[1]] = env_act[1]
-                if selfplay:
-                    o_in, o_merged = self._views(obs4, opp_ids, not play_as_red)
-                    with self._autocast():
-                        o_act, _, _, _ = self.opponent.get_action_and_value(o_in, o_merged)
-                    o_act = canonicalize_action(o_act.view(2, N), not play_as_red)
-                    actions[:, opp_ids[0]] = o_act[0]
-                    actions[:, opp_ids[1]] = o_act[1]
-                if use_views:                                         # next step's network inputs land in slot t+1;
-                    env.set_view_outputs(play_as_red, ro.obs[t + 1], ro.merged[t + 1], raw_obs=selfplay)   # raw obs only for the opponent net
-                out = env._step_with_host_bots(actions) if env._bot_team is not None else env.step_batched(actions)
-                obs4 = out["obs"]                                     # finished envs already show the new episode
-                if not use_views:
-                    store_views(t + 1, obs4)
-                ro.reward[t, 0] = out["shaped_reward"][learner_ids[0]]
-                ro.reward[t, 1] = out["shaped_reward"][learner_ids[1]]
-                ro.done[t] = out["done"].to(torch.float32).unsqueeze(0).expand(2, N)
-                # episode bookkeeping (`:516-538`): team_reward = sum over both learners = 2 x team reward
-                team_reward = 2.0 * out["reward"][team_row]
-                self._ep_return += team_reward
-                db = out["done"].bool()
-                # final score of a finished episode (`:525-531`): the env restarted in-kernel, so the score is
-                # tracked here from the per-step score_change output
-                self._score += out["score_change"]
-                won = (self._score > 0) if play_as_red else (self._score < 0)
-                stats[0] += db.sum()
-                stats[1] += (self._ep_return * db).sum()
-                stats[2] += (db & won).sum()
-                stats[3] += team_reward.sum()
-                self._ep_return.masked_fill_(db, 0.0)
-                self._score.masked_fill_(db, 0)
+                if graphs is None:
+                    step_body(t)
+                    continue
+                if t not in graphs:
+                    g = torch.cuda.CUDAGraph()
+                    if self._graph_pool is None:
+                        self._graph_pool = torch.cuda.graph_pool_handle()
+                    steps0, ver0 = env.steps, env._version
+                    try:
+                        with torch.cuda.graph(g, pool=self._graph_pool):
+                            step_body(t)
+                    except RuntimeError as e:                        # something in the step cannot be captured: stay eager
+                        print(f"[MAPPOTrainer] rollout step not captured ({str(e).splitlines()[0][:120]}); eager launches", flush=True)
+                        env.steps, env._version = steps0, ver0
+                        self.cfg.graph_rollout, graphs = False, None
+                        self._graphs.pop(key, None)
+                        step_body(t)
+                        continue
+                    env.steps, env._version = steps0, ver0          # capturing runs the host code but not the kernels
+                    graphs[t] = g
+                if use_views:                                        # (host-side descriptor, for callers that look at it)
+                    env.set_view_outputs(play_as_red, ro.obs[t + 1], ro.merged[t + 1], raw_obs=selfplay)
+                graphs[t].replay()
+                env.steps += 1
+                env._version += 1
         finally:
             env.set_view_outputs(None)
         with self._autocast():

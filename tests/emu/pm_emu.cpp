@@ -46,10 +46,12 @@ static void run(const PmParams &P) {
         }
         for (int el = 0; el < P.E; ++el) {
             if (MODE == PM_MODE_STEP) {
-                if (bots && views) pm_phaseA_step<1, 1>(P, sm, sm, M, el, n0);
-                else if (bots) pm_phaseA_step<1, 0>(P, sm, sm, M, el, n0);
-                else if (views) pm_phaseA_step<0, 1>(P, sm, sm, M, el, n0);
-                else pm_phaseA_step<0, 0>(P, sm, sm, M, el, n0);
+                PmFetch F;
+                pm_phaseA_fetch(P, sm, M, el, n0, F);
+                if (bots && views) pm_phaseA_step<1, 1>(P, sm, sm, M, el, n0, F);
+                else if (bots) pm_phaseA_step<1, 0>(P, sm, sm, M, el, n0, F);
+                else if (views) pm_phaseA_step<0, 1>(P, sm, sm, M, el, n0, F);
+                else pm_phaseA_step<0, 0>(P, sm, sm, M, el, n0, F);
             } else if (views) pm_phaseA_static<MODE, 1>(P, sm, sm, M, el, n0);
             else pm_phaseA_static<MODE, 0>(P, sm, sm, M, el, n0);
         }
@@ -58,8 +60,6 @@ static void run(const PmParams &P) {
         if (P.obs)
             for (int w = 0; w < EMU_THREADS / 32; ++w)
                 for (int lane = 0; lane < 32; ++lane) pm_phaseB<MODE>(P, sm, sm, M, w, EMU_THREADS / 32, lane, n0);
-        if (views)
-            for (int u = 0; u < 3 * P.E; ++u) pm_views_prep<MODE>(P, sm, M, u, 4 + (bots ? 1 : 0));
         if (views)
             for (int w = 0; w < EMU_THREADS / 32; ++w)
                 for (int lane = 0; lane < 32; ++lane)

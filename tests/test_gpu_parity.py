@@ -565,6 +565,47 @@ def test_mappo_rollout_identical_with_kernel_views_and_torch_views():
         assert torch.equal(lva, lvb) and torch.equal(sa, sb)
 
 
+def test_mappo_rollout_from_cuda_graphs_equals_eager_launches():
+    """graph_rollout: from its second use on, a rollout step (both network forwards, sampling, the env launch, the
+    bookkeeping) is replayed from a CUDA graph per t.  Same seeds -> the same rollouts as with eager launches, collect after
+    collect (the later ones start from masked resets: new episode numbers, new opponent draws), and the weights after an
+    update in between agree too."""
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    flags = (torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    # plain fp32 and no autotuning: both trainers then run the very same network kernels, captured or not
+    torch.backends.cudnn.benchmark = torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        for mode, red in (("randomTeam", False), ("Self(Curr)", True)):
+            trs = []
+            for graph in (True, False):
+                cfg = M.TrainConfig(num_envs=64, num_steps=12, num_minibatches=2, update_epochs=1, total_updates=4,
+                                    length=20, seed=3, checkpoint_every=0, graph_rollout=graph, fast_math=False)
+                trs.append(M.MAPPOTrainer(cfg, device="cuda:0"))
+            prev_actions = None
+            for it in range(4):
+                outs = []
+                for tr in trs:
+                    torch.manual_seed(100 + it)
+                    lv, stats = tr.collect(mode, play_as_red=red)
+                    outs.append((lv.clone(), stats.clone()))
+                a, b = trs[0].rollout, trs[1].rollout
+                for name in ("obs", "merged", "action", "reward", "done"):
+                    assert torch.equal(getattr(a, name), getattr(b, name)), f"{mode} collect {it}: {name} differs"
+                for name in ("logp", "value"):
+                    torch.testing.assert_close(getattr(a, name), getattr(b, name), rtol=1e-4, atol=1e-5)
+                assert torch.equal(outs[0][1], outs[1][1])
+                if prev_actions is not None and mode == "randomTeam":
+                    assert not torch.equal(prev_actions, a.action)      # a new rollout is not a replay of the previous one
+                prev_actions = a.action.clone()
+            assert len(trs[0]._graphs) == 1 and len(next(iter(trs[0]._graphs.values()))) == 12 and not trs[1]._graphs
+            for tr in trs:                                              # and an update on top of a replayed rollout
+                tr.update(outs[0][0], tr.schedule(1))
+            for pa, pb in zip(trs[0].agent.parameters(), trs[1].agent.parameters()):
+                torch.testing.assert_close(pa, pb, rtol=1e-3, atol=1e-5)
+    finally:
+        torch.backends.cudnn.benchmark, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = flags
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the reference-shaped API itself (1 env, dicts, Python scalars, lists of legal actions)
 # ---------------------------------------------------------------------------------------------------------

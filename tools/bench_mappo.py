@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--views", type=int, default=1)
     ap.add_argument("--fused", type=int, default=1, help="row-f3 kernels (gather, fused loss, Adam+EMA) vs eager ops")
     ap.add_argument("--attn", default="bmm", help="critic attention: auto, kernel (pm_attn), bmm (written out) or module (nn.TransformerEncoder)")
+    ap.add_argument("--graph", type=int, default=1, help="rollout steps replayed from CUDA graphs")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -33,10 +34,11 @@ def main():
     from pacman_marl_2025_b200 import pacman_mappo_resnet as M
     lay = os.path.join(os.path.dirname(M.__file__), "layouts", a.layout + ".lay")
     cfg = M.TrainConfig(layout_file=lay, num_envs=a.envs, num_steps=a.steps, amp_bf16=bool(a.amp), checkpoint_every=0,
-                        pair_agents=bool(a.pair), use_views=bool(a.views), fused_pipeline=bool(a.fused))
+                        pair_agents=bool(a.pair), use_views=bool(a.views), fused_pipeline=bool(a.fused), graph_rollout=bool(a.graph))
     M.MAPPOAgent.attn_impl = a.attn
     tr = M.MAPPOTrainer(cfg, device=f"cuda:{local}")
     tr.train_one(0)                                        # warm-up (cuDNN autotune, allocator)
+    tr.train_one(0)                                        # second use of the opponent: the rollout steps are captured here
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     parts = dict(rollout=0.0, update=0.0)
@@ -59,7 +61,7 @@ def main():
                           "unit": "samples/s", "n_gpus": world, "config": {"workload": f"{a.layout}, {a.envs} envs/GPU x {a.steps} steps, "
                           f"{cfg.update_epochs} epochs x {cfg.num_minibatches} minibatches, randomTeam opponent", "amp_bf16": bool(a.amp),
                           "pair_agents": bool(a.pair), "kernel_views": bool(a.views), "fused_pipeline": bool(a.fused),
-                          "critic_attention": a.attn},
+                          "critic_attention": a.attn, "graph_rollout": bool(a.graph)},
                           "rollout_s": parts["rollout"], "update_s": parts["update"],
                           "env_agent_steps_per_s_in_rollout": 4 * a.envs * a.steps * a.updates * world / parts["rollout"]}), flush=True)
     if world > 1:
