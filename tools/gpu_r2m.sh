@@ -1,7 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out
-TAG=${1:-r02n}
-T0=$SECONDS; timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$? wall $((SECONDS-T0)) s"
-tail -6 gpurun_out/pytest_gpu_$TAG.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 300 python tools/run_variants.py --layout bloxCapture --chain 50 --reps 200 --small 0 --only views,bots+views 2>&1 | grep -v "^{" | tee -a gpurun_out/variants_$TAG.log
+TAG=${1:-r02p}
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "cuda_graphs or rollout_identical or trainer_rollout" 2>&1 | tail -4
+NG=$(nvidia-smi -L | wc -l); echo "GPUs: $NG"
+T0=$SECONDS; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG --impl reference > gpurun_out/bench_ref_${TAG}_n$NG.json 2>gpurun_out/bench_ref_${TAG}_n$NG.err; echo "ref rc=$? wall $((SECONDS-T0)) s"
+T0=$SECONDS; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $NG > gpurun_out/bench_${TAG}_n$NG.json 2>gpurun_out/bench_${TAG}_n$NG.err; echo "bench rc=$? wall $((SECONDS-T0)) s"
+tail -5 gpurun_out/bench_${TAG}_n$NG.err
+python - <<PY
+import json
+d=json.loads([l for l in open('gpurun_out/bench_${TAG}_n$NG.json') if l.startswith('{')][-1])
+print('n',d['n_gpus'],'value',d['value'],'roofline',d['roofline']['frac'],d['roofline']['write_only_reference'],'sep',d['roofline']['separate_launches']['frac'], d['separate_launches']['value'])
+print('e2e',d['e2e']['value'],'chain',d['e2e_chain']['value'])
+print(json.dumps(d['also'])[:1800])
+PY
