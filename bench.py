@@ -723,22 +723,6 @@ def main():
                                           "roofline_frac": algo * 16.0 * N / (km * 1e-3) / 1e9 / peak}
         del e4, a4, one4
         torch.cuda.empty_cache()
-        # opt-in: leave the observation elements that cannot have changed (walls; capsule planes of capsule-free boards)
-        # as the previous step left them in the env's own buffer (pm_step_out.obs_static_valid): same tensors, fewer bytes
-        ee = gymPacMan_parallel_env(layout_file=layout_path(args.layout), self_play=True, length=args.length, num_envs=N,
-                                    device=device, auto_reset=True, elide_static_planes=True)
-        ae = torch.randint(0, 5, (4, N, 4), dtype=torch.uint8, device=device)
-        ee.reset_batched()
-        for i in range(5):
-            ee.step_batched(ae[i % 4])
-        km, _ = time_launches(torch, lambda i: ee.step_batched(ae[i % 4]), 60)
-        static_frac = (1 + (0 if ee._desc.has_caps else 2)) / 8.0
-        also[f"{args.layout}_static_planes_elided"] = {
-            "value": 4.0 * N / (km * 1e-3), "kernel_ms": km, "bytes_written_frac": 1 - static_frac,
-            "hbm_GBps_of_bytes_actually_written": (algo - 32 * H * Wd * static_frac) * 4.0 * N / (km * 1e-3) / 1e9,
-            "note": "not the headline: the roofline above counts all 8 planes as written every step"}
-        del ee, ae
-        torch.cuda.empty_cache()
         # the other kernels of the path, each timed alone (CUDA events, this stream)
         also["kernels"] = other_kernels(torch, device, N, peak)
     if also:

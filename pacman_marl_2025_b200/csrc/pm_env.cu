@@ -29,8 +29,11 @@
 #define PM_THREADS 128
 #endif
 #ifndef PM_MIN_CTAS
-#define PM_MIN_CTAS 8                             // 64 registers/thread: 8 CTAs x 4 warps per SM
+#define PM_MIN_CTAS 8                             // 64 registers/thread: 8 CTAs x 4 warps per SM (reset / observe / views variants)
 #endif
+#ifndef PM_MIN_CTAS_STEP
+#define PM_MIN_CTAS_STEP 5                        // the plain step (fp32 observations): 96 registers, no spills in the rules
+#endif                                            // phase, 5 CTAs per SM - round-2 B200 sweep, see DESIGN.md 3.1
 #ifndef PM_MIN_CTAS_BOTS
 #define PM_MIN_CTAS_BOTS 8                         // step with the baselineTeam look-ahead (B200 sweep: 4 -> 448 us, 6 -> 400, 8 -> 350 on tiny)
 #endif
@@ -61,7 +64,10 @@ extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToS
 // E = envs per CTA: PM_E (32) for big batches; PM_E_SMALL (8) when the batch would otherwise leave most SMs
 // without a CTA (a trainer-sized batch of 1 024 envs is 32 CTAs of 32 envs but 128 CTAs of 8).
 template <int MODE, int BOTS, int VIEWS, int E>
-__global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS : (MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS : PM_MIN_CTAS)) pm_env_kernel(const PmParams P) {
+__global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS
+                                                    : MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS
+                                                    : (MODE == PM_MODE_STEP && !VIEWS) ? PM_MIN_CTAS_STEP : PM_MIN_CTAS)
+pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0, VIEWS);
     const int tid = threadIdx.x;

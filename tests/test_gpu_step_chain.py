@@ -124,6 +124,25 @@ def test_chain_with_layout_pool():
     assert torch.equal(a._obs, b._obs) and torch.equal(a._state, b._state) and torch.equal(a._layout_id, b._layout_id)
 
 
+def test_chain_with_static_plane_elision_and_packed_bits():
+    """the opt-in outputs ride along: obs_static_valid (skip planes that cannot have changed) inside a chain leaves the
+    same observation tensor as plain sequential steps, and the packed observation bits of the last step agree"""
+    N, T = 8192, 45
+    a = make("smallCapture", N, length=20)
+    b = make("smallCapture", N, length=20, elide_static_planes=True)
+    for e in (a, b):
+        e.reset_batched()
+        e.set_bits_output(True)
+    rng = np.random.default_rng(5)
+    acts = torch.from_numpy(np.stack([biased_actions(rng, N, 0.6, t) for t in range(T)])).cuda()
+    for t in range(T):
+        oa = a.step_batched(acts[t])
+    ob = b.step_chain(acts[:20])
+    ob = b.step_chain(acts[20:])
+    assert torch.equal(a._obs, b._obs) and torch.equal(a._state, b._state)
+    assert torch.equal(oa["obs_bits"], ob["obs_bits"])
+
+
 def test_chain_with_pinned_host_actions_and_records():
     """pm_step_chain_host_mapped: the per-step records in pinned host memory == step_host_mapped called T times"""
     N, T = 16384, 40

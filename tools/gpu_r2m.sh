@@ -1,15 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-TAG=${1:-r02p}
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "cuda_graphs or rollout_identical or trainer_rollout" 2>&1 | tail -4
-NG=$(nvidia-smi -L | wc -l); echo "GPUs: $NG"
-T0=$SECONDS; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG --impl reference > gpurun_out/bench_ref_${TAG}_n$NG.json 2>gpurun_out/bench_ref_${TAG}_n$NG.err; echo "ref rc=$? wall $((SECONDS-T0)) s"
-T0=$SECONDS; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $NG > gpurun_out/bench_${TAG}_n$NG.json 2>gpurun_out/bench_${TAG}_n$NG.err; echo "bench rc=$? wall $((SECONDS-T0)) s"
-tail -5 gpurun_out/bench_${TAG}_n$NG.err
-python - <<PY
-import json
-d=json.loads([l for l in open('gpurun_out/bench_${TAG}_n$NG.json') if l.startswith('{')][-1])
-print('n',d['n_gpus'],'value',d['value'],'roofline',d['roofline']['frac'],d['roofline']['write_only_reference'],'sep',d['roofline']['separate_launches']['frac'], d['separate_launches']['value'])
-print('e2e',d['e2e']['value'],'chain',d['e2e_chain']['value'])
-print(json.dumps(d['also'])[:1800])
-PY
+TAG=${1:-r02t}
+for V in bots6 bots5; do
+  for L in tinyCapture bloxCapture; do
+    PM_LIB_PATH=$PWD/build_variants/lib_$V.so timeout 300 python tools/run_variants.py --layout $L --reps 100 --small 0 --only bots,bots+views 2>&1 | grep -v "^{\|^lib" | sed "s/^/$V /" | tee -a gpurun_out/variants_$TAG.log
+  done
+done
+timeout 300 python tools/run_variants.py --chain 50 --reps 200 --only plain,bots,bots+views,plain-elide 2>&1 | grep -v "^{\|^lib" | sed "s/^/default /" | tee -a gpurun_out/variants_$TAG.log
+timeout 300 python tools/run_variants.py --envs 262144 --small 16384 --chain 20 --reps 40 --only plain 2>&1 | grep -v "^{\|^lib" | sed "s/^/default /" | tee -a gpurun_out/variants_$TAG.log
