@@ -14,7 +14,9 @@ for i, k in enumerate(hdr):
     ix.setdefault(k, i)
 bars = [i for i, r in enumerate(data) if "BAR.SYNC" in r[1]]
 stall = [k for k in hdr if k.startswith("stall_") and "Not Issued" not in k]
-names = ["staging", "rules phase", "encoder"] + ["tail"] * 8
+# step kernels: barrier after the (chain-only) tile wait, after the table staging, after the rules phase
+nb = len(bars)
+names = (["prologue", "state fetch + staging", "rules phase", "encoder"] if nb >= 3 else ["staging", "rules phase", "encoder"]) + ["after the last barrier"] * 8
 prev = 0
 for si, b in enumerate(bars + [len(data)]):
     seg = data[prev:b]
