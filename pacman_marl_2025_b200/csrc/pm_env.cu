@@ -307,6 +307,11 @@ static int launch_env(const PmParams &P, cudaStream_t st) {
     } else {
         if constexpr (MODE == PM_MODE_STEP && VIEWS)
             if (P.obs == nullptr) return launch_env_e<MODE, BOTS, VIEWS, PM_E_RULES>(P, st);
+        // the launches of a chain overlap, so the wave structure of a single launch does not matter to them and the
+        // larger tiles win (tinyCapture 65,536 envs: 175.3 -> 171.7 us per chained step; alone: 194 -> 219 us)
+        if constexpr (MODE == PM_MODE_STEP && !VIEWS)
+            if (P.chain_flags != nullptr && (P.n_end - P.n_begin) >= (int64_t)4 * PM_E_RULES * pm_sm_count())
+                return launch_env_e<MODE, BOTS, VIEWS, PM_E_RULES>(P, st);
         return launch_env_e<MODE, BOTS, VIEWS, PM_E>(P, st);
     }
 }
