@@ -46,6 +46,9 @@
 #ifndef PM_E_RULES
 #define PM_E_RULES 64                             // envs per CTA of the launches bound by the rules phase (see launch_env)
 #endif
+#ifndef PM_E_BOTS
+#define PM_E_BOTS PM_E_RULES                      // envs per CTA of the launches with the baselineTeam look-ahead
+#endif
 #ifndef PM_E_SMALL
 #define PM_E_SMALL 8                              // envs per CTA for batches too small to give every SM work at PM_E
 #endif
@@ -303,7 +306,7 @@ static int launch_env(const PmParams &P, cudaStream_t st) {
     // all CTAs resident in one wave (B200, tinyCapture 65,536 envs: bots 292 -> 274 us, bots + views 178 -> 143 us,
     // views only 94 -> 86 us; the fp32 step itself is 3 % slower that way and stays at PM_E).
     if constexpr (MODE == PM_MODE_STEP && BOTS) {
-        return launch_env_e<MODE, BOTS, VIEWS, PM_E_RULES>(P, st);
+        return launch_env_e<MODE, BOTS, VIEWS, PM_E_BOTS>(P, st);
     } else {
         if constexpr (MODE == PM_MODE_STEP && VIEWS)
             if (P.obs == nullptr) return launch_env_e<MODE, BOTS, VIEWS, PM_E_RULES>(P, st);
