@@ -723,6 +723,19 @@ def main():
                                           "roofline_frac": algo * 16.0 * N / (km * 1e-3) / 1e9 / peak}
         del e4, a4, one4
         torch.cuda.empty_cache()
+        # BASELINE config 3 asks for bloxCapture over a range of batch sizes: the two ends beside the 65,536 above
+        ab = ALGO_BYTES_PER_AGENT_STEP["bloxCapture"]
+        sweep = {}
+        for nb in (16384, 262144):
+            eb, a_b, _ = measure_layout(torch, gymPacMan_parallel_env, "bloxCapture", nb, 0, 3, args.length, device, pool=10)
+            run_chained(eb, a_b, 10)
+            cm = time_chained(torch, eb, a_b, 20)
+            km, _ = time_launches(torch, lambda i: eb.step_batched(a_b[i % 10]), 20)
+            sweep[str(nb)] = {"value": 4.0 * nb / (cm * 1e-3), "kernel_ms": cm, "roofline_frac": ab * 4.0 * nb / (cm * 1e-3) / 1e9 / peak,
+                              "separate_launches": {"kernel_ms": km, "roofline_frac": ab * 4.0 * nb / (km * 1e-3) / 1e9 / peak}}
+            del eb, a_b
+            torch.cuda.empty_cache()
+        also["bloxCapture_envs_sweep"] = sweep
         # the other kernels of the path, each timed alone (CUDA events, this stream)
         also["kernels"] = other_kernels(torch, device, N, peak)
     if also:

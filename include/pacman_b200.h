@@ -375,6 +375,28 @@ int pm_attn_fwd(const float *qkv, float *out, float *lse, int S, int64_t B, int 
 int pm_attn_bwd(const float *qkv, const float *out, const float *dout, const float *lse, float *dqkv, int S, int64_t B,
                 int n_heads, pm_stream_t stream);
 
+/* ---- ABI 8: the networks' normalisations at the shapes PyTorch's kernels handle worst ----
+ * y = LayerNorm_32(a + b) * gamma + beta over `rows` rows of 32 floats (b may be NULL): the post-norm residual of the
+ * critic's nn.TransformerEncoderLayer (d_model 32, pacman_mappo_resnet.py:131-136).  stats [rows][2] = (mean, rstd),
+ * may be NULL when no backward pass follows.  Backward: dx = d loss / d a = d loss / d b; partial is
+ * [pm_layernorm32_blocks(rows)][64] floats whose column sums are dgamma (0..31) and dbeta (32..63).            */
+int pm_layernorm32_blocks(int64_t rows);
+int pm_add_layernorm32_fwd(const float *a, const float *b, const float *gamma, const float *beta, float *y, float *stats,
+                           int64_t rows, double eps, pm_stream_t stream);
+int pm_add_layernorm32_bwd(const float *a, const float *b, const float *gamma, const float *stats, const float *dy, float *dx,
+                           float *partial, int64_t rows, pm_stream_t stream);
+/* y = [gelu](GroupNorm(4, 32)(x) [+ res]) on [n_samples][32][HW] (NCHW, HW even, <= pm_groupnorm_4x8_max_hw()): the
+ * ResidualBlock of the actor (`:49-68`): `act(gn1(conv1(x)))` (res NULL, gelu 1) and `act(gn2(conv2(h)) + x)` (res = x,
+ * gelu 1).  stats [n_samples][4][2] = (mean, rstd) per group.  Backward: dx (w.r.t. x), dres (w.r.t. res, NULL when res
+ * is NULL); partial is [pm_groupnorm_blocks(n_samples)][64] floats whose column sums are dgamma and dbeta.        */
+int pm_groupnorm_blocks(int64_t n_samples);
+int pm_groupnorm_4x8_max_hw(void);
+int pm_groupnorm_4x8_fwd(const float *x, const float *res, const float *gamma, const float *beta, float *y, float *stats,
+                         int64_t n_samples, int HW, double eps, int gelu, pm_stream_t stream);
+int pm_groupnorm_4x8_bwd(const float *x, const float *res, const float *gamma, const float *beta, const float *stats,
+                         const float *dy, float *dx, float *dres, float *partial, int64_t n_samples, int HW, int gelu,
+                         pm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

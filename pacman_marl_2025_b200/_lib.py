@@ -25,6 +25,8 @@ EXPORTS = [
     "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
     "pm_obs_bits_words", "pm_observe_bits",
     "pm_chain_scratch_bytes", "pm_step_chain", "pm_step_chain_host_mapped", "pm_attn_fwd", "pm_attn_bwd",
+    "pm_layernorm32_blocks", "pm_add_layernorm32_fwd", "pm_add_layernorm32_bwd", "pm_groupnorm_blocks", "pm_groupnorm_4x8_max_hw",
+    "pm_groupnorm_4x8_fwd", "pm_groupnorm_4x8_bwd",
     "pm_make_observation", "pm_gather_rows", "pm_ppo_scratch_bytes", "pm_ppo_loss", "pm_adam_scratch_bytes", "pm_adam_ema",
 ]
 
@@ -159,6 +161,19 @@ def load():
     L.pm_attn_fwd.argtypes = [vp, vp, vp, i32, i64, i32, vp]
     L.pm_attn_bwd.restype = i32
     L.pm_attn_bwd.argtypes = [vp, vp, vp, vp, vp, i32, i64, i32, vp]
+    L.pm_layernorm32_blocks.restype = i32
+    L.pm_layernorm32_blocks.argtypes = [i64]
+    L.pm_add_layernorm32_fwd.restype = i32
+    L.pm_add_layernorm32_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i64, C.c_double, vp]
+    L.pm_add_layernorm32_bwd.restype = i32
+    L.pm_add_layernorm32_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.pm_groupnorm_blocks.restype = i32
+    L.pm_groupnorm_blocks.argtypes = [i64]
+    L.pm_groupnorm_4x8_max_hw.restype = i32
+    L.pm_groupnorm_4x8_fwd.restype = i32
+    L.pm_groupnorm_4x8_fwd.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, C.c_double, i32, vp]
+    L.pm_groupnorm_4x8_bwd.restype = i32
+    L.pm_groupnorm_4x8_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
     if L.pm_abi_version() != ABI_VERSION:
         raise RuntimeError("libpacman_b200.so ABI version mismatch; rebuild")
     _lib = L

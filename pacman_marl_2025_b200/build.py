@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpacman_b200.so")
-SOURCES = ["pm_env.cu", "pm_bfs.cu", "pm_gae.cu", "pm_ppo.cu", "pm_attn.cu", "pm_pack.cpp"]
+SOURCES = ["pm_env.cu", "pm_bfs.cu", "pm_gae.cu", "pm_ppo.cu", "pm_attn.cu", "pm_norm.cu", "pm_pack.cpp"]
 HEADERS = ["pm_env_core.cuh", "pm_format.h", os.path.join("..", "..", "include", "pacman_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

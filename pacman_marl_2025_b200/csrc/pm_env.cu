@@ -3,15 +3,16 @@
 // pm_env_core.cuh; this file owns the CTA choreography, launch geometry and the
 // ABI glue (include/pacman_b200.h).
 //
-// CTA choreography (one CTA = PM_E = 32 consecutive envs, 4 warps; B200 sweeps in DESIGN.md §3.1):
-//   stage geometry masks (+ the layout record when the batch has one layout)
-//   into shared memory -> phase A (lane el of warp 0 steps env n0+el and leaves
+// CTA choreography (one CTA = PM_E = 32 consecutive envs, 4 warps; B200 sweeps in DESIGN.md §3.1 / §3.2):
+//   the rules threads issue their state loads (pm_phaseA_fetch) -> stage geometry masks (+ the layout record
+//   when the batch has one layout) into shared memory -> phase A (lane el of warp 0 steps env n0+el and leaves
 //   four snapshots in smem) -> phase B (every warp builds the observation bit
 //   string of one (env, agent) at a time in registers and streams it to HBM as
-//   fp32 planes with 128-bit stores).  Several CTAs are resident per SM, so the
-//   latency-bound phase A of one CTA runs underneath the HBM-bound phase B of
-//   the others.  (Persistent producer/consumer CTAs, a per-sub-move pipeline with
-//   named barriers, early stores of the static planes, a staggered first wave and
+//   fp32 planes with 128-bit stores).  Several CTAs are resident per SM (5 x 96 registers for the plain step,
+//   8 x 64 for the views / bots variants), so the latency-bound phase A of one CTA runs underneath the
+//   HBM-bound phase B of the others; pm_step_chain extends that overlap ACROSS launches (programmatic dependent
+//   launch + one release/acquire counter per env tile).  (Persistent producer/consumer CTAs, a per-sub-move
+//   pipeline with named barriers, early stores of the static planes, staggered first waves and
 //   higher-occupancy encoders were all measured on B200 and did not beat this
 //   plain schedule — DESIGN.md §3.1.)
 // HBM traffic per env-step: ~2 x (64 + 4*NW) B of state, 4 B actions, ~70 B of

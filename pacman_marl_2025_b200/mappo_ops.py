@@ -181,6 +181,113 @@ def attention_hd8(qkv: torch.Tensor, n_heads: int) -> torch.Tensor:
     return _Attention8.apply(qkv, n_heads)
 
 
+class _AddLayerNorm32(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, weight, bias, eps):
+        L = _lib.load()
+        dev = a.device
+        a_, b_ = a.contiguous(), (b.contiguous() if b is not None else None)
+        rows = a_.numel() // 32
+        y = torch.empty_like(a_)
+        need = a.requires_grad or (b is not None and b.requires_grad) or weight.requires_grad
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=dev) if need else None
+        with torch.cuda.device(dev):
+            _lib.check(L.pm_add_layernorm32_fwd(a_.data_ptr(), b_.data_ptr() if b_ is not None else None, weight.data_ptr(),
+                                                bias.data_ptr(), y.data_ptr(), stats.data_ptr() if need else None, rows,
+                                                float(eps), _stream(dev)), "pm_add_layernorm32_fwd")
+        if need:
+            ctx.save_for_backward(a_, b_ if b_ is not None else a_.new_empty(0), weight, stats)
+        ctx.has_b = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        a_, b_, weight, stats = ctx.saved_tensors
+        L = _lib.load()
+        dev = a_.device
+        rows = a_.numel() // 32
+        g = g.contiguous()
+        dx = torch.empty_like(a_)
+        partial = torch.empty((int(L.pm_layernorm32_blocks(rows)), 64), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.pm_add_layernorm32_bwd(a_.data_ptr(), b_.data_ptr() if ctx.has_b else None, weight.data_ptr(),
+                                                stats.data_ptr(), g.data_ptr(), dx.data_ptr(), partial.data_ptr(), rows,
+                                                _stream(dev)), "pm_add_layernorm32_bwd")
+        s = partial.sum(0)
+        return dx, (dx if ctx.has_b else None), s[:32], s[32:], None
+
+
+def _kernel_ok(*tensors) -> bool:
+    return all(t is None or (t.is_cuda and t.dtype == torch.float32 and t.data_ptr() % 16 == 0) for t in tensors)
+
+
+def add_layer_norm_d32(a: torch.Tensor, b, norm: "torch.nn.LayerNorm") -> torch.Tensor:
+    """``norm(a + b)`` for ``nn.LayerNorm(32)`` (the post-norm residuals of the critic's encoder layers,
+    `pacman_mappo_resnet.py:131-136`) as one kernel forward and one backward; ``b`` may be None.  Falls through to
+    ``norm`` itself for anything the kernel does not cover (other widths, bf16 autocast, CPU tensors)."""
+    if (a.shape[-1] != 32 or tuple(norm.normalized_shape) != (32,) or norm.weight is None or norm.bias is None
+            or torch.is_autocast_enabled("cuda") or not _kernel_ok(a, b, norm.weight, norm.bias)
+            or (b is not None and b.shape != a.shape)):
+        return norm(a if b is None else a + b)
+    return _AddLayerNorm32.apply(a, b, norm.weight, norm.bias, norm.eps)
+
+
+class _GroupNorm4x8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, weight, bias, eps, gelu):
+        L = _lib.load()
+        dev = x.device
+        x_, r_ = x.contiguous(), (res.contiguous() if res is not None else None)
+        B, HW = x_.shape[0], x_.shape[2] * x_.shape[3]
+        y = torch.empty_like(x_)
+        need = x.requires_grad or (res is not None and res.requires_grad) or weight.requires_grad
+        stats = torch.empty((B, 4, 2), dtype=torch.float32, device=dev) if need else None
+        with torch.cuda.device(dev):
+            _lib.check(L.pm_groupnorm_4x8_fwd(x_.data_ptr(), r_.data_ptr() if r_ is not None else None, weight.data_ptr(),
+                                              bias.data_ptr(), y.data_ptr(), stats.data_ptr() if need else None, B, HW,
+                                              float(eps), int(gelu), _stream(dev)), "pm_groupnorm_4x8_fwd")
+        if need:
+            ctx.save_for_backward(x_, r_ if r_ is not None else x_.new_empty(0), weight, bias, stats)
+        ctx.has_res, ctx.gelu = res is not None, int(gelu)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x_, r_, weight, bias, stats = ctx.saved_tensors
+        L = _lib.load()
+        dev = x_.device
+        B, HW = x_.shape[0], x_.shape[2] * x_.shape[3]
+        g = g.contiguous()
+        dx = torch.empty_like(x_)
+        dres = torch.empty_like(x_) if ctx.has_res else None
+        partial = torch.empty((int(L.pm_groupnorm_blocks(B)), 64), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.pm_groupnorm_4x8_bwd(x_.data_ptr(), r_.data_ptr() if ctx.has_res else None, weight.data_ptr(), bias.data_ptr(),
+                                              stats.data_ptr(), g.data_ptr(), dx.data_ptr(), dres.data_ptr() if ctx.has_res else None,
+                                              partial.data_ptr(), B, HW, ctx.gelu, _stream(dev)), "pm_groupnorm_4x8_bwd")
+        s = partial.sum(0)
+        return dx, dres, s[:32], s[32:], None, None
+
+
+def group_norm_4x8(x: torch.Tensor, norm: "torch.nn.GroupNorm", res=None, gelu: bool = False) -> torch.Tensor:
+    """``[gelu](norm(x) [+ res])`` for ``nn.GroupNorm(4, 32)`` on NCHW ``x`` - the two halves of the actor's ResidualBlock
+    (`pacman_mappo_resnet.py:49-68`) as one kernel each, forward and backward.  Falls through to the PyTorch modules for
+    anything the kernel does not cover (boards with more than ``pm_groupnorm_4x8_max_hw()`` cells, odd H*W, bf16
+    autocast, channels-last or CPU tensors)."""
+    ok = (x.dim() == 4 and x.shape[1] == 32 and norm.num_groups == 4 and norm.num_channels == 32 and norm.weight is not None
+          and not torch.is_autocast_enabled("cuda") and _kernel_ok(x, res, norm.weight, norm.bias) and x.is_contiguous()
+          and (res is None or (res.shape == x.shape and res.is_contiguous())))
+    if ok:
+        HW = x.shape[2] * x.shape[3]
+        ok = HW % 2 == 0 and HW <= int(_lib.load().pm_groupnorm_4x8_max_hw())
+    if not ok:
+        y = norm(x)
+        if res is not None:
+            y = y + res
+        return torch.nn.functional.gelu(y) if gelu else y
+    return _GroupNorm4x8.apply(x, res, norm.weight, norm.bias, norm.eps, gelu)
+
+
 class FlatAdamEMA:
     """``clip_grad_norm_`` + ``Adam.step`` + the EMA copy of the policy (`pacman_mappo_resnet.py:588-595`) as two
     kernels over flat buffers.  The module's parameters (and the EMA module's) are re-pointed to views of one flat

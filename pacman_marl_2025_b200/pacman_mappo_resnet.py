@@ -83,7 +83,13 @@ class ResidualBlock(nn.Module):
         self.conv2 = nn.Conv2d(channels, channels, 3, padding=1)
         self.gn2 = nn.GroupNorm(4, channels)
 
+    fused_norm = True      # GroupNorm + GELU (+ skip) as one kernel each (mappo_ops.group_norm_4x8) where it applies
+
     def forward(self, x):
+        if self.fused_norm and x.is_cuda:
+            from .mappo_ops import group_norm_4x8
+            h = group_norm_4x8(self.conv1(x), self.gn1, gelu=True)
+            return group_norm_4x8(self.conv2(h), self.gn2, res=x, gelu=True)
         y = self.gn2(self.conv2(self.act(self.gn1(self.conv1(x)))))
         return self.act(y + x)
 
@@ -175,6 +181,10 @@ class MAPPOAgent(nn.Module):
             q, k, v = (t.reshape(S, B * h, hd).transpose(0, 1) for t in qkv.chunk(3, dim=-1))   # [B*h, S, hd]
             p = torch.softmax(torch.bmm(q * (1.0 / math.sqrt(hd)), k.transpose(1, 2)), dim=-1)
             o = torch.bmm(p, v).transpose(0, 1).reshape(S, B, E)
+        if kernel:
+            from .mappo_ops import add_layer_norm_d32
+            x = add_layer_norm_d32(x, sa.out_proj(o), layer.norm1)
+            return add_layer_norm_d32(x, layer.linear2(nn.functional.relu(layer.linear1(x))), layer.norm2)
         x = layer.norm1(x + sa.out_proj(o))
         return layer.norm2(x + layer.linear2(nn.functional.relu(layer.linear1(x))))
 

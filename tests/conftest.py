@@ -19,6 +19,12 @@ def pytest_collection_modifyitems(config, items):
     except Exception:  # pragma: no cover
         has_gpu = False
     if has_gpu:
+        # a kernel that hangs must cost minutes, not the session: every GPU test gets a wall-clock limit
+        # (pytest-timeout; the largest full-size parity test takes ~25 s)
+        if config.pluginmanager.hasplugin("timeout"):
+            for item in items:
+                if "gpu" in item.keywords and item.get_closest_marker("timeout") is None:
+                    item.add_marker(pytest.mark.timeout(300))
         return
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for item in items:

@@ -185,7 +185,7 @@ def test_attention_kernels_match_multihead_attention_math(S, B, h):
     ref = torch.bmm(p, v).transpose(0, 1).reshape(S, B, E)
     ref.backward(dout.double())
     tol = lambda t: 1e-5 * float(t.abs().max())
-    assert float((out.double() - ref).abs().max()) <= tol(ref)
+    assert float((out.detach().double() - ref.detach()).abs().max()) <= tol(ref.detach())
     assert float((qkv.grad.double() - x.grad).abs().max()) <= tol(x.grad)
 
 
@@ -213,4 +213,95 @@ def test_critic_with_attention_kernel_equals_the_module_path():
             assert float((gk - gm).abs().max()) <= 2e-4 * float(gm.abs().max()) + 1e-6, n
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        M.MAPPOAgent.attn_impl = "auto"
+
+
+@pytest.mark.parametrize("rows,with_b", [(154 * 64, True), (7, True), (1, False), (100003, False)])
+def test_add_layernorm32_kernel_matches_torch(rows, with_b):
+    """pm_add_layernorm32_fwd / _bwd == nn.LayerNorm(32)(a + b) (the post-norm residual of the reference critic's encoder
+    layers, `pacman_mappo_resnet.py:131-136`): output and every gradient against an fp64 evaluation, 1e-5 of the scale."""
+    from pacman_marl_2025_b200.mappo_ops import add_layer_norm_d32
+    g = torch.Generator(device="cuda").manual_seed(rows)
+    norm = torch.nn.LayerNorm(32).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(32, generator=g, device="cuda") * 0.5 + 1.0)
+        norm.bias.copy_(torch.randn(32, generator=g, device="cuda") * 0.3)
+    a = (torch.randn((rows, 32), generator=g, device="cuda") * 2 + 0.5).requires_grad_(True)
+    b = torch.randn((rows, 32), generator=g, device="cuda").requires_grad_(True) if with_b else None
+    dy = torch.randn((rows, 32), generator=g, device="cuda")
+    y = add_layer_norm_d32(a, b, norm)
+    y.backward(dy)
+    got = [y.detach(), a.grad, norm.weight.grad.clone(), norm.bias.grad.clone()] + ([b.grad] if with_b else [])
+    norm.zero_grad()
+    n64 = torch.nn.LayerNorm(32).cuda().double()
+    n64.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+    a64 = a.detach().double().requires_grad_(True)
+    b64 = b.detach().double().requires_grad_(True) if with_b else None
+    r = n64(a64 + b64 if with_b else a64)
+    r.backward(dy.double())
+    want = [r.detach(), a64.grad, n64.weight.grad, n64.bias.grad] + ([b64.grad] if with_b else [])
+    for k, (x, w) in enumerate(zip(got, want)):
+        assert float((x.double() - w).abs().max()) <= 2e-5 * max(1.0, float(w.abs().max())), k
+
+
+@pytest.mark.parametrize("H,W,B", [(11, 14, 96), (7, 20, 33), (2, 4, 5), (1, 2, 3), (12, 16, 17)])
+@pytest.mark.parametrize("res,gelu", [(False, True), (True, True), (False, False)])
+def test_groupnorm_4x8_kernel_matches_torch(H, W, B, res, gelu):
+    """pm_groupnorm_4x8_fwd / _bwd == [gelu](nn.GroupNorm(4, 32)(x) [+ res]) - the two halves of the reference actor's
+    ResidualBlock (`:49-68`) - output and every gradient against fp64; H*W = 154 makes float4s straddle channels."""
+    from pacman_marl_2025_b200.mappo_ops import group_norm_4x8
+    g = torch.Generator(device="cuda").manual_seed(H * 100 + W + B)
+    norm = torch.nn.GroupNorm(4, 32).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(32, generator=g, device="cuda") * 0.5 + 1.0)
+        norm.bias.copy_(torch.randn(32, generator=g, device="cuda") * 0.3)
+    x = (torch.randn((B, 32, H, W), generator=g, device="cuda") * 1.5 + 0.2).requires_grad_(True)
+    r = torch.randn((B, 32, H, W), generator=g, device="cuda").requires_grad_(True) if res else None
+    dy = torch.randn((B, 32, H, W), generator=g, device="cuda")
+    y = group_norm_4x8(x, norm, res=r, gelu=gelu)
+    y.backward(dy)
+    got = [y.detach(), x.grad, norm.weight.grad.clone(), norm.bias.grad.clone()] + ([r.grad] if res else [])
+    n64 = torch.nn.GroupNorm(4, 32).cuda().double()
+    n64.load_state_dict({k: v.double() for k, v in norm.state_dict().items()})
+    x64 = x.detach().double().requires_grad_(True)
+    r64 = r.detach().double().requires_grad_(True) if res else None
+    z = n64(x64)
+    if res:
+        z = z + r64
+    if gelu:
+        z = torch.nn.functional.gelu(z)
+    z.backward(dy.double())
+    want = [z.detach(), x64.grad, n64.weight.grad, n64.bias.grad] + ([r64.grad] if res else [])
+    for k, (a, w) in enumerate(zip(got, want)):
+        assert float((a.double() - w).abs().max()) <= 2e-5 * max(1.0, float(w.abs().max())), k
+
+
+def test_networks_with_fused_norm_kernels_equal_the_plain_modules():
+    """MAPPOAgent with the library's normalisation / attention kernels in the loop == the same modules evaluated by
+    PyTorch alone (attn_impl 'module', ResidualBlock.fused_norm False): logits, values and every parameter gradient;
+    a 20 x 20 board falls through to the PyTorch GroupNorm and must agree trivially."""
+    from pacman_marl_2025_b200 import pacman_mappo_resnet as M
+    prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        for H, W in ((11, 14), (20, 20)):
+            torch.manual_seed(9)
+            agent = M.MAPPOAgent((8, H, W), 5, 2).cuda()
+            x = (torch.rand(48, 8, H, W, device="cuda") < 0.2).float()
+            res = {}
+            for fused in (False, True):
+                M.ResidualBlock.fused_norm = fused
+                agent.attn_impl = "kernel" if fused else "module"
+                agent.zero_grad(set_to_none=True)
+                lg, v = agent.logits(x), agent.get_value(x)
+                ((lg * torch.linspace(-1, 1, 5, device="cuda")).sum() + (v * torch.linspace(-1, 1, 48, device="cuda")).sum()).backward()
+                res[fused] = (lg.detach().clone(), v.detach().clone(), {n: p.grad.clone() for n, p in agent.named_parameters()})
+            np.testing.assert_allclose(res[True][0].cpu().numpy(), res[False][0].cpu().numpy(), rtol=2e-4, atol=2e-5)
+            np.testing.assert_allclose(res[True][1].cpu().numpy(), res[False][1].cpu().numpy(), rtol=2e-4, atol=2e-5)
+            for n, gm in res[False][2].items():
+                gk = res[True][2][n]
+                assert float((gk - gm).abs().max()) <= 3e-4 * float(gm.abs().max()) + 1e-6, (H, W, n)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = prev
+        M.ResidualBlock.fused_norm = True
         M.MAPPOAgent.attn_impl = "auto"
