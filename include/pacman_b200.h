@@ -385,7 +385,7 @@ int pm_add_layernorm32_fwd(const float *a, const float *b, const float *gamma, c
                            int64_t rows, double eps, pm_stream_t stream);
 int pm_add_layernorm32_bwd(const float *a, const float *b, const float *gamma, const float *stats, const float *dy, float *dx,
                            float *partial, int64_t rows, pm_stream_t stream);
-/* y = [gelu](GroupNorm(4, 32)(x) [+ res]) on [n_samples][32][HW] (NCHW, HW even, <= pm_groupnorm_4x8_max_hw()): the
+/* y = [gelu](GroupNorm(4, 32)(x) [+ res]) on [n_samples][32][HW] (NCHW, HW even, <= pm_groupnorm_4x8_max_hw() = 1024): the
  * ResidualBlock of the actor (`:49-68`): `act(gn1(conv1(x)))` (res NULL, gelu 1) and `act(gn2(conv2(h)) + x)` (res = x,
  * gelu 1).  stats [n_samples][4][2] = (mean, rstd) per group.  Backward: dx (w.r.t. x), dres (w.r.t. res, NULL when res
  * is NULL); partial is [pm_groupnorm_blocks(n_samples)][64] floats whose column sums are dgamma and dbeta.        */

@@ -272,8 +272,7 @@ class _GroupNorm4x8(torch.autograd.Function):
 def group_norm_4x8(x: torch.Tensor, norm: "torch.nn.GroupNorm", res=None, gelu: bool = False) -> torch.Tensor:
     """``[gelu](norm(x) [+ res])`` for ``nn.GroupNorm(4, 32)`` on NCHW ``x`` - the two halves of the actor's ResidualBlock
     (`pacman_mappo_resnet.py:49-68`) as one kernel each, forward and backward.  Falls through to the PyTorch modules for
-    anything the kernel does not cover (boards with more than ``pm_groupnorm_4x8_max_hw()`` cells, odd H*W, bf16
-    autocast, channels-last or CPU tensors)."""
+    anything the kernels do not cover (odd H*W, bf16 autocast, channels-last or CPU tensors)."""
     ok = (x.dim() == 4 and x.shape[1] == 32 and norm.num_groups == 4 and norm.num_channels == 32 and norm.weight is not None
           and not torch.is_autocast_enabled("cuda") and _kernel_ok(x, res, norm.weight, norm.bias) and x.is_contiguous()
           and (res is None or (res.shape == x.shape and res.is_contiguous())))

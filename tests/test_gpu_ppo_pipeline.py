@@ -244,11 +244,12 @@ def test_add_layernorm32_kernel_matches_torch(rows, with_b):
         assert float((x.double() - w).abs().max()) <= 2e-5 * max(1.0, float(w.abs().max())), k
 
 
-@pytest.mark.parametrize("H,W,B", [(11, 14, 96), (7, 20, 33), (2, 4, 5), (1, 2, 3), (12, 16, 17)])
+@pytest.mark.parametrize("H,W,B", [(11, 14, 96), (7, 20, 33), (2, 4, 5), (1, 2, 3), (12, 16, 17), (20, 20, 21), (32, 32, 3), (13, 18, 9)])
 @pytest.mark.parametrize("res,gelu", [(False, True), (True, True), (False, False)])
 def test_groupnorm_4x8_kernel_matches_torch(H, W, B, res, gelu):
     """pm_groupnorm_4x8_fwd / _bwd == [gelu](nn.GroupNorm(4, 32)(x) [+ res]) - the two halves of the reference actor's
-    ResidualBlock (`:49-68`) - output and every gradient against fp64; H*W = 154 makes float4s straddle channels."""
+    ResidualBlock (`:49-68`) - output and every gradient against fp64; H*W = 154 makes float4s straddle channels, boards
+    above 192 cells (20 x 20, 32 x 32, 13 x 18) take the CTA-per-group kernels."""
     from pacman_marl_2025_b200.mappo_ops import group_norm_4x8
     g = torch.Generator(device="cuda").manual_seed(H * 100 + W + B)
     norm = torch.nn.GroupNorm(4, 32).cuda()
@@ -279,7 +280,7 @@ def test_groupnorm_4x8_kernel_matches_torch(H, W, B, res, gelu):
 def test_networks_with_fused_norm_kernels_equal_the_plain_modules():
     """MAPPOAgent with the library's normalisation / attention kernels in the loop == the same modules evaluated by
     PyTorch alone (attn_impl 'module', ResidualBlock.fused_norm False): logits, values and every parameter gradient;
-    a 20 x 20 board falls through to the PyTorch GroupNorm and must agree trivially."""
+    on smallCapture's 11 x 14 (warp-per-group GroupNorm) and on a 20 x 20 board (CTA-per-group)."""
     from pacman_marl_2025_b200 import pacman_mappo_resnet as M
     prev = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
