@@ -30,11 +30,12 @@
 #define PM_THREADS 128
 #endif
 #ifndef PM_MIN_CTAS
-#define PM_MIN_CTAS 8                             // 64 registers/thread: 8 CTAs x 4 warps per SM (reset / observe / views variants)
-#endif
-#ifndef PM_MIN_CTAS_STEP
-#define PM_MIN_CTAS_STEP 5                        // the plain step (fp32 observations): 96 registers, no spills in the rules
-#endif                                            // phase, 5 CTAs per SM - round-2 B200 sweep, see DESIGN.md 3.1
+#define PM_MIN_CTAS 5                             // 96 registers/thread, no spills in the rules phase, 5 CTAs x 4 warps per SM:
+#endif                                            // the step with fp32 observations (with or without views), reset, observe -
+                                                  // round-2 B200 sweep, DESIGN.md 3.2 (round 1: 8 CTAs x 64 registers)
+#ifndef PM_MIN_CTAS_VIEWS_ONLY
+#define PM_MIN_CTAS_VIEWS_ONLY 8                  // the views-only step (64 envs per CTA) is bound by its rules phase and by
+#endif                                            // instruction issue, not by stores: more resident warps win (86 vs 90 us)
 #ifndef PM_MIN_CTAS_BOTS
 #define PM_MIN_CTAS_BOTS 8                         // step with the baselineTeam look-ahead (B200 sweep: 4 -> 448 us, 6 -> 400, 8 -> 350 on tiny)
 #endif
@@ -70,7 +71,7 @@ extern "C" int pm_trace_set(unsigned long long *buf) { return (int)cudaMemcpyToS
 template <int MODE, int BOTS, int VIEWS, int E>
 __global__ void __launch_bounds__(PM_THREADS, BOTS ? PM_MIN_CTAS_BOTS
                                                     : MODE == PM_MODE_OBSERVE ? PM_MIN_CTAS_OBS
-                                                    : (MODE == PM_MODE_STEP && !VIEWS) ? PM_MIN_CTAS_STEP : PM_MIN_CTAS)
+                                                    : (MODE == PM_MODE_STEP && VIEWS && E == PM_E_RULES) ? PM_MIN_CTAS_VIEWS_ONLY : PM_MIN_CTAS)
 pm_env_kernel(const PmParams P) {
     extern __shared__ __align__(16) uint32_t sm[];
     const PmSmem M = pm_smem_map(P.HW, P.LS, E, P.has_caps, P.L, 4 + BOTS + 2 * VIEWS, BOTS ? P.dist_stage_words : 0, VIEWS);
