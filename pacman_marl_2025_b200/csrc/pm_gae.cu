@@ -1,9 +1,9 @@
 // pm_gae.cu — rollout post-processing kernels (sm_100a).
 //
 //  pm_gae      compute_gae (pacman_mappo_resnet.py:277-290) for M independent
-//              columns of a [T][M] rollout buffer: one thread per column walks t
-//              from T-1 down to 0, so every load/store of a warp is a coalesced
-//              128 B row segment.  20 algorithmic bytes per (t, column): read
+//              columns of a [T][M] rollout buffer: one thread per column (per four
+//              adjacent columns for wide buffers) walks t from T-1 down to 0, so every
+//              load/store of a warp is a coalesced 128 B / 512 B row segment.  20 algorithmic bytes per (t, column): read
 //              reward, value, done; write advantage, return.  The arithmetic
 //              reproduces torch's fp32 op order (Python float scalars are rounded
 //              to fp32 before meeting a tensor; float*float stays double), with
@@ -17,40 +17,61 @@
 
 #define GAE_UNROLL 8
 
+// V columns per thread (1 or 4): with V = 4 every load / store is 128-bit and a thread keeps 3 x GAE_UNROLL of them in
+// flight, which is what it takes to hide HBM latency with M/4 threads; the arithmetic per column is the same sequence
+// of _rn operations either way, so results do not depend on V.
+template <int V> struct GaeVec;
+template <> struct GaeVec<1> { typedef float T; };
+template <> struct GaeVec<4> { typedef float4 T; };
+__device__ __forceinline__ float gae_get(const float &v, int) { return v; }
+__device__ __forceinline__ float gae_get(const float4 &v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+__device__ __forceinline__ void gae_set(float &v, int, float x) { v = x; }
+__device__ __forceinline__ void gae_set(float4 &v, int i, float x) { if (i == 0) v.x = x; else if (i == 1) v.y = x; else if (i == 2) v.z = x; else v.w = x; }
+
+template <int V>
 __global__ void __launch_bounds__(128) pm_gae_kernel(const float *__restrict__ rew, const float *__restrict__ val,
                                                      const float *__restrict__ done, const float *__restrict__ last_value,
                                                      float gamma_f, float gl_f, double gamma_d, float *__restrict__ adv,
                                                      float *__restrict__ ret, int T, int64_t M) {
-    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    typedef typename GaeVec<V>::T vec;
+    const int64_t m = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;     // first of this thread's V columns
     if (m >= M) return;
     // t = T-1 bootstraps from last_value: gamma * next_val is Python float * float (double), then meets a tensor
-    float gv_next = (float)(gamma_d * (double)last_value[m]);
+    float gv_next[V], lastgaelam[V], v_next[V];
+#pragma unroll
+    for (int c = 0; c < V; ++c) { gv_next[c] = (float)(gamma_d * (double)last_value[m + c]); lastgaelam[c] = 0.0f; v_next[c] = 0.0f; }
     bool first = true;
-    float lastgaelam = 0.0f;
-    float v_next = 0.0f;
     for (int t0 = T - 1; t0 >= 0; t0 -= GAE_UNROLL) {
-        float r[GAE_UNROLL], v[GAE_UNROLL], d[GAE_UNROLL];
+        vec r[GAE_UNROLL], v[GAE_UNROLL], d[GAE_UNROLL];
 #pragma unroll
         for (int u = 0; u < GAE_UNROLL; ++u) {           // independent loads first: GAE_UNROLL rows in flight per thread
             const int t = t0 - u;
             if (t >= 0) {
                 const size_t o = (size_t)t * M + m;
-                r[u] = __ldcs(rew + o); v[u] = __ldcs(val + o); d[u] = __ldcs(done + o);
+                r[u] = __ldcs(reinterpret_cast<const vec *>(rew + o)); v[u] = __ldcs(reinterpret_cast<const vec *>(val + o));
+                d[u] = __ldcs(reinterpret_cast<const vec *>(done + o));
             }
         }
 #pragma unroll
         for (int u = 0; u < GAE_UNROLL; ++u) {
             const int t = t0 - u;
             if (t >= 0) {
-                const float nonterm = __fsub_rn(1.0f, d[u]);
-                const float gv = first ? gv_next : __fmul_rn(gamma_f, v_next);
+                vec a_out, r_out;
+#pragma unroll
+                for (int c = 0; c < V; ++c) {
+                    const float vc = gae_get(v[u], c);
+                    const float nonterm = __fsub_rn(1.0f, gae_get(d[u], c));
+                    const float gv = first ? gv_next[c] : __fmul_rn(gamma_f, v_next[c]);
+                    const float delta = __fsub_rn(__fadd_rn(gae_get(r[u], c), __fmul_rn(gv, nonterm)), vc);
+                    lastgaelam[c] = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl_f, nonterm), lastgaelam[c]));
+                    gae_set(a_out, c, lastgaelam[c]);
+                    gae_set(r_out, c, __fadd_rn(lastgaelam[c], vc));
+                    v_next[c] = vc;
+                }
                 first = false;
-                const float delta = __fsub_rn(__fadd_rn(r[u], __fmul_rn(gv, nonterm)), v[u]);
-                lastgaelam = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl_f, nonterm), lastgaelam));
                 const size_t o = (size_t)t * M + m;
-                __stcs(adv + o, lastgaelam);
-                __stcs(ret + o, __fadd_rn(lastgaelam, v[u]));
-                v_next = v[u];
+                __stcs(reinterpret_cast<vec *>(adv + o), a_out);
+                __stcs(reinterpret_cast<vec *>(ret + o), r_out);
             }
         }
     }
@@ -59,9 +80,16 @@ __global__ void __launch_bounds__(128) pm_gae_kernel(const float *__restrict__ r
 extern "C" int pm_gae(const float *rew, const float *val, const float *done, const float *last_value, double gamma,
                       double lam, float *adv, float *ret, int T, int64_t M, pm_stream_t stream) {
     if (!rew || !val || !done || !last_value || !adv || !ret || T <= 0 || M <= 0) return PM_EINVAL;
-    const unsigned grid = (unsigned)((M + 127) / 128);
-    pm_gae_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(rew, val, done, last_value, (float)gamma, (float)(gamma * lam),
-                                                          gamma, adv, ret, T, M);
+    const bool aligned = ((((size_t)rew | (size_t)val | (size_t)done | (size_t)adv | (size_t)ret) & 15) == 0) && (M & 3) == 0;
+    if (aligned && M >= 4 * 128 * 64) {                  // enough columns to give every SM work at four per thread
+        const unsigned grid = (unsigned)((M / 4 + 127) / 128);
+        pm_gae_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>(rew, val, done, last_value, (float)gamma, (float)(gamma * lam),
+                                                                 gamma, adv, ret, T, M);
+    } else {
+        const unsigned grid = (unsigned)((M + 127) / 128);
+        pm_gae_kernel<1><<<grid, 128, 0, (cudaStream_t)stream>>>(rew, val, done, last_value, (float)gamma, (float)(gamma * lam),
+                                                                 gamma, adv, ret, T, M);
+    }
     return (int)cudaGetLastError();
 }
 

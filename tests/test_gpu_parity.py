@@ -345,6 +345,21 @@ def test_gae_bit_exact_vs_reference_and_oracle():
                            torch.as_tensor(lv).cuda())
     np.testing.assert_array_equal(adv.cpu().numpy().view(np.uint32), oa.view(np.uint32))
     np.testing.assert_array_equal(ret.cpu().numpy().view(np.uint32), orr.view(np.uint32))
+    # wide buffers take four columns per thread (128-bit accesses); a width that is not a multiple of four, or an
+    # unaligned view, falls back to one: the same bits either way
+    for T, M, off in ((48, 65536, 0), (33, 65538, 0), (40, 65536, 1)):
+        r = rng.standard_normal((T, M + off)).astype(np.float32)
+        v = rng.standard_normal((T, M + off)).astype(np.float32)
+        d = (rng.random((T, M + off)) < 0.05).astype(np.float32)
+        lv = rng.standard_normal(M + off).astype(np.float32)
+        rt, vt, dt, lt = (torch.as_tensor(a).cuda() for a in (r, v, d, lv))
+        if off:
+            rt, vt, dt, lt = rt[:, off:], vt[:, off:], dt[:, off:], lt[off:]
+            r, v, d, lv = r[:, off:], v[:, off:], d[:, off:], lv[off:]
+        oa, orr = oracle.gae(np.ascontiguousarray(r), np.ascontiguousarray(v), np.ascontiguousarray(d), np.ascontiguousarray(lv))
+        adv, ret = compute_gae(rt, vt, dt, lt)
+        np.testing.assert_array_equal(adv.cpu().numpy().view(np.uint32), oa.view(np.uint32), err_msg=f"{T}x{M}+{off}")
+        np.testing.assert_array_equal(ret.cpu().numpy().view(np.uint32), orr.view(np.uint32))
 
 
 def test_adv_norm_vs_reference():
