@@ -106,27 +106,56 @@ __device__ __forceinline__ float block_sum(float x, float *red) {
     return s;
 }
 
-__global__ void __launch_bounds__(256) pm_adv_norm_kernel(const float *__restrict__ adv, const int64_t *__restrict__ inds,
+// CACHE = 1: the minibatch's gathered advantages (mb floats) are kept in shared memory after the first pass, so the
+// random 4-byte gathers - each costs a 32-byte sector of HBM traffic - happen once instead of three times.
+template <int CACHE>
+__global__ void __launch_bounds__(1024) pm_adv_norm_kernel(const float *__restrict__ adv, const int64_t *__restrict__ inds,
                                                           float *__restrict__ out, int64_t n, int mb) {
-    __shared__ float red[8];
+    extern __shared__ float vals[];
+    __shared__ float red[32];
     const int64_t s = (int64_t)blockIdx.x * mb;
     const int k = (int)min((int64_t)mb, n - s);
     float part = 0.f;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) part += adv[inds[s + i]];
+    // the gather is latency-bound (index, then a random 4-byte read): eight independent pairs in flight per thread
+    for (int i0 = threadIdx.x; i0 < k; i0 += 8 * blockDim.x) {
+        int64_t ix[8];
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; ix[u] = i < k ? __ldg(inds + s + i) : -1; }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = ix[u] >= 0 ? __ldg(adv + ix[u]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < k) { if (CACHE) vals[i] = a[u]; part += a[u]; }
+        }
+    }
     const float mean = block_sum(part, red) / (float)k;
     part = 0.f;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) { const float dlt = adv[inds[s + i]] - mean; part += dlt * dlt; }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) { const float dlt = (CACHE ? vals[i] : adv[inds[s + i]]) - mean; part += dlt * dlt; }
     // unbiased variance; a trailing group of ONE sample has none (torch.std gives NaN there): treat it as 0, so the
     // lone sample normalises to (a - a) / 1e-8 = 0 instead of poisoning the loss
     const float ssq = block_sum(part, red);
     const float var = k > 1 ? ssq / (float)(k - 1) : 0.0f;
     const float denom = sqrtf(var) + 1e-8f;
-    for (int i = threadIdx.x; i < k; i += blockDim.x) out[s + i] = (adv[inds[s + i]] - mean) / denom;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[s + i] = ((CACHE ? vals[i] : adv[inds[s + i]]) - mean) / denom;
 }
 
 extern "C" int pm_adv_norm(const float *adv, const int64_t *inds, float *out, int64_t n, int mb, pm_stream_t stream) {
     if (!adv || !inds || !out || n <= 0 || mb <= 1) return PM_EINVAL;
     const unsigned grid = (unsigned)((n + mb - 1) / mb);
-    pm_adv_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(adv, inds, out, n, mb);
+    const size_t smem = (size_t)mb * sizeof(float);
+    // about eight samples per thread (B200, 33.5 M shuffled samples: 0.37-0.40 ms for minibatches of 512 ... 16 384;
+    // 256 threads on 8 192 samples took 0.93 ms)
+    const int threads = mb >= 8192 ? 1024 : mb >= 4096 ? 512 : 256;
+    if (smem <= 160 * 1024) {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(pm_adv_norm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+        pm_adv_norm_kernel<1><<<grid, threads, smem, (cudaStream_t)stream>>>(adv, inds, out, n, mb);
+    } else {
+        pm_adv_norm_kernel<0><<<grid, threads, 0, (cudaStream_t)stream>>>(adv, inds, out, n, mb);
+    }
     return (int)cudaGetLastError();
 }

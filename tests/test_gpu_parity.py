@@ -368,6 +368,18 @@ def test_adv_norm_vs_reference():
     out = normalize_advantages(torch.as_tensor(z["norm_adv"]).cuda(), torch.as_tensor(z["norm_inds"]).cuda(),
                                int(z["norm_mb"]))
     np.testing.assert_allclose(out.cpu().numpy(), z["norm_out"], rtol=1e-5, atol=1e-6)   # north_star tolerance
+    # larger shuffles against the reference's expression (`:577`), minibatches that fit the kernel's shared-memory cache
+    # (8 192, 512) and one that does not (50 000), ragged tails included
+    g = torch.Generator(device="cuda").manual_seed(4)
+    adv = torch.randn(300_001, generator=g, device="cuda") * 3 + 0.7
+    idx = torch.randperm(adv.numel(), generator=g, device="cuda")
+    for mb in (8192, 512, 50_000):
+        got = normalize_advantages(adv, idx, mb)
+        for s0 in range(0, adv.numel(), mb):
+            a = adv[idx[s0:s0 + mb]].double()
+            if a.numel() > 1:
+                want = (a - a.mean()) / (a.std() + 1e-8)
+                assert float((got[s0:s0 + mb].double() - want).abs().max()) <= 2e-5, (mb, s0)
 
 
 def test_reference_shaped_single_env_api():
