@@ -278,13 +278,25 @@ def other_kernels(torch, device, N, peak):
         ev1.record(); torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / reps
     # (3) all-pairs maze distances: one shipped board, and 256 distinct mazeGenerator boards in one launch (config 4)
+    # `ms`: the call a user makes (host-side packing of the boards + upload + kernel); `kernel_ms`: pm_distances alone on
+    # boards already packed on the device (what an env does with its own table)
+    from pacman_marl_2025_b200.gymPacMan import pack_tables
+    import numpy as _np
+
+    def dev_table(lays):
+        return torch.from_numpy(pack_tables(lays)[1].view(_np.int32)).to(device)
     blox = [getLayout(layout_path("bloxCapture"))]
     ms = timed(lambda: compute_distances(blox, device=device), 20)
-    out["bfs_bloxCapture"] = {"ms": ms, "n_open": 190, "reference_python_ms_survey_container": 100.0}
+    tb, ob = dev_table(blox), compute_distances(blox, device=device)
+    kms = timed(lambda: compute_distances(blox, device=device, table=tb, out=ob), 50)
+    out["bfs_bloxCapture"] = {"ms": ms, "kernel_ms": kms, "n_open": 190, "reference_python_ms_survey_container": 100.0}
     mazes = [Layout(mazeGenerator.generateMaze(1000 + s).split("\n")) for s in range(256)]
     tabs = compute_distances(mazes, device=device)
     ms = timed(lambda: compute_distances(mazes, device=device), 5)
-    out["bfs_256_random_mazes"] = {"ms": ms, "ms_per_maze": ms / 256, "table_bytes": int(tabs.dist.numel() * 2),
+    tm = dev_table(mazes)
+    kms = timed(lambda: compute_distances(mazes, device=device, table=tm, out=tabs), 20)
+    out["bfs_256_random_mazes"] = {"ms": ms, "ms_per_maze": ms / 256, "kernel_ms": kms, "kernel_us_per_maze": kms * 1e3 / 256,
+                                   "table_bytes": int(tabs.dist.numel() * 2),
                                    "reference_python_ms_per_maze_survey_container": "190-335"}
     # (4) GAE over a [T, M] rollout: 20 algorithmic bytes per element (read r, V, done; write A, ret)
     T, M = 256, 2 * N

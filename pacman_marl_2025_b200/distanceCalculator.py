@@ -48,27 +48,40 @@ class DistanceTables:
         return np.where(m == UNREACHABLE, -1, m).astype(np.int32)
 
 
-def compute_distances(layouts: Sequence[_layout.Layout], device=None, nmax: int | None = None) -> DistanceTables:
-    """distanceCalculator.computeDistances for every layout in ``layouts`` (same W x H)."""
+def compute_distances(layouts: Sequence[_layout.Layout], device=None, nmax: int | None = None, table: torch.Tensor | None = None,
+                      out: DistanceTables | None = None) -> DistanceTables:
+    """distanceCalculator.computeDistances for every layout in ``layouts`` (same W x H).  ``table``: the layouts' packed
+    records already on the device (``gymPacMan.pack_tables`` -> int32 [L, LS]), e.g. an env's own table - skips the
+    host-side packing and the upload.  ``out``: a DistanceTables of a previous call over boards of the same shape whose
+    buffers are written again (then the call is one kernel launch)."""
     L = _lib.load()
     if not torch.cuda.is_available():
         raise RuntimeError("compute_distances needs a CUDA device; there is no CPU fallback")
     dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-    _, table, _ = pack_tables(layouts)
     W, H = layouts[0].width, layouts[0].height
-    if nmax is None:
-        nmax = max(int((~lay.walls.array).sum()) for lay in layouts)
-    nmax = (int(nmax) + 7) & ~7
-    tab = torch.from_numpy(table.view(np.int32)).to(dev)
     nl = len(layouts)
-    n_open = torch.zeros(nl, dtype=torch.int32, device=dev)
-    node_of = torch.empty((nl, W * H), dtype=torch.int16, device=dev)
-    dist = torch.empty((nl, nmax, nmax), dtype=torch.int16, device=dev)
+    if table is None:
+        _, packed, _ = pack_tables(layouts)
+        table = torch.from_numpy(packed.view(np.int32)).to(dev)
+    elif table.device != dev or table.dtype != torch.int32 or table.shape[0] != nl or not table.is_contiguous():
+        raise ValueError("table must be the contiguous int32 [L, LS] device table of these layouts")
+    if out is not None:
+        if (out.W, out.H) != (W, H) or out.dist.shape[0] != nl or out.dist.device != dev:
+            raise ValueError("out does not match these layouts")
+        n_open, node_of, dist = out.n_open, out.node_of_cell, out.dist
+        nmax = int(dist.shape[1])
+    else:
+        if nmax is None:
+            nmax = max(int((~lay.walls.array).sum()) for lay in layouts)
+        nmax = (int(nmax) + 7) & ~7
+        n_open = torch.zeros(nl, dtype=torch.int32, device=dev)
+        node_of = torch.empty((nl, W * H), dtype=torch.int16, device=dev)
+        dist = torch.empty((nl, nmax, nmax), dtype=torch.int16, device=dev)
     with torch.cuda.device(dev):
         st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(L.pm_distances(W, H, tab.data_ptr(), nl, n_open.data_ptr(), node_of.data_ptr(), dist.data_ptr(),
+        _lib.check(L.pm_distances(W, H, table.data_ptr(), nl, n_open.data_ptr(), node_of.data_ptr(), dist.data_ptr(),
                                   nmax, st), "pm_distances")
-    return DistanceTables(W, H, n_open, node_of, dist)
+    return out if out is not None else DistanceTables(W, H, n_open, node_of, dist)
 
 
 def manhattanDistance(x, y):

@@ -473,7 +473,7 @@ class gymPacMan_parallel_env:
         d.bot_first_best = int(self._opponent_tiebreak == "first")
         if max(k0, k2) >= 2 and getattr(self, "_dist_for", None) is not self._layouts:
             from .distanceCalculator import compute_distances
-            self._dist_tables = compute_distances(self._layouts, device=self.device)
+            self._dist_tables = compute_distances(self._layouts, device=self.device, table=self._table)
             self._dist_for = self._layouts
         if max(k0, k2) >= 2:
             t = self._dist_tables
