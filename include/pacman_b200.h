@@ -65,6 +65,11 @@ int pm_pack_geom(int W, int H, uint32_t *out);
 /* One `.lay` board (layout.py:95-130): text = H rows of W chars, row 0 = top.
  * Writes pm_layout_words(W,H) words; *has_caps (optional) = board has capsules. */
 int pm_pack_layout(const char *text, int W, int H, uint32_t *out, int *has_caps);
+/* L boards of one size at once (a pool of mazeGenerator boards): texts = n_layouts x (H*W) characters back to back,
+ * out = n_layouts x pm_layout_words(W,H) words.  Optional outputs: *has_caps = any board has a capsule, *max_open =
+ * the largest number of open cells of any board (the nmax pm_distances needs), *bad = index of the first malformed
+ * board when the call returns a PM_E* code.                                                                    */
+int pm_pack_layouts(const char *texts, int W, int H, int n_layouts, uint32_t *out, int *has_caps, int *max_open, int *bad);
 
 /* ---- batch descriptor ---------------------------------------------------- */
 typedef struct pm_env_desc {

@@ -19,7 +19,7 @@ PM_ERRORS = {-1: "PM_EINVAL (bad argument)", -2: "PM_ELAYOUT (malformed layout t
 ABI_VERSION = 8
 
 EXPORTS = [
-    "pm_abi_version", "pm_geom_words", "pm_layout_words", "pm_state_bytes", "pm_pack_geom", "pm_pack_layout",
+    "pm_abi_version", "pm_geom_words", "pm_layout_words", "pm_state_bytes", "pm_pack_geom", "pm_pack_layout", "pm_pack_layouts",
     "pm_reset", "pm_step", "pm_observe", "pm_step_host", "pm_get_state",
     "pm_set_state", "pm_distances", "pm_gae", "pm_adv_norm", "pm_pipe_create", "pm_pipe_destroy",
     "pm_step_host_pipelined", "pm_step_host_mapped", "pm_step_host_mapped_async", "pm_observe_views",
@@ -89,6 +89,10 @@ def declare_pack_api(L):
     L.pm_pack_geom.argtypes = [C.c_int, C.c_int, C.c_void_p]
     L.pm_pack_layout.restype = C.c_int
     L.pm_pack_layout.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    if hasattr(L, "pm_pack_layouts"):
+        L.pm_pack_layouts.restype = C.c_int
+        L.pm_pack_layouts.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_int)]
     return L
 
 

@@ -138,3 +138,26 @@ extern "C" int pm_pack_layout(const char *text, int W, int H, uint32_t *out, int
     (void)NW;
     return 0;
 }
+
+// L boards of one size at once: texts = L x (H*W) characters back to back, out = L x pm_layout_words words.
+// *has_caps (optional) = any board has a capsule; *max_open (optional) = the largest number of open (non-wall) cells of
+// any board - the row count pm_distances needs.  Stops at the first malformed board: returns its PM_E* code and its
+// index in *bad (optional).
+extern "C" int pm_pack_layouts(const char *texts, int W, int H, int n_layouts, uint32_t *out, int *has_caps, int *max_open, int *bad) {
+    if (!texts || !out || n_layouts <= 0) return PM_EINVAL;
+    if (int rc = check_dims(W, H)) return rc;
+    const int HW = W * H, LS = pm_layout_words_(HW), NW = pm_nw(HW);
+    int any_caps = 0, mo = 0;
+    for (int l = 0; l < n_layouts; ++l) {
+        int hc = 0;
+        uint32_t *o = out + (size_t)l * LS;
+        if (int rc = pm_pack_layout(texts + (size_t)l * HW, W, H, o, &hc)) { if (bad) *bad = l; return rc; }
+        any_caps |= hc;
+        int walls = 0;
+        for (int w = 0; w < NW; ++w) walls += __builtin_popcount(o[pm_l_walls(HW) + w]);
+        if (HW - walls > mo) mo = HW - walls;
+    }
+    if (has_caps) *has_caps = any_caps;
+    if (max_open) *max_open = mo;
+    return 0;
+}

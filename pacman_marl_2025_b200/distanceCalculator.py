@@ -61,8 +61,10 @@ def compute_distances(layouts: Sequence[_layout.Layout], device=None, nmax: int 
     W, H = layouts[0].width, layouts[0].height
     nl = len(layouts)
     if table is None:
-        _, packed, _ = pack_tables(layouts)
+        _, packed, _, max_open = pack_tables(layouts, with_max_open=True)
         table = torch.from_numpy(packed.view(np.int32)).to(dev)
+        if nmax is None:
+            nmax = max_open
     elif table.device != dev or table.dtype != torch.int32 or table.shape[0] != nl or not table.is_contiguous():
         raise ValueError("table must be the contiguous int32 [L, LS] device table of these layouts")
     if out is not None:

@@ -75,8 +75,10 @@ def decode_obs_bits(bits, H: int, W: int):
     return flat.reshape(*b.shape[:-1], 8, H, W)
 
 
-def pack_tables(layouts: Sequence[_layout.Layout]):
-    """Layout objects -> (geom[u32], table[L, LS] u32, has_caps) via the library's host packer."""
+def pack_tables(layouts: Sequence[_layout.Layout], with_max_open: bool = False):
+    """Layout objects -> (geom[u32], table[L, LS] u32, has_caps) via the library's host packer (one call for all L
+    boards).  ``with_max_open``: a fourth value, the largest open-cell count of any board (what pm_distances sizes its
+    tables with)."""
     L = _lib.load()
     W, H = layouts[0].width, layouts[0].height
     gw = L.pm_geom_words(W, H)
@@ -84,18 +86,22 @@ def pack_tables(layouts: Sequence[_layout.Layout]):
     geom = np.zeros(gw, np.uint32)
     _lib.check(L.pm_pack_geom(W, H, geom.ctypes.data), "pm_pack_geom")
     LS = L.pm_layout_words(W, H)
-    table = np.zeros((len(layouts), LS), np.uint32)
-    has_caps = 0
-    for i, lay in enumerate(layouts):
+    nl = len(layouts)
+    table = np.zeros((nl, LS), np.uint32)
+    parts = []
+    for lay in layouts:
         if (lay.width, lay.height) != (W, H):
             raise ValueError("all layouts of one batch must share the same width and height")
         text = "".join(lay.layoutText)
         if len(text) != W * H:
             raise ValueError("ragged layout text")
-        hc = C.c_int(0)
-        _lib.check(L.pm_pack_layout(text.encode("ascii"), W, H, table[i].ctypes.data, C.byref(hc)), "pm_pack_layout")
-        has_caps |= hc.value
-    return geom, table, has_caps
+        parts.append(text)
+    hc, mo, bad = C.c_int(0), C.c_int(0), C.c_int(-1)
+    rc = L.pm_pack_layouts("".join(parts).encode("ascii"), W, H, nl, table.ctypes.data, C.byref(hc), C.byref(mo), C.byref(bad))
+    _lib.check(rc, "pm_pack_layouts" + (f" (layout {bad.value})" if bad.value >= 0 else ""))
+    if with_max_open:
+        return geom, table, hc.value, mo.value
+    return geom, table, hc.value
 
 
 class OnDeviceAgent:

@@ -166,3 +166,30 @@ def test_layout_loader_matches_reference_fixture(name):
     for i in range(4):
         x, y = lay.starts[i]
         assert rows[H - 1 - y][x] == str(i + 1)
+
+
+def test_batched_layout_packer_equals_one_by_one_and_reports_the_bad_board():
+    """pm_pack_layouts (L boards per call, + the largest open-cell count) == pm_pack_layout per board; a malformed board is
+    reported with its index and the single-board error code."""
+    import ctypes as C
+    import numpy as np
+    from pacman_marl_2025_b200 import _lib, mazeGenerator
+    from pacman_marl_2025_b200.gymPacMan import pack_tables
+    from pacman_marl_2025_b200.layout import Layout
+    L = _lib.load()
+    lays = [Layout(mazeGenerator.generateMaze(300 + s).split("\n")) for s in range(9)]
+    W, H = lays[0].width, lays[0].height
+    geom, table, has_caps, max_open = pack_tables(lays, with_max_open=True)
+    LS = L.pm_layout_words(W, H)
+    for i, lay in enumerate(lays):
+        one = np.zeros(LS, np.uint32)
+        hc = C.c_int(0)
+        assert L.pm_pack_layout("".join(lay.layoutText).encode(), W, H, one.ctypes.data, C.byref(hc)) == 0
+        np.testing.assert_array_equal(table[i], one)
+    assert max_open == max(int((~l.walls.array).sum()) for l in lays) and has_caps == 1
+    texts = ["".join(l.layoutText) for l in lays]
+    texts[4] = texts[4].replace("1", " ", 1)                      # only three agents on board 4
+    out = np.zeros((9, LS), np.uint32)
+    bad = C.c_int(-1)
+    rc = L.pm_pack_layouts("".join(texts).encode(), W, H, 9, out.ctypes.data, None, None, C.byref(bad))
+    assert rc == -2 and bad.value == 4
