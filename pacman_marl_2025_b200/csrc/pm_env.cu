@@ -48,6 +48,9 @@
 #ifndef PM_E_RULES
 #define PM_E_RULES 64                             // envs per CTA of the launches bound by the rules phase (see launch_env)
 #endif
+#ifndef PM_E_CHAIN
+#define PM_E_CHAIN PM_E_RULES                     // envs per CTA of the plain step inside a pm_step_chain run (large batches)
+#endif
 #ifndef PM_E_BOTS
 #define PM_E_BOTS PM_E_RULES                      // envs per CTA of the launches with the baselineTeam look-ahead
 #endif
@@ -315,8 +318,8 @@ static int launch_env(const PmParams &P, cudaStream_t st) {
         // the launches of a chain overlap, so the wave structure of a single launch does not matter to them and the
         // larger tiles win (tinyCapture 65,536 envs: 175.3 -> 171.7 us per chained step; alone: 194 -> 219 us)
         if constexpr (MODE == PM_MODE_STEP && !VIEWS)
-            if (P.chain_flags != nullptr && (P.n_end - P.n_begin) >= (int64_t)4 * PM_E_RULES * pm_sm_count())
-                return launch_env_e<MODE, BOTS, VIEWS, PM_E_RULES>(P, st);
+            if (P.chain_flags != nullptr && (P.n_end - P.n_begin) >= (int64_t)4 * PM_E_CHAIN * pm_sm_count())
+                return launch_env_e<MODE, BOTS, VIEWS, PM_E_CHAIN>(P, st);
         return launch_env_e<MODE, BOTS, VIEWS, PM_E>(P, st);
     }
 }
