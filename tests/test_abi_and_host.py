@@ -193,3 +193,27 @@ def test_batched_layout_packer_equals_one_by_one_and_reports_the_bad_board():
     bad = C.c_int(-1)
     rc = L.pm_pack_layouts("".join(texts).encode(), W, H, 9, out.ctypes.data, None, None, C.byref(bad))
     assert rc == -2 and bad.value == 4
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs first, on the box's host cores; no GPU needed): one JSON line
+    with the same metric / unit / config keys as the GPU arm plus impl, cpu_baseline and a zero-copy e2e block."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--envs", "256", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert p.returncode == 0, p.stderr[-500:]
+    line = json.loads([ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "agent-steps/sec (env step+obs)" and line["unit"] == "agent-steps/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
+    assert line["config"]["layout"] == "tinyCapture" and line["config"]["envs_per_gpu"] == 256
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
+    assert line["e2e"] == {"value": line["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a second rank of a torchrun launch prints nothing and exits 0
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--envs", "256",
+                         "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert p2.returncode == 0 and not p2.stdout.strip()
